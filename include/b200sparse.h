@@ -1,0 +1,150 @@
+/*
+ * b200sparse.h -- C ABI of libb200sparse.so, the B200 (sm_100a) drop-in for the
+ * legate.sparse hot path: CSR SpMV, CSR x CSR SpGEMM and the CG inner loop.
+ *
+ * What this boundary replaces.  The reference has no plain C ABI for the path: its .so
+ * exports only `perform_registration()` and a projection-functor hook
+ * (src/sparse/sparse_c.h:138-143) and every op is a Legate task
+ * `static void X::gpu_variant(legate::TaskContext&)` looked up by opcode
+ * (src/sparse/sparse_c.h:25-110 enum, e.g. CSR_SPMV_ROW_SPLIT, AXPBY,
+ * SPGEMM_CSR_CSR_CSR_GPU) with stores fetched positionally
+ * (src/sparse/array/csr/spmv_template.inl:77-84).  Each entry point below names the
+ * task variant whose body it replaces; the Python side (legate/sparse_b200/*.py) plays
+ * the role of the reference's task builders in sparse/csr.py and sparse/linalg.py.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer owned by the caller unless the name ends in
+ *    `_host`; the library never frees caller memory and never synchronises the stream
+ *    unless the comment says "syncs";
+ *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *  - return value: B2S_OK (0) or an error code; b2s_last_error() returns a
+ *    thread-local message for the last failure (the reference aborts instead,
+ *    src/sparse/util/cuda_help.h:51-74);
+ *  - vt: value type 0=float32 1=float64; it: column-index width 0=int32 1=int64;
+ *    pt: indptr width 0=int32 1=int64  (reference: util/dispatch.h:23-74);
+ *  - CSR is scipy-style: indptr[nrows+1], indices[nnz], vals[nnz].  The reference's
+ *    Rect<1> `pos` {lo,hi} (sparse/csr.py:186-203) is indptr[i], indptr[i+1]-1.
+ */
+#ifndef B200SPARSE_H
+#define B200SPARSE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2S_OK            0
+#define B2S_EINVAL        1   /* bad argument (null pointer, negative size, unknown type code) */
+#define B2S_ECUDA         2   /* CUDA runtime error; message in b2s_last_error() */
+#define B2S_EUNSUPPORTED  3   /* valid request this build does not implement */
+#define B2S_ENOMEM        4   /* caller-provided buffer too small */
+
+#define B2S_F32 0
+#define B2S_F64 1
+#define B2S_I32 0
+#define B2S_I64 1
+
+/* ---- library / device ------------------------------------------------------------- */
+int         b2s_version(void);                 /* ABI version, currently 1 */
+const char* b2s_last_error(void);              /* thread-local, never NULL */
+/* out[0]=SM count, out[1]=L2 bytes, out[2]=cc major*10+minor, out[3]=max dyn smem/block.
+ * Replaces Runtime.num_gpus / cudalibs handle bring-up (sparse/runtime.py:57-96,
+ * src/sparse/cudalibs.cu:48-102). Host-side query; no stream. */
+int         b2s_device_info(int device, int64_t* out4_host);
+
+/* Size in bytes of the reduction workspace every *_dot / dot / nrm2 / cg_* call needs.
+ * The caller allocates it once per (device, stream), zero-fills it once, and passes it
+ * as `ws`; calls leave it zeroed again. */
+int64_t     b2s_ws_bytes(void);
+
+/* ---- CSR SpMV  (replaces CSRSpMVRowSplit::gpu_variant -> cusparseSpMV,
+ *                 src/sparse/array/csr/spmv.cu:24-123,181-184) ---------------------- */
+
+/* Tiled plan: the row-block / merge-path split of the (rows + nnz) work list into
+ * fixed-size tiles.  Stands in for the partitions the reference computes once per store
+ * and caches (sparse/partition.py:56-128 CompressedImagePartition,
+ * src/sparse/partition/fast_image_range.cu:27-54).
+ * b2s_spmv_plan_tiles: number of tiles T for this matrix/value type; the plan buffer
+ * holds (T+1) int32.  b2s_spmv_plan_build fills it (device, async). */
+int64_t     b2s_spmv_plan_tiles(int vt, int64_t nrows, int64_t nnz);
+int         b2s_spmv_plan_build(int vt, int pt, int64_t nrows, int64_t nnz,
+                                const void* indptr, int32_t* plan, void* stream);
+
+/* y = A x  (alpha=1, beta=0 as spmv.cu:79-80).  `plan` may be NULL: then a plan-free
+ * row-per-lane-group kernel is used (slower on short rows).  x has ncols entries,
+ * y has nrows entries; y must not alias x. */
+int         b2s_spmv_csr(int vt, int it, int pt, int64_t nrows, int64_t ncols, int64_t nnz,
+                         const void* indptr, const void* indices, const void* vals,
+                         const void* x, void* y, const int32_t* plan, void* stream);
+
+/* y = A x and *dot_out = sum_i w[i] * y[i] in one pass (CG: q = A p, pq = p.q;
+ * sparse/linalg.py:549-550 fused).  w has nrows entries (for a row shard it is the
+ * shard's slice of p).  dot_out: one value of type vt on the device.  Requires plan. */
+int         b2s_spmv_csr_dot(int vt, int it, int pt, int64_t nrows, int64_t ncols, int64_t nnz,
+                             const void* indptr, const void* indices, const void* vals,
+                             const void* x, void* y, const void* w, void* dot_out,
+                             const int32_t* plan, void* ws, void* stream);
+
+/* ---- CG vector kernels ---------------------------------------------------------------
+ * b2s_axpby replaces AXPBY::gpu_variant (src/sparse/linalg/axpby.cu:25-62):
+ *   val = a[0]/b[0]; negate -> -val; isalpha ? y = val*x + y : y = x + val*y
+ * a_dev/b_dev are 1-element device arrays (the reference passes futures, linalg.py:479-496). */
+int         b2s_axpby(int vt, int64_t n, void* y, const void* x, const void* a_dev,
+                      const void* b_dev, int isalpha, int negate, void* stream);
+/* r.dot(z), p.dot(q) and np.linalg.norm(r) (call sites sparse/linalg.py:540,550,561; the
+ * arithmetic is cuNumeric's in the reference).  fp64 accumulation, deterministic order,
+ * result (type vt) written to out_dev. */
+int         b2s_dot (int vt, int64_t n, const void* x, const void* y, void* out_dev, void* ws, void* stream);
+int         b2s_nrm2(int vt, int64_t n, const void* x, void* out_dev, void* ws, void* stream);
+/* Fused CG step (sparse/linalg.py:553-555 + the next iteration's r.dot(z) with M = I):
+ *   alpha = rho[0]/pq[0];  x += alpha p;  r -= alpha q;  *rr_out = r.r */
+int         b2s_cg_update_xr(int vt, int64_t n, void* x, void* r, const void* p, const void* q,
+                             const void* rho_dev, const void* pq_dev, void* rr_out_dev,
+                             void* ws, void* stream);
+
+/* ---- CSR x CSR -> CSR SpGEMM  (replaces SpGEMMCSRxCSRxCSRGPU::gpu_variant ->
+ *      cusparseSpGEMM_{workEstimation,compute,copy}, src/sparse/array/csr/
+ *      spgemm_csr_csr_csr.cu:33-272, and the NNZ/fill pair of the CPU branch,
+ *      spgemm_csr_csr_csr.cc:26-154).  C[m,n] = A[m,k] * B[k,n].  int32 column indices.
+ * Pass 1 (symbolic): c_indptr[m+1] (int64) = exclusive scan of per-row structural nnz.
+ *   info_host[0] = nnz(C), info_host[1] = number of A*B products ("flops/2"),
+ *   info_host[2] = rows whose nnz exceeds the largest shared-memory table (they need the
+ *   dense accumulator in pass 2; size it with b2s_spgemm_dense_bytes).  syncs the stream
+ *   (the reference also blocks here: sparse/csr.py:1442 `int(nnz)`).
+ * Pass 2 (numeric): fills c_indices (int32) / c_vals; rows come out SORTED by column
+ *   (canonical form; reference/scipy rows are unsorted, compare after sort_indices()).
+ *   Structural zeros from cancellation are kept, as in the reference.
+ * `scratch`: device buffer of b2s_spgemm_scratch_bytes(m, n) bytes shared by both passes.
+ * `dense_ws`: device buffer of b2s_spgemm_dense_bytes(vt, n, info_host[2]) bytes (may be
+ *   NULL when that is 0) -- the parallel form of the reference's per-thread `workspace` /
+ *   `already_set` arrays (spgemm_csr_csr_csr.cc:100-118, _omp.cc:92-167). */
+int64_t     b2s_spgemm_scratch_bytes(int64_t m, int64_t n);
+int64_t     b2s_spgemm_dense_bytes(int vt, int64_t n, int64_t dense_rows);
+int         b2s_spgemm_csr_symbolic(int pt, int64_t m, int64_t k, int64_t n,
+                                    const void* a_indptr, const int32_t* a_indices,
+                                    const void* b_indptr, const int32_t* b_indices,
+                                    int64_t* c_indptr, int64_t* info_host /*[3]*/,
+                                    void* scratch, void* stream);
+int         b2s_spgemm_csr_numeric(int vt, int pt, int64_t m, int64_t k, int64_t n,
+                                   const void* a_indptr, const int32_t* a_indices, const void* a_vals,
+                                   const void* b_indptr, const int32_t* b_indices, const void* b_vals,
+                                   const int64_t* c_indptr, int32_t* c_indices, void* c_vals,
+                                   void* scratch, void* dense_ws, int64_t dense_ws_bytes, void* stream);
+
+/* ---- multi-GPU plumbing: peer-visible x shards over NVLink (CUDA IPC) ----------------
+ * One process per GPU.  A rank exports the allocation holding its x shard, peers map it,
+ * and the window-exchange kernel pulls [lo,hi) pieces of remote shards straight over
+ * NVLink.  Replaces the implicit Legion/Realm halo copies driven by MinMaxImagePartition
+ * (sparse/partition.py:139-208).  Handles are 64 opaque bytes (cudaIpcMemHandle_t). */
+int         b2s_ipc_export(const void* dev_ptr, void* handle64_host);
+int         b2s_ipc_open(const void* handle64_host, void** dev_ptr_out);
+int         b2s_ipc_close(void* dev_ptr);
+/* dst[i] = src[i] for i in [0,n) elements of type vt where src is a (possibly peer) device
+ * pointer; 128-bit loads when both are 16-byte aligned. */
+int         b2s_copy(int vt, int64_t n, void* dst, const void* src, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200SPARSE_H */

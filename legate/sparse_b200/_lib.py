@@ -1,0 +1,89 @@
+"""ctypes binding of libb200sparse.so (the C ABI declared in include/b200sparse.h).
+
+Plays the part of the reference's cffi/opcode glue (sparse/config.py:21-152: Library subclass,
+`SparseOpCode` enum import) -- here there are no opcodes, just C functions.  There is NO CPU
+fallback: if the shared library cannot be loaded (or built) this module raises at import.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+from . import _build
+
+c_i32 = ctypes.c_int
+c_i64 = ctypes.c_int64
+c_vp = ctypes.c_void_p
+
+OK, EINVAL, ECUDA, EUNSUPPORTED, ENOMEM = 0, 1, 2, 3, 4
+F32, F64 = 0, 1
+I32, I64 = 0, 1
+
+# name -> (restype, argtypes); every symbol include/b200sparse.h declares
+SIGNATURES = {
+    "b2s_version": (c_i32, []),
+    "b2s_last_error": (ctypes.c_char_p, []),
+    "b2s_device_info": (c_i32, [c_i32, c_vp]),
+    "b2s_ws_bytes": (c_i64, []),
+    "b2s_spmv_plan_tiles": (c_i64, [c_i32, c_i64, c_i64]),
+    "b2s_spmv_plan_build": (c_i32, [c_i32, c_i32, c_i64, c_i64, c_vp, c_vp, c_vp]),
+    "b2s_spmv_csr": (c_i32, [c_i32, c_i32, c_i32, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "b2s_spmv_csr_dot": (c_i32, [c_i32, c_i32, c_i32, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp,
+                                 c_vp, c_vp, c_vp, c_vp]),
+    "b2s_axpby": (c_i32, [c_i32, c_i64, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_vp]),
+    "b2s_dot": (c_i32, [c_i32, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "b2s_nrm2": (c_i32, [c_i32, c_i64, c_vp, c_vp, c_vp, c_vp]),
+    "b2s_cg_update_xr": (c_i32, [c_i32, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "b2s_spgemm_scratch_bytes": (c_i64, [c_i64, c_i64]),
+    "b2s_spgemm_dense_bytes": (c_i64, [c_i32, c_i64, c_i64]),
+    "b2s_spgemm_csr_symbolic": (c_i32, [c_i32, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "b2s_spgemm_csr_numeric": (c_i32, [c_i32, c_i32, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp,
+                                       c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
+    "b2s_ipc_export": (c_i32, [c_vp, c_vp]),
+    "b2s_ipc_open": (c_i32, [c_vp, ctypes.POINTER(c_vp)]),
+    "b2s_ipc_close": (c_i32, [c_vp]),
+    "b2s_copy": (c_i32, [c_i32, c_i64, c_vp, c_vp, c_vp]),
+    # tuning hooks (not in the public header)
+    "b2s_spmv_set_config": (c_i32, [c_i32, c_i32]),
+    "b2s_spmv_get_config": (c_i32, []),
+}
+
+
+class B200SparseError(RuntimeError):
+    pass
+
+
+def _load() -> ctypes.CDLL:
+    path = _build.LIB_PATH
+    if not os.path.exists(path) or (_build.needs_build() and _build.shutil.which("nvcc")):
+        try:
+            _build.build()
+        except Exception as exc:  # pragma: no cover - environment dependent
+            if not os.path.exists(path):
+                raise ImportError(
+                    "legate.sparse_b200: libb200sparse.so is missing and could not be built "
+                    f"({exc}). There is no CPU fallback."
+                ) from exc
+    try:
+        lib = ctypes.CDLL(path)
+    except OSError as exc:
+        raise ImportError(f"legate.sparse_b200: cannot load {path}: {exc}. There is no CPU fallback.") from exc
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError here = ABI mismatch: fail loudly
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+lib = _load()
+LIB_PATH = _build.LIB_PATH
+
+
+def last_error() -> str:
+    return lib.b2s_last_error().decode("utf-8", "replace")
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != OK:
+        names = {EINVAL: "EINVAL", ECUDA: "ECUDA", EUNSUPPORTED: "EUNSUPPORTED", ENOMEM: "ENOMEM"}
+        raise B200SparseError(f"{what or 'libb200sparse'} failed [{names.get(rc, rc)}]: {last_error()}")

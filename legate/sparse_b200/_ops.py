@@ -1,0 +1,160 @@
+"""Leaf-op launchers: torch device tensors in, C-ABI calls out.
+
+This is the layer that corresponds to the reference's "task builders" (free functions
+`spmv` sparse/csr.py:863-968, `cg_axpby` sparse/linalg.py:479-496, `spgemm_csr_csr_csr`
+sparse/csr.py:1317-1490): they marshal stores into a task launch; here they marshal device
+pointers into libb200sparse.so.  Everything runs on the caller's current CUDA stream.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from . import _lib
+from .runtime import idx_code, ptr, runtime, vt_code
+
+L = _lib.lib
+
+
+def _stream():
+    return runtime.stream_ptr()
+
+
+def _chk_dev(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            runtime.require_cuda("legate.sparse_b200 kernel launch")
+            raise RuntimeError("operand is not a CUDA tensor; legate.sparse_b200 has no CPU fallback")
+
+
+# ---- SpMV -----------------------------------------------------------------------------------------
+def spmv_plan(indptr: torch.Tensor, nrows: int, nnz: int, vdtype) -> tuple[torch.Tensor, int]:
+    """Build the tile plan for a CSR structure. Returns (plan int32[T+1], config id)."""
+    _chk_dev(indptr)
+    vt = vt_code(vdtype)
+    ntiles = int(L.b2s_spmv_plan_tiles(vt, nrows, nnz))
+    plan = torch.empty(ntiles + 1, dtype=torch.int32, device=indptr.device)
+    _lib.check(L.b2s_spmv_plan_build(vt, idx_code(indptr.dtype), nrows, nnz, ptr(indptr), ptr(plan), _stream()),
+               "b2s_spmv_plan_build")
+    return plan, int(L.b2s_spmv_get_config())
+
+
+def spmv(indptr, indices, data, x, y, shape, plan=None):
+    """y = A @ x (replaces task CSR_SPMV_ROW_SPLIT, sparse/csr.py:928-968)."""
+    _chk_dev(indptr, indices, data, x, y)
+    nrows, ncols = shape
+    nnz = data.shape[0]
+    assert x.dtype == data.dtype == y.dtype and x.is_contiguous() and y.is_contiguous()
+    assert x.shape[0] == ncols and y.shape[0] == nrows
+    _lib.check(L.b2s_spmv_csr(vt_code(data.dtype), idx_code(indices.dtype), idx_code(indptr.dtype), nrows, ncols,
+                              nnz, ptr(indptr), ptr(indices), ptr(data), ptr(x), ptr(y), ptr(plan), _stream()),
+               "b2s_spmv_csr")
+    return y
+
+
+def spmv_dot(indptr, indices, data, x, y, w, out, shape, plan):
+    """y = A @ x and out[0] = w . y in one launch."""
+    _chk_dev(indptr, indices, data, x, y, w, out, plan)
+    nrows, ncols = shape
+    nnz = data.shape[0]
+    assert x.dtype == data.dtype == y.dtype == w.dtype == out.dtype
+    assert w.shape[0] == nrows and w.is_contiguous()
+    ws = runtime.workspace()
+    _lib.check(L.b2s_spmv_csr_dot(vt_code(data.dtype), idx_code(indices.dtype), idx_code(indptr.dtype), nrows,
+                                  ncols, nnz, ptr(indptr), ptr(indices), ptr(data), ptr(x), ptr(y), ptr(w),
+                                  ptr(out), ptr(plan), ptr(ws), _stream()), "b2s_spmv_csr_dot")
+    return y
+
+
+# ---- CG vector kernels --------------------------------------------------------------------------------
+def axpby(y, x, a, b, isalpha=True, negate=False):
+    _chk_dev(y, x, a, b)
+    assert y.dtype == x.dtype == a.dtype == b.dtype and y.shape == x.shape
+    assert y.is_contiguous() and x.is_contiguous()
+    _lib.check(L.b2s_axpby(vt_code(y.dtype), y.numel(), ptr(y), ptr(x), ptr(a), ptr(b), int(bool(isalpha)),
+                           int(bool(negate)), _stream()), "b2s_axpby")
+    return y
+
+
+def dot(x, y, out=None):
+    _chk_dev(x, y)
+    assert x.dtype == y.dtype and x.shape == y.shape and x.is_contiguous() and y.is_contiguous()
+    if out is None:
+        out = torch.empty(1, dtype=x.dtype, device=x.device)
+    _lib.check(L.b2s_dot(vt_code(x.dtype), x.numel(), ptr(x), ptr(y), ptr(out), ptr(runtime.workspace()), _stream()),
+               "b2s_dot")
+    return out
+
+
+def nrm2(x, out=None):
+    _chk_dev(x)
+    assert x.is_contiguous()
+    if out is None:
+        out = torch.empty(1, dtype=x.dtype, device=x.device)
+    _lib.check(L.b2s_nrm2(vt_code(x.dtype), x.numel(), ptr(x), ptr(out), ptr(runtime.workspace()), _stream()),
+               "b2s_nrm2")
+    return out
+
+
+def cg_update_xr(x, r, p, q, rho, pq, rr_out):
+    _chk_dev(x, r, p, q, rho, pq, rr_out)
+    assert x.dtype == r.dtype == p.dtype == q.dtype == rho.dtype == pq.dtype == rr_out.dtype
+    _lib.check(L.b2s_cg_update_xr(vt_code(x.dtype), x.numel(), ptr(x), ptr(r), ptr(p), ptr(q), ptr(rho), ptr(pq),
+                                  ptr(rr_out), ptr(runtime.workspace()), _stream()), "b2s_cg_update_xr")
+    return rr_out
+
+
+def copy(dst, src_ptr: int, n: int):
+    """dst[:n] = *(src_ptr) -- src may be a peer-mapped (IPC) pointer."""
+    _chk_dev(dst)
+    _lib.check(L.b2s_copy(vt_code(dst.dtype), n, ptr(dst), src_ptr, _stream()), "b2s_copy")
+    return dst
+
+
+# ---- SpGEMM --------------------------------------------------------------------------------------------
+def spgemm(a_indptr, a_indices, a_data, b_indptr, b_indices, b_data, shape_a, shape_b):
+    """C = A @ B (replaces SPGEMM_CSR_CSR_CSR_GPU + scan_local_results_and_scale_pos,
+    sparse/csr.py:1322-1389, 827-859). Returns (c_indptr int64, c_indices int32, c_data, info)."""
+    _chk_dev(a_indptr, a_indices, a_data, b_indptr, b_indices, b_data)
+    m, k = shape_a
+    k2, n = shape_b
+    assert k == k2
+    assert a_indices.dtype == torch.int32 and b_indices.dtype == torch.int32, "SpGEMM needs int32 column indices"
+    assert a_indptr.dtype == b_indptr.dtype and a_data.dtype == b_data.dtype
+    dev = a_data.device
+    pt = idx_code(a_indptr.dtype)
+    vt = vt_code(a_data.dtype)
+    st = _stream()
+    scratch = torch.empty(int(L.b2s_spgemm_scratch_bytes(m, n)), dtype=torch.uint8, device=dev)
+    c_indptr = torch.empty(m + 1, dtype=torch.int64, device=dev)
+    info = (_lib.c_i64 * 3)()
+    _lib.check(L.b2s_spgemm_csr_symbolic(pt, m, k, n, ptr(a_indptr), ptr(a_indices), ptr(b_indptr), ptr(b_indices),
+                                         ptr(c_indptr), info, ptr(scratch), st), "b2s_spgemm_csr_symbolic")
+    nnz, products, dense_rows = int(info[0]), int(info[1]), int(info[2])
+    c_indices = torch.empty(nnz, dtype=torch.int32, device=dev)
+    c_data = torch.empty(nnz, dtype=a_data.dtype, device=dev)
+    dense_bytes = int(L.b2s_spgemm_dense_bytes(vt, n, dense_rows))
+    dense = torch.empty(dense_bytes, dtype=torch.uint8, device=dev) if dense_bytes else None
+    _lib.check(L.b2s_spgemm_csr_numeric(vt, pt, m, k, n, ptr(a_indptr), ptr(a_indices), ptr(a_data), ptr(b_indptr),
+                                        ptr(b_indices), ptr(b_data), ptr(c_indptr), ptr(c_indices), ptr(c_data),
+                                        ptr(scratch), ptr(dense), dense_bytes, st), "b2s_spgemm_csr_numeric")
+    return c_indptr, c_indices, c_data, {"nnz": nnz, "products": products, "dense_rows": dense_rows}
+
+
+# ---- CUDA IPC ------------------------------------------------------------------------------------------
+def ipc_export(t: torch.Tensor) -> bytes:
+    _chk_dev(t)
+    buf = ctypes.create_string_buffer(64)
+    _lib.check(L.b2s_ipc_export(ptr(t), buf), "b2s_ipc_export")
+    return buf.raw
+
+
+def ipc_open(handle: bytes) -> int:
+    out = _lib.c_vp()
+    _lib.check(L.b2s_ipc_open(handle, ctypes.byref(out)), "b2s_ipc_open")
+    return int(out.value)
+
+
+def ipc_close(p: int) -> None:
+    _lib.check(L.b2s_ipc_close(p), "b2s_ipc_close")

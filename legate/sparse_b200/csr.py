@@ -1,0 +1,394 @@
+"""`csr_array` -- the scipy.sparse-compatible CSR matrix of the hot path.
+
+Mirrors the public surface of the reference class (sparse/csr.py:98-262 constructor forms,
+:304-322 astype/copy, :426-440 to_scipy_sparse_csr, :442-582 dot, :799 __matmul__), but the
+three Legate stores `pos`/`crd`/`vals` become three device tensors in plain scipy layout:
+
+    indptr  int32 (int64 when nnz >= 2^31)   -- reference: Rect<1> pos, 16 B/row
+    indices int32 (int64 when ncols >= 2^31) -- reference: int64 crd
+    data    float32 / float64
+
+so a 5-point Laplacian row costs 5*12 + 4 bytes instead of 5*16 + 16.  Dense vectors are either
+numpy arrays (host; copied to the device and back around the kernel) or torch CUDA tensors
+(device resident; the role cuNumeric ndarrays play in the reference).  Compute always happens in
+libb200sparse.so; there is no CPU path.
+"""
+from __future__ import annotations
+
+import os
+import warnings
+
+import numpy as np
+import scipy.sparse
+import torch
+
+from . import _ops
+from .runtime import (
+    SUPPORTED_VALUE_DTYPES,
+    is_device_array,
+    numpy_dtype,
+    runtime,
+    to_device,
+    to_host,
+    torch_dtype,
+)
+
+_INT32_MAX = 2**31 - 1
+
+
+def _force_wide() -> bool:
+    # testing knob: keep 64-bit indices/indptr (exercises the int64 kernel instantiations)
+    return os.environ.get("B2S_INDEX_WIDTH", "") == "64"
+
+
+def cast_to_common_type(*args):
+    """numpy.result_type promotion of the operands (reference sparse/utils.py:134-140)."""
+    dts = [numpy_dtype(a.dtype) for a in args]
+    common = np.result_type(*dts)
+    return tuple(a.astype(common, copy=False) if numpy_dtype(a.dtype) != common else a for a in args)
+
+
+def _dense_astype(x, dtype):
+    if isinstance(x, torch.Tensor):
+        return x.to(torch_dtype(dtype))
+    return x.astype(dtype, copy=False)
+
+
+class csr_array:
+    """CSR matrix resident on one B200 (or, with no GPU visible, on the host for format logic)."""
+
+    ndim = 2
+    format = "csr"
+
+    def __init__(self, arg, shape=None, dtype=None, copy=False):
+        from .module import is_sparse_matrix
+
+        self._plan = None
+        self._plan_key = None
+        if isinstance(arg, torch.Tensor) and arg.ndim == 2:
+            arg = to_host(arg)
+        if isinstance(arg, np.ndarray):
+            # dense -> CSR: nonzero test is `!= 0`, columns ascending
+            # (src/sparse/array/conv/dense_to_csr.cc:32-38,53-62)
+            assert arg.ndim == 2
+            shape = arg.shape
+            mask = arg != 0
+            counts = mask.sum(axis=1).astype(np.int64)
+            indptr = np.zeros(shape[0] + 1, dtype=np.int64)
+            np.cumsum(counts, out=indptr[1:])
+            rows, cols = np.nonzero(mask)
+            self._set_arrays(indptr, cols, arg[rows, cols])
+        elif isinstance(arg, (scipy.sparse.csr_array, scipy.sparse.csr_matrix)):
+            shape = arg.shape
+            self._set_arrays(arg.indptr, arg.indices, arg.data, copy=True)
+        elif isinstance(arg, tuple):
+            if copy:
+                raise NotImplementedError
+            if shape is None:
+                raise AssertionError("Cannot infer shape in this case.")
+            if len(arg) == 2:
+                # (data, (row, col)) goes through COO (reference csr.py:174-185)
+                from .coo import coo_array
+
+                data, (row, col) = arg
+                res = coo_array((data, (row, col)), shape=shape).tocsr()
+                self._indptr, self._indices, self._data = res._indptr, res._indices, res._data
+                shape = res.shape
+            elif len(arg) == 3:
+                data, indices, indptr = arg
+                assert indptr.shape[0] == shape[0] + 1
+                self._set_arrays(indptr, indices, data)
+            else:
+                raise AssertionError
+        elif is_sparse_matrix(arg):
+            csr = arg.tocsr()
+            if copy:
+                csr = csr.copy()
+            self._indptr, self._indices, self._data = csr._indptr, csr._indices, csr._data
+            shape = csr.shape
+        elif scipy.sparse.issparse(arg):
+            s = arg.tocsr()
+            shape = s.shape
+            self._set_arrays(s.indptr, s.indices, s.data, copy=True)
+        else:
+            raise NotImplementedError
+
+        assert shape is not None
+        self.shape = tuple(int(i) for i in shape)
+        assert self._indptr.shape[0] == self.shape[0] + 1
+        if dtype is not None and numpy_dtype(dtype) != numpy_dtype(self._data.dtype):
+            self._data = self._data.to(torch_dtype(dtype))
+        self.dtype = numpy_dtype(self._data.dtype)
+
+    # -- storage ------------------------------------------------------------------------------------
+    def _set_arrays(self, indptr, indices, data, copy=False):
+        nnz = int(data.shape[0])
+        wide = _force_wide()
+        ptr_dt = np.int64 if (wide or nnz > _INT32_MAX) else np.int32
+        self._indptr = to_device(indptr, dtype=ptr_dt, copy=copy)
+        if isinstance(indices, torch.Tensor):
+            idx_dt = np.int64 if wide else np.int32
+            if not wide and indices.numel() and int(indices.max()) > _INT32_MAX:
+                idx_dt = np.int64
+        else:
+            indices = np.asarray(indices)
+            idx_dt = np.int64 if (wide or (indices.size and int(indices.max()) > _INT32_MAX)) else np.int32
+        self._indices = to_device(indices, dtype=idx_dt, copy=copy)
+        self._data = to_device(data, copy=copy)
+
+    # reference exposes `.data` / `.indices` as device arrays (csr.py:264-287); `.indptr` is added
+    # because the layout here is plain scipy CSR.
+    @property
+    def data(self):
+        return self._data
+
+    @data.setter
+    def data(self, value):
+        self._data = to_device(value)
+        self.dtype = numpy_dtype(self._data.dtype)
+
+    @property
+    def indices(self):
+        return self._indices
+
+    @indices.setter
+    def indices(self, value):
+        self._indices = to_device(value)
+        self._plan = None
+
+    @property
+    def indptr(self):
+        return self._indptr
+
+    @property
+    def nnz(self) -> int:
+        return int(self._data.shape[0])
+
+    @property
+    def device(self):
+        return self._data.device
+
+    @classmethod
+    def _from_parts(cls, indptr, indices, data, shape):
+        obj = cls.__new__(cls)
+        obj._plan = None
+        obj._plan_key = None
+        obj._indptr, obj._indices, obj._data = indptr, indices, data
+        obj.shape = tuple(int(i) for i in shape)
+        obj.dtype = numpy_dtype(data.dtype)
+        return obj
+
+    @classmethod
+    def make_empty(cls, shape, dtype):
+        dev = runtime.device
+        return cls._from_parts(
+            torch.zeros(shape[0] + 1, dtype=torch.int32, device=dev),
+            torch.zeros(0, dtype=torch.int32, device=dev),
+            torch.zeros(0, dtype=torch_dtype(dtype), device=dev),
+            shape,
+        )
+
+    # -- conversions ----------------------------------------------------------------------------------
+    def astype(self, dtype, casting="unsafe", copy=True):
+        dtype = np.dtype(dtype)
+        if not copy and dtype == self.dtype:
+            return self
+        data = self._data.to(torch_dtype(dtype), copy=copy)
+        indptr = self._indptr.clone() if copy else self._indptr
+        indices = self._indices.clone() if copy else self._indices
+        return csr_array._from_parts(indptr, indices, data, self.shape)
+
+    def copy(self):
+        return csr_array._from_parts(self._indptr.clone(), self._indices.clone(), self._data.clone(), self.shape)
+
+    def conj(self, copy=True):
+        # real dtypes only: conj is the identity
+        return self.copy() if copy else self
+
+    def tocsr(self, copy=False):
+        return self.copy() if copy else self
+
+    def tocoo(self, copy=False):
+        from .coo import coo_array
+
+        counts = (self._indptr[1:] - self._indptr[:-1]).to(torch.int64)
+        rows = torch.repeat_interleave(
+            torch.arange(self.shape[0], dtype=torch.int64, device=self.device), counts
+        )
+        return coo_array((self._data.clone() if copy else self._data, (rows, self._indices)), shape=self.shape)
+
+    def to_scipy_sparse_csr(self):
+        return scipy.sparse.csr_array(
+            (to_host(self._data), to_host(self._indices), to_host(self._indptr)), shape=self.shape, dtype=self.dtype
+        )
+
+    def todense(self, order=None, out=None):
+        if order is not None:
+            raise NotImplementedError
+        res = self.to_scipy_sparse_csr().toarray()
+        if out is not None:
+            out[...] = res
+            return out
+        return res
+
+    toarray = todense
+
+    def transpose(self, copy=False):
+        # host-side (construction path only; reference does CSR.T via CSC aliasing, csc.py:317-324)
+        t = self.to_scipy_sparse_csr().T.tocsr()
+        return csr_array(t)
+
+    T = property(transpose)
+
+    def diagonal(self, k=0):
+        if k != 0:
+            raise NotImplementedError
+        return to_device(self.to_scipy_sparse_csr().diagonal())
+
+    # -- the hot path -----------------------------------------------------------------------------------
+    def _get_plan(self):
+        """Tile plan for the SpMV kernel, built once per structure and cached (the reference caches
+        its image partitions per store the same way, sparse/partition.py:96-120)."""
+        from . import _lib
+
+        key = (self._indptr.data_ptr(), int(_lib.lib.b2s_spmv_get_config()), self.dtype.itemsize)
+        if self._plan is None or self._plan_key != key:
+            self._plan, _ = _ops.spmv_plan(self._indptr, self.shape[0], self.nnz, self.dtype)
+            self._plan_key = key
+        return self._plan
+
+    def _promoted(self, common):
+        """A cast to the resolved dtype of (A, x) -- reference cast_to_common_type, csr.py:493 -- cached
+        so a mixed-dtype SpMV does not re-cast the matrix on every call."""
+        if self.dtype == common:
+            return self
+        cache = self.__dict__.setdefault("_promo_cache", {})
+        hit = cache.get(common)
+        if hit is None or hit[0] != self._data.data_ptr():
+            cache[common] = (self._data.data_ptr(), self.astype(common, copy=False))
+        return cache[common][1]
+
+    def dot(self, other, out=None, spmv_domain_part=False):
+        """`A.dot(x)` / `A @ B`; see reference sparse/csr.py:442-582.
+
+        * x 1-D or (n,1), numpy or torch CUDA tensor -> SpMV; result has x's array kind.
+        * other a csr_array -> SpGEMM (CSR x CSR -> CSR).
+        `spmv_domain_part` (column-split SpMV, csr.py:869-927) is accepted for signature
+        compatibility; a single GPU has no column split and the row-split kernel is used.
+        """
+        from .module import is_sparse_matrix
+
+        if isinstance(other, csr_array):
+            if out is not None:
+                raise ValueError("Cannot provide out for CSRxCSR matmul.")
+            assert self.shape[1] == other.shape[0]
+            return spgemm_csr_csr_csr(*cast_to_common_type(self, other))
+        if is_sparse_matrix(other) or scipy.sparse.issparse(other):
+            other = np.asarray(other.todense())
+            other_originally_sparse = True
+        else:
+            other_originally_sparse = False
+        if not isinstance(other, (np.ndarray, torch.Tensor)):
+            other = np.asarray(other)
+        if other.ndim == 1 or (other.ndim == 2 and other.shape[1] == 1):
+            runtime.require_cuda("csr_array.dot")
+            assert self.shape[1] == other.shape[0]
+            on_device = is_device_array(other) and other.is_cuda
+            other_originally_2d = other.ndim == 2
+            x = other.reshape(-1) if other_originally_2d else other
+            if isinstance(x, torch.Tensor) and not x.is_contiguous():
+                warnings.warn(
+                    "CSR SpMV creating an implicit copy due to transformed x vector.",
+                    category=RuntimeWarning,
+                    stacklevel=2,
+                )
+            xdt = numpy_dtype(x.dtype)
+            common = np.result_type(self.dtype, xdt)
+            if common not in SUPPORTED_VALUE_DTYPES:
+                raise NotImplementedError(
+                    f"SpMV for resolved dtype {common} is not implemented (float32/float64 kernels only)"
+                )
+            A = self._promoted(common)
+            xd = to_device(x, dtype=common)
+            if out is not None:
+                odt = numpy_dtype(out.dtype)
+                if odt != common:
+                    raise ValueError(f"Output type {odt} is not consistent with resolved dtype {common}")
+                if other_originally_2d:
+                    assert tuple(out.shape) == (self.shape[0], 1)
+                    assert not spmv_domain_part
+                else:
+                    assert tuple(out.shape) == (self.shape[0],)
+            direct = isinstance(out, torch.Tensor) and out.is_cuda and out.is_contiguous()
+            y = out.reshape(-1) if direct else torch.empty(self.shape[0], dtype=torch_dtype(common), device=A.device)
+            _ops.spmv(A._indptr, A._indices, A._data, xd, y, A.shape, plan=A._get_plan())
+            if out is None:
+                result = y if on_device else to_host(y)
+                if other_originally_2d:
+                    result = result.reshape(-1, 1)
+            else:
+                if not direct:
+                    if isinstance(out, torch.Tensor):
+                        out.reshape(-1).copy_(y)
+                    else:
+                        out.reshape(-1)[...] = to_host(y)
+                result = out
+            if other_originally_sparse:
+                return csr_array(np.asarray(to_host(result)).reshape(self.shape[0], -1))
+            return result
+        raise NotImplementedError("csr_array.dot: only vector (SpMV) and csr_array (SpGEMM) operands are implemented")
+
+    def matvec(self, other):
+        return self @ other
+
+    def __matmul__(self, other):
+        return self.dot(other)
+
+    def __rmatmul__(self, other):
+        raise NotImplementedError
+
+    def __mul__(self, other):
+        if np.isscalar(other):
+            return csr_array._from_parts(self._indptr, self._indices, self._data * other, self.shape)
+        raise NotImplementedError
+
+    __rmul__ = __mul__
+
+    def __neg__(self):
+        return self * -1
+
+    def balance(self):
+        """No-op on a single device; kept for API parity (reference base.py:198-282 re-tiles the rows by
+        nnz; the multi-GPU row plan lives in dist.py)."""
+        return None
+
+    def __repr__(self):
+        return (f"<{self.shape[0]}x{self.shape[1]} legate.sparse_b200 csr_array, {self.nnz} stored elements, "
+                f"dtype {self.dtype}, device {self.device}>")
+
+    def __str__(self):
+        return repr(self)
+
+
+csr_matrix = csr_array
+
+
+def spgemm_csr_csr_csr(A: csr_array, B: csr_array) -> csr_array:
+    """C = A @ B (reference builder sparse/csr.py:1317-1490). Rows of C are sorted by column."""
+    runtime.require_cuda("spgemm_csr_csr_csr")
+    if A.dtype not in SUPPORTED_VALUE_DTYPES:
+        raise NotImplementedError(f"SpGEMM for dtype {A.dtype} is not implemented")
+    a_idx, b_idx = A._indices, B._indices
+    if a_idx.dtype != torch.int32 or b_idx.dtype != torch.int32:
+        if max(A.shape[1], B.shape[1]) > _INT32_MAX:
+            raise NotImplementedError("SpGEMM needs column counts < 2^31")
+        a_idx, b_idx = a_idx.to(torch.int32), b_idx.to(torch.int32)
+    a_ptr, b_ptr = A._indptr, B._indptr
+    if a_ptr.dtype != b_ptr.dtype:
+        a_ptr, b_ptr = a_ptr.to(torch.int64), b_ptr.to(torch.int64)
+    c_ptr, c_idx, c_val, info = _ops.spgemm(a_ptr, a_idx, A._data, b_ptr, b_idx, B._data, A.shape, B.shape)
+    if info["nnz"] <= _INT32_MAX and not _force_wide():
+        c_ptr = c_ptr.to(torch.int32)
+    C = csr_array._from_parts(c_ptr, c_idx, c_val, (A.shape[0], B.shape[1]))
+    C.spgemm_info = info
+    return C

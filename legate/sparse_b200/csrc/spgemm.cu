@@ -1,0 +1,638 @@
+// spgemm.cu -- CSR x CSR -> CSR SpGEMM for sm_100a (two-pass, row-binned hash / dense accumulators).
+//
+// Replaces SpGEMMCSRxCSRxCSRGPU::gpu_variant (reference src/sparse/array/csr/spgemm_csr_csr_csr.cu:33-272:
+// int64->int32 casts + cusparseSpGEMM_{workEstimation,compute,copy}) and mirrors the two-phase structure of
+// the reference's CPU branch (spgemm_csr_csr_csr.cc:26-83 count, :85-154 fill; sparse/csr.py:1390-1490):
+//
+//   symbolic : products-per-row upper bound -> rows binned by size -> per-bin kernels count the distinct
+//              columns of each row (shared-memory hash sets; global two-level bitmaps for the largest rows)
+//              -> exclusive scan = c_indptr (int64).
+//   numeric  : rows re-binned by their exact nnz -> per-bin kernels accumulate (col,val) in shared-memory
+//              hash tables (global dense accumulator + bitmap for the largest rows, i.e. the reference's
+//              `workspace`/`already_set` pair) -> rows are emitted SORTED by column.
+//
+// Like the reference (and scipy) the structure is symbolic: cancellation zeros are kept.  Integer /
+// HBM-latency bound work: no tensor cores.  Within the warp-per-row bins the A-row is walked in order and
+// lanes cover one B-row at a time, so per-column accumulation order equals the reference's Gustavson order.
+#include "common.cuh"
+#include <limits.h>
+
+namespace b2s {
+
+constexpr int NCLS = 5;                 // 0: empty, 1: <=128 (warp), 2: <=1024 (CTA), 3: <=8192 (CTA), 4: larger
+constexpr int64_t CLS1_MAX = 128, CLS2_MAX = 1024, CLS3_MAX = 8192;
+constexpr int TBL1 = 256, TBL2 = 2048, TBL3 = 16384;
+constexpr int SCAN_BLOCK = 1024;        // elements per scan block (256 threads x 4)
+
+struct Header {                          // first 256 bytes of scratch (device)
+  unsigned long long counts[8];          // class histogram
+  unsigned long long cursors[8];         // class fill cursors
+  unsigned long long flops;              // number of A*B products
+  unsigned long long pad[15];
+};
+static_assert(sizeof(Header) == 256, "header layout");
+
+struct ScratchLayout {
+  int64_t off_ub, off_perm, off_blocksums, off_bitmaps, total;
+  int64_t bitmap_words0, bitmap_words1, bitmap_slot_bytes;
+  int nslots;
+};
+
+static inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+
+static ScratchLayout scratch_layout(int64_t m, int64_t n, int sm_count) {
+  ScratchLayout L;
+  int64_t o = 256;
+  L.off_ub = o;        o = align_up(o + 8 * (m > 0 ? m : 1), 256);
+  L.off_perm = o;      o = align_up(o + 4 * (m > 0 ? m : 1), 256);
+  L.off_blocksums = o; o = align_up(o + 8 * ((m + 1 + SCAN_BLOCK - 1) / SCAN_BLOCK + 1), 256);
+  L.bitmap_words0 = (n + 31) / 32;
+  L.bitmap_words1 = (L.bitmap_words0 + 31) / 32;
+  L.bitmap_slot_bytes = align_up(4 * (L.bitmap_words0 + L.bitmap_words1), 256);
+  L.nslots = 2 * sm_count;
+  L.off_bitmaps = o;   o += L.bitmap_slot_bytes * L.nslots;
+  L.total = o;
+  return L;
+}
+
+__host__ __device__ __forceinline__ int classify(long long v) {
+  return v == 0 ? 0 : (v <= CLS1_MAX ? 1 : (v <= CLS2_MAX ? 2 : (v <= CLS3_MAX ? 3 : 4)));
+}
+
+__device__ __forceinline__ unsigned hash_col(int32_t c, int bits) {
+  return ((unsigned)c * 2654435761u) >> (32 - bits);
+}
+
+// insert `col` into an open-addressing set/table (keys == -1 empty). Returns slot; *fresh = newly inserted.
+template <int TBL, int BITS>
+__device__ __forceinline__ int hash_insert(int32_t* keys, int32_t col, bool* fresh) {
+  unsigned slot = hash_col(col, BITS);
+  while (true) {
+    int32_t prev = atomicCAS(&keys[slot], -1, col);
+    if (prev == -1) { *fresh = true; return (int)slot; }
+    if (prev == col) { *fresh = false; return (int)slot; }
+    slot = (slot + 1) & (TBL - 1);
+  }
+}
+
+// ---- pass 0: products per row ---------------------------------------------------------------------------
+template <typename P>
+__global__ void __launch_bounds__(256)
+spgemm_ub_kernel(int64_t m, const P* __restrict__ a_ptr, const int32_t* __restrict__ a_idx,
+                 const P* __restrict__ b_ptr, long long* __restrict__ ub) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t i = warp; i < m; i += nwarps) {
+    const int64_t lo = (int64_t)a_ptr[i], hi = (int64_t)a_ptr[i + 1];
+    long long s = 0;
+    for (int64_t k = lo + lane; k < hi; k += 32) {
+      const int32_t kk = a_idx[k];
+      s += (long long)b_ptr[kk + 1] - (long long)b_ptr[kk];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) ub[i] = s;
+  }
+}
+
+// ---- binning: histogram + scatter (block-aggregated atomics) -----------------------------------------------
+// `size_of(i)` is ub[i] (symbolic) or c_indptr[i+1]-c_indptr[i] (numeric).
+template <bool FROM_INDPTR>
+__global__ void __launch_bounds__(256)
+bin_count_kernel(int64_t m, const long long* __restrict__ src, Header* hdr, int add_flops) {
+  __shared__ unsigned long long s_cnt[NCLS];
+  __shared__ unsigned long long s_flops;
+  if (threadIdx.x < NCLS) s_cnt[threadIdx.x] = 0;
+  if (threadIdx.x == 0) s_flops = 0;
+  __syncthreads();
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < m) {
+    const long long v = FROM_INDPTR ? (src[i + 1] - src[i]) : src[i];
+    atomicAdd(&s_cnt[classify(v)], 1ull);
+    if (add_flops && v) atomicAdd(&s_flops, (unsigned long long)v);
+  }
+  __syncthreads();
+  if (threadIdx.x < NCLS && s_cnt[threadIdx.x]) atomicAdd(&hdr->counts[threadIdx.x], s_cnt[threadIdx.x]);
+  if (threadIdx.x == 0 && add_flops && s_flops) atomicAdd(&hdr->flops, s_flops);
+}
+
+struct ClsOffsets { long long off[NCLS + 1]; };
+
+template <bool FROM_INDPTR>
+__global__ void __launch_bounds__(256)
+bin_scatter_kernel(int64_t m, const long long* __restrict__ src, Header* hdr, ClsOffsets offs,
+                   int32_t* __restrict__ perm) {
+  __shared__ unsigned int s_cnt[NCLS];
+  __shared__ unsigned long long s_base[NCLS];
+  if (threadIdx.x < NCLS) s_cnt[threadIdx.x] = 0;
+  __syncthreads();
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int c = -1;
+  unsigned int local = 0;
+  if (i < m) {
+    const long long v = FROM_INDPTR ? (src[i + 1] - src[i]) : src[i];
+    c = classify(v);
+    local = atomicAdd(&s_cnt[c], 1u);
+  }
+  __syncthreads();
+  if (threadIdx.x < NCLS && s_cnt[threadIdx.x])
+    s_base[threadIdx.x] = atomicAdd(&hdr->cursors[threadIdx.x], (unsigned long long)s_cnt[threadIdx.x]);
+  __syncthreads();
+  if (c >= 0) perm[offs.off[c] + (long long)s_base[c] + local] = (int32_t)i;
+}
+
+// ---- exclusive scan of int64 (3 kernels) --------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+scan_block_kernel(int64_t n, long long* __restrict__ data, long long* __restrict__ block_sums) {
+  __shared__ long long s_warp[8];
+  const int64_t base = (int64_t)blockIdx.x * SCAN_BLOCK + threadIdx.x * 4;
+  long long v[4];
+#pragma unroll
+  for (int q = 0; q < 4; q++) v[q] = (base + q < n) ? data[base + q] : 0;
+  long long tsum = v[0] + v[1] + v[2] + v[3];
+  // inclusive warp scan of thread sums
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  long long inc = tsum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    long long t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) s_warp[wid] = inc;
+  __syncthreads();
+  long long woff = 0;
+  for (int w = 0; w < wid; w++) woff += s_warp[w];
+  long long excl = woff + inc - tsum;
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    if (base + q < n) data[base + q] = excl;
+    excl += v[q];
+  }
+  if (threadIdx.x == 255) block_sums[blockIdx.x] = woff + inc;
+}
+
+__global__ void __launch_bounds__(1024)
+scan_sums_kernel(int64_t nblocks, long long* __restrict__ block_sums) {
+  // single block; serial over chunks of 1024 with a running carry; writes exclusive prefix and total at [nblocks]
+  __shared__ long long s_warp[32];
+  __shared__ long long s_carry;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int64_t base = 0; base < nblocks; base += 1024) {
+    const int64_t i = base + threadIdx.x;
+    long long v = (i < nblocks) ? block_sums[i] : 0;
+    long long inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      long long t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    if (lane == 31) s_warp[wid] = inc;
+    __syncthreads();
+    long long woff = 0;
+    for (int w = 0; w < wid; w++) woff += s_warp[w];
+    const long long carry = s_carry;
+    if (i < nblocks) block_sums[i] = carry + woff + inc - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) s_carry = carry + woff + inc;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) block_sums[nblocks] = s_carry;
+}
+
+__global__ void __launch_bounds__(256)
+scan_add_kernel(int64_t n, long long* __restrict__ data, const long long* __restrict__ block_sums) {
+  const int64_t base = (int64_t)blockIdx.x * SCAN_BLOCK + threadIdx.x * 4;
+  const long long add = block_sums[blockIdx.x];
+#pragma unroll
+  for (int q = 0; q < 4; q++)
+    if (base + q < n) data[base + q] += add;
+}
+
+// ---- bitonic sort of (key,val) pairs in shared memory ------------------------------------------------------
+template <typename V, typename SyncF>
+__device__ __forceinline__ void bitonic_sort_kv(int32_t* keys, V* vals, int n, int tid, int nthreads, SyncF sync) {
+  for (int k = 2; k <= n; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = tid; i < n; i += nthreads) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const bool up = ((i & k) == 0);
+          const int32_t a = keys[i], b = keys[ixj];
+          if ((a > b) == up) {
+            keys[i] = b; keys[ixj] = a;
+            const V va = vals[i]; vals[i] = vals[ixj]; vals[ixj] = va;
+          }
+        }
+      }
+      sync();
+    }
+  }
+}
+
+// ---- class 1: warp per row ---------------------------------------------------------------------------------
+// NUMERIC=false: count distinct columns -> row_nnz[row]; NUMERIC=true: accumulate, sort, write.
+template <typename V, typename P, bool NUMERIC>
+__global__ void __launch_bounds__(256)
+spgemm_warp_kernel(int64_t count, const int32_t* __restrict__ perm, const P* __restrict__ a_ptr,
+                   const int32_t* __restrict__ a_idx, const V* __restrict__ a_val, const P* __restrict__ b_ptr,
+                   const int32_t* __restrict__ b_idx, const V* __restrict__ b_val, long long* __restrict__ c_ptr,
+                   int32_t* __restrict__ c_idx, V* __restrict__ c_val) {
+  constexpr int WARPS = 8;
+  __shared__ int32_t s_keys[WARPS][TBL1];
+  __shared__ V s_vals[NUMERIC ? WARPS : 1][NUMERIC ? TBL1 : 1];
+  __shared__ int32_t s_ck[NUMERIC ? WARPS : 1][NUMERIC ? (int)CLS1_MAX : 1];
+  __shared__ V s_cv[NUMERIC ? WARPS : 1][NUMERIC ? (int)CLS1_MAX : 1];
+  __shared__ int s_n[WARPS];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int64_t gw = (int64_t)blockIdx.x * WARPS + wid;
+  const int64_t nw = (int64_t)gridDim.x * WARPS;
+  int32_t* keys = s_keys[wid];
+  for (int64_t it = gw; it < count; it += nw) {
+    const int32_t row = perm[it];
+    for (int i = lane; i < TBL1; i += 32) { keys[i] = -1; if (NUMERIC) s_vals[wid][i] = (V)0; }
+    if (lane == 0) s_n[wid] = 0;
+    __syncwarp();
+    int fresh_cnt = 0;
+    const int64_t alo = (int64_t)a_ptr[row], ahi = (int64_t)a_ptr[row + 1];
+    for (int64_t ka = alo; ka < ahi; ka++) {
+      const int32_t kk = a_idx[ka];
+      const int64_t blo = (int64_t)b_ptr[kk], bhi = (int64_t)b_ptr[kk + 1];
+      V av = (V)0;
+      if (NUMERIC) av = a_val[ka];
+      for (int64_t jb = blo + lane; jb < bhi; jb += 32) {
+        bool fresh;
+        const int slot = hash_insert<TBL1, 8>(keys, b_idx[jb], &fresh);
+        fresh_cnt += fresh ? 1 : 0;
+        if (NUMERIC) atomicAdd(&s_vals[wid][slot], av * b_val[jb]);
+      }
+      __syncwarp();  // order accumulation steps: per-column sums follow the A-row order
+    }
+    if (!NUMERIC) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) fresh_cnt += __shfl_xor_sync(0xffffffffu, fresh_cnt, o);
+      if (lane == 0) c_ptr[row] = fresh_cnt;
+    } else {
+      // compact -> sort pow2 >= n -> write
+      for (int i = lane; i < TBL1; i += 32) {
+        const int32_t k = keys[i];
+        if (k != -1) {
+          const int p = atomicAdd(&s_n[wid], 1);
+          s_ck[wid][p] = k; s_cv[wid][p] = s_vals[wid][i];
+        }
+      }
+      __syncwarp();
+      const int n = s_n[wid];
+      int np2 = 1;
+      while (np2 < n) np2 <<= 1;
+      for (int i = n + lane; i < np2; i += 32) { s_ck[wid][i] = INT_MAX; s_cv[wid][i] = (V)0; }
+      __syncwarp();
+      bitonic_sort_kv<V>(s_ck[wid], s_cv[wid], np2, lane, 32, [] { __syncwarp(); });
+      const long long base = c_ptr[row];
+      for (int i = lane; i < n; i += 32) { c_idx[base + i] = s_ck[wid][i]; c_val[base + i] = s_cv[wid][i]; }
+      __syncwarp();
+    }
+  }
+}
+
+// ---- classes 2/3: CTA per row, shared-memory hash table -------------------------------------------------------
+template <typename V, typename P, int TBL, int BITS, int THREADS, bool NUMERIC>
+__global__ void __launch_bounds__(THREADS)
+spgemm_cta_kernel(int64_t count, const int32_t* __restrict__ perm, const P* __restrict__ a_ptr,
+                  const int32_t* __restrict__ a_idx, const V* __restrict__ a_val, const P* __restrict__ b_ptr,
+                  const int32_t* __restrict__ b_idx, const V* __restrict__ b_val, long long* __restrict__ c_ptr,
+                  int32_t* __restrict__ c_idx, V* __restrict__ c_val) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  int32_t* keys = reinterpret_cast<int32_t*>(smem_raw);
+  V* vals = reinterpret_cast<V*>(smem_raw + sizeof(int32_t) * TBL);
+  __shared__ double red[32];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  constexpr int NWARPS = THREADS / 32;
+  for (int64_t it = blockIdx.x; it < count; it += gridDim.x) {
+    const int32_t row = perm[it];
+    __syncthreads();
+    for (int i = tid; i < TBL; i += THREADS) { keys[i] = -1; if (NUMERIC) vals[i] = (V)0; }
+    __syncthreads();
+    int fresh_cnt = 0;
+    const int64_t alo = (int64_t)a_ptr[row], ahi = (int64_t)a_ptr[row + 1];
+    for (int64_t ka = alo + wid; ka < ahi; ka += NWARPS) {
+      const int32_t kk = a_idx[ka];
+      const int64_t blo = (int64_t)b_ptr[kk], bhi = (int64_t)b_ptr[kk + 1];
+      V av = (V)0;
+      if (NUMERIC) av = a_val[ka];
+      for (int64_t jb = blo + lane; jb < bhi; jb += 32) {
+        bool fresh;
+        const int slot = hash_insert<TBL, BITS>(keys, b_idx[jb], &fresh);
+        fresh_cnt += fresh ? 1 : 0;
+        if (NUMERIC) atomicAdd(&vals[slot], av * b_val[jb]);
+      }
+    }
+    if (!NUMERIC) {
+      double tot = block_sum<THREADS>((double)fresh_cnt, red);
+      if (tid == 0) c_ptr[row] = (long long)(tot + 0.5);
+    } else {
+      __syncthreads();
+      for (int i = tid; i < TBL; i += THREADS) if (keys[i] == -1) keys[i] = INT_MAX;
+      __syncthreads();
+      bitonic_sort_kv<V>(keys, vals, TBL, tid, THREADS, [] { __syncthreads(); });
+      const long long base = c_ptr[row];
+      const int n = (int)(c_ptr[row + 1] - base);
+      for (int i = tid; i < n; i += THREADS) { c_idx[base + i] = keys[i]; c_val[base + i] = vals[i]; }
+    }
+  }
+}
+
+// ---- class 4: global two-level bitmap (+ dense value accumulator in the numeric pass) ----------------------------
+template <typename V, typename P, int THREADS, bool NUMERIC>
+__global__ void __launch_bounds__(THREADS)
+spgemm_dense_kernel(int64_t count, const int32_t* __restrict__ perm, const P* __restrict__ a_ptr,
+                    const int32_t* __restrict__ a_idx, const V* __restrict__ a_val, const P* __restrict__ b_ptr,
+                    const int32_t* __restrict__ b_idx, const V* __restrict__ b_val, long long* __restrict__ c_ptr,
+                    int32_t* __restrict__ c_idx, V* __restrict__ c_val, unsigned char* __restrict__ bitmaps,
+                    int64_t slot_bytes, int64_t words0, int64_t words1, V* __restrict__ dense, int64_t n) {
+  __shared__ double red[32];
+  __shared__ int s_scan[THREADS / 32];
+  __shared__ long long s_base;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  constexpr int NWARPS = THREADS / 32;
+  unsigned int* bm0 = reinterpret_cast<unsigned int*>(bitmaps + slot_bytes * blockIdx.x);
+  unsigned int* bm1 = bm0 + words0;
+  V* acc = NUMERIC ? dense + n * (int64_t)blockIdx.x : nullptr;
+  for (int64_t it = blockIdx.x; it < count; it += gridDim.x) {
+    const int32_t row = perm[it];
+    const int64_t alo = (int64_t)a_ptr[row], ahi = (int64_t)a_ptr[row + 1];
+    for (int64_t ka = alo + wid; ka < ahi; ka += NWARPS) {
+      const int32_t kk = a_idx[ka];
+      const int64_t blo = (int64_t)b_ptr[kk], bhi = (int64_t)b_ptr[kk + 1];
+      V av = (V)0;
+      if (NUMERIC) av = a_val[ka];
+      for (int64_t jb = blo + lane; jb < bhi; jb += 32) {
+        const int32_t j = b_idx[jb];
+        const unsigned int bit = 1u << (j & 31);
+        const unsigned int old = atomicOr(&bm0[j >> 5], bit);
+        if (old == 0) atomicOr(&bm1[j >> 10], 1u << ((j >> 5) & 31));
+        if (NUMERIC) atomicAdd(&acc[j], av * b_val[jb]);
+      }
+    }
+    __threadfence_block();
+    __syncthreads();
+    if (!NUMERIC) {
+      // count set bits, clearing as we go (only level-0 words flagged in level 1 are visited)
+      long long cnt = 0;
+      for (int64_t w1 = tid; w1 < words1; w1 += THREADS) {
+        unsigned int m1 = bm1[w1];
+        if (!m1) continue;
+        bm1[w1] = 0;
+        while (m1) {
+          const int b = __ffs(m1) - 1;
+          m1 &= m1 - 1;
+          const int64_t w0 = w1 * 32 + b;
+          cnt += __popc(bm0[w0]);
+          bm0[w0] = 0;
+        }
+      }
+      double tot = block_sum<THREADS>((double)cnt, red);
+      if (tid == 0) c_ptr[row] = (long long)(tot + 0.5);
+      __syncthreads();
+    } else {
+      // ordered emission: walk level-1 words in chunks of THREADS, block-scan the popcounts
+      if (tid == 0) s_base = c_ptr[row];
+      __syncthreads();
+      for (int64_t c0 = 0; c0 < words1; c0 += THREADS) {
+        const int64_t w1 = c0 + tid;
+        unsigned int m1 = (w1 < words1) ? bm1[w1] : 0u;
+        int mine = 0;
+        {
+          unsigned int t1 = m1;
+          while (t1) { const int b = __ffs(t1) - 1; t1 &= t1 - 1; mine += __popc(bm0[w1 * 32 + b]); }
+        }
+        // block exclusive scan of `mine`
+        int inc = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+        if (lane == 31) s_scan[wid] = inc;
+        __syncthreads();
+        int woff = 0, total = 0;
+        for (int w = 0; w < NWARPS; w++) { if (w < wid) woff += s_scan[w]; total += s_scan[w]; }
+        long long pos = s_base + woff + inc - mine;
+        if (m1) {
+          bm1[w1] = 0;
+          while (m1) {
+            const int b = __ffs(m1) - 1;
+            m1 &= m1 - 1;
+            const int64_t w0 = w1 * 32 + b;
+            unsigned int m0 = bm0[w0];
+            bm0[w0] = 0;
+            while (m0) {
+              const int bb = __ffs(m0) - 1;
+              m0 &= m0 - 1;
+              const int64_t j = w0 * 32 + bb;
+              c_idx[pos] = (int32_t)j;
+              c_val[pos] = acc[j];
+              acc[j] = (V)0;
+              pos++;
+            }
+          }
+        }
+        __syncthreads();
+        if (tid == 0) s_base += total;
+        __syncthreads();
+      }
+    }
+  }
+}
+
+// ---- host orchestration -----------------------------------------------------------------------------------------
+static int run_scan(long long* data, int64_t n, long long* block_sums, cudaStream_t st) {
+  const int64_t nblocks = (n + SCAN_BLOCK - 1) / SCAN_BLOCK;
+  scan_block_kernel<<<(unsigned)nblocks, 256, 0, st>>>(n, data, block_sums);
+  B2S_LAUNCH_CHECK();
+  scan_sums_kernel<<<1, 1024, 0, st>>>(nblocks, block_sums);
+  B2S_LAUNCH_CHECK();
+  scan_add_kernel<<<(unsigned)nblocks, 256, 0, st>>>(n, data, block_sums);
+  B2S_LAUNCH_CHECK();
+  return B2S_OK;
+}
+
+template <bool FROM_INDPTR>
+static int run_binning(int64_t m, const long long* src, Header* hdr, int32_t* perm, bool add_flops,
+                       unsigned long long counts_host[8], unsigned long long* flops_host, ClsOffsets* offs,
+                       cudaStream_t st) {
+  B2S_CUDA(cudaMemsetAsync(hdr, 0, sizeof(Header), st));
+  const unsigned grid = (unsigned)((m + 255) / 256);
+  bin_count_kernel<FROM_INDPTR><<<grid, 256, 0, st>>>(m, src, hdr, add_flops ? 1 : 0);
+  B2S_LAUNCH_CHECK();
+  Header h;
+  B2S_CUDA(cudaMemcpyAsync(&h, hdr, sizeof(Header), cudaMemcpyDeviceToHost, st));
+  B2S_CUDA(cudaStreamSynchronize(st));
+  long long o = 0;
+  for (int c = 0; c < NCLS; c++) { offs->off[c] = o; o += (long long)h.counts[c]; counts_host[c] = h.counts[c]; }
+  offs->off[NCLS] = o;
+  if (flops_host) *flops_host = h.flops;
+  bin_scatter_kernel<FROM_INDPTR><<<grid, 256, 0, st>>>(m, src, hdr, *offs, perm);
+  B2S_LAUNCH_CHECK();
+  return B2S_OK;
+}
+
+template <typename V, typename P, bool NUMERIC>
+static int run_classes(int sm_count, const unsigned long long counts[8], const ClsOffsets& offs, const int32_t* perm,
+                       const void* a_ptr, const int32_t* a_idx, const void* a_val, const void* b_ptr,
+                       const int32_t* b_idx, const void* b_val, long long* c_ptr, int32_t* c_idx, void* c_val,
+                       unsigned char* bitmaps, const ScratchLayout& L, void* dense, int64_t dense_slots, int64_t n,
+                       cudaStream_t st) {
+  const P* ap = (const P*)a_ptr; const P* bp = (const P*)b_ptr;
+  const V* av = (const V*)a_val; const V* bv = (const V*)b_val; V* cv = (V*)c_val;
+  if (counts[1]) {
+    int64_t want = ((int64_t)counts[1] + 7) / 8, cap = (int64_t)sm_count * 16;
+    unsigned grid = (unsigned)(want < cap ? want : cap);
+    spgemm_warp_kernel<V, P, NUMERIC><<<grid, 256, 0, st>>>((int64_t)counts[1], perm + offs.off[1], ap, a_idx, av, bp,
+                                                            b_idx, bv, c_ptr, c_idx, cv);
+    B2S_LAUNCH_CHECK();
+  }
+  if (counts[2]) {
+    auto kern = spgemm_cta_kernel<V, P, TBL2, 11, 128, NUMERIC>;
+    const size_t smem = sizeof(int32_t) * TBL2 + (NUMERIC ? sizeof(V) * TBL2 : 0);
+    int64_t cap = (int64_t)sm_count * 16;
+    unsigned grid = (unsigned)((int64_t)counts[2] < cap ? (int64_t)counts[2] : cap);
+    kern<<<grid, 128, smem, st>>>((int64_t)counts[2], perm + offs.off[2], ap, a_idx, av, bp, b_idx, bv, c_ptr, c_idx, cv);
+    B2S_LAUNCH_CHECK();
+  }
+  if (counts[3]) {
+    auto kern = spgemm_cta_kernel<V, P, TBL3, 14, 256, NUMERIC>;
+    const size_t smem = sizeof(int32_t) * TBL3 + (NUMERIC ? sizeof(V) * TBL3 : 0);
+    B2S_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int64_t cap = (int64_t)sm_count * (NUMERIC ? 2 : 6);
+    unsigned grid = (unsigned)((int64_t)counts[3] < cap ? (int64_t)counts[3] : cap);
+    kern<<<grid, 256, smem, st>>>((int64_t)counts[3], perm + offs.off[3], ap, a_idx, av, bp, b_idx, bv, c_ptr, c_idx, cv);
+    B2S_LAUNCH_CHECK();
+  }
+  if (counts[4]) {
+    int64_t slots = L.nslots;
+    if (NUMERIC && dense_slots < slots) slots = dense_slots;
+    if ((int64_t)counts[4] < slots) slots = (int64_t)counts[4];
+    if (slots < 1) { set_error("dense accumulator workspace too small"); return B2S_ENOMEM; }
+    spgemm_dense_kernel<V, P, 256, NUMERIC><<<(unsigned)slots, 256, 0, st>>>(
+        (int64_t)counts[4], perm + offs.off[4], ap, a_idx, av, bp, b_idx, bv, c_ptr, c_idx, cv, bitmaps,
+        L.bitmap_slot_bytes, L.bitmap_words0, L.bitmap_words1, (V*)dense, n);
+    B2S_LAUNCH_CHECK();
+  }
+  return B2S_OK;
+}
+
+}  // namespace b2s
+
+using namespace b2s;
+
+extern "C" {
+
+int64_t b2s_spgemm_scratch_bytes(int64_t m, int64_t n) {
+  if (m < 0 || n < 0) return 0;
+  DeviceProps pr;
+  if (get_props(&pr)) return 0;
+  return scratch_layout(m, n, pr.sm_count).total;
+}
+
+int64_t b2s_spgemm_dense_bytes(int vt, int64_t n, int64_t dense_rows) {
+  if (dense_rows <= 0 || n <= 0) return 0;
+  DeviceProps pr;
+  if (get_props(&pr)) return 0;
+  const int64_t per = n * (vt == B2S_F32 ? 4 : 8);
+  int64_t slots = 2 * pr.sm_count;
+  if (dense_rows < slots) slots = dense_rows;
+  const int64_t budget = 8LL << 30;  // at most 8 GiB of accumulators
+  if (slots * per > budget) slots = budget / per;
+  if (slots < 1) slots = 1;
+  return slots * per;
+}
+
+int b2s_spgemm_csr_symbolic(int pt, int64_t m, int64_t k, int64_t n, const void* a_indptr, const int32_t* a_indices,
+                            const void* b_indptr, const int32_t* b_indices, int64_t* c_indptr, int64_t* info_host,
+                            void* scratch, void* stream) {
+  B2S_CHECK_ARG(pt == B2S_I32 || pt == B2S_I64, "bad indptr type code %d", pt);
+  B2S_CHECK_ARG(m >= 0 && k >= 0 && n >= 0, "negative dimension");
+  B2S_CHECK_ARG(m < 2147483647LL && n < 2147483647LL && k < 2147483647LL, "dimensions >= 2^31-1 unsupported");
+  B2S_CHECK_ARG(a_indptr && b_indptr && c_indptr && info_host && scratch, "NULL pointer argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  DeviceProps pr;
+  if (int rc = get_props(&pr)) return rc;
+  const ScratchLayout L = scratch_layout(m, n, pr.sm_count);
+  unsigned char* sc = (unsigned char*)scratch;
+  Header* hdr = (Header*)sc;
+  long long* ub = (long long*)(sc + L.off_ub);
+  int32_t* perm = (int32_t*)(sc + L.off_perm);
+  long long* bsums = (long long*)(sc + L.off_blocksums);
+  unsigned char* bitmaps = sc + L.off_bitmaps;
+  info_host[0] = info_host[1] = info_host[2] = 0;
+  B2S_CUDA(cudaMemsetAsync(c_indptr, 0, sizeof(int64_t) * (size_t)(m + 1), st));
+  if (m == 0) { B2S_CUDA(cudaStreamSynchronize(st)); return B2S_OK; }
+  {
+    int64_t want = (m * 32 + 255) / 256, cap = (int64_t)pr.sm_count * 32;
+    unsigned grid = (unsigned)(want < cap ? want : cap);
+    if (pt == B2S_I32) spgemm_ub_kernel<int32_t><<<grid, 256, 0, st>>>(m, (const int32_t*)a_indptr, a_indices, (const int32_t*)b_indptr, ub);
+    else               spgemm_ub_kernel<int64_t><<<grid, 256, 0, st>>>(m, (const int64_t*)a_indptr, a_indices, (const int64_t*)b_indptr, ub);
+    B2S_LAUNCH_CHECK();
+  }
+  unsigned long long counts[8] = {0};
+  unsigned long long flops = 0;
+  ClsOffsets offs;
+  if (int rc = run_binning<false>(m, ub, hdr, perm, true, counts, &flops, &offs, st)) return rc;
+  if (counts[4]) B2S_CUDA(cudaMemsetAsync(bitmaps, 0, (size_t)(L.bitmap_slot_bytes * L.nslots), st));
+  int rc;
+  long long* cp = (long long*)c_indptr;
+  if (pt == B2S_I32) rc = run_classes<float, int32_t, false>(pr.sm_count, counts, offs, perm, a_indptr, a_indices, nullptr, b_indptr, b_indices, nullptr, cp, nullptr, nullptr, bitmaps, L, nullptr, 0, n, st);
+  else               rc = run_classes<float, int64_t, false>(pr.sm_count, counts, offs, perm, a_indptr, a_indices, nullptr, b_indptr, b_indices, nullptr, cp, nullptr, nullptr, bitmaps, L, nullptr, 0, n, st);
+  if (rc) return rc;
+  if (int rc2 = run_scan(cp, m + 1, bsums, st)) return rc2;
+  long long nnz = 0;
+  B2S_CUDA(cudaMemcpyAsync(&nnz, cp + m, sizeof(long long), cudaMemcpyDeviceToHost, st));
+  // rows whose exact nnz exceeds the largest shared-memory table need the dense accumulator in pass 2
+  unsigned long long counts2[8] = {0};
+  ClsOffsets offs2;
+  if (int rc3 = run_binning<true>(m, cp, hdr, perm, false, counts2, nullptr, &offs2, st)) return rc3;
+  B2S_CUDA(cudaStreamSynchronize(st));
+  info_host[0] = nnz;
+  info_host[1] = (int64_t)flops;
+  info_host[2] = (int64_t)counts2[4];
+  return B2S_OK;
+}
+
+int b2s_spgemm_csr_numeric(int vt, int pt, int64_t m, int64_t k, int64_t n, const void* a_indptr,
+                           const int32_t* a_indices, const void* a_vals, const void* b_indptr,
+                           const int32_t* b_indices, const void* b_vals, const int64_t* c_indptr, int32_t* c_indices,
+                           void* c_vals, void* scratch, void* dense_ws, int64_t dense_ws_bytes, void* stream) {
+  B2S_CHECK_ARG(vt == B2S_F32 || vt == B2S_F64, "bad value type code %d", vt);
+  B2S_CHECK_ARG(pt == B2S_I32 || pt == B2S_I64, "bad indptr type code %d", pt);
+  B2S_CHECK_ARG(m >= 0 && k >= 0 && n >= 0, "negative dimension");
+  B2S_CHECK_ARG(a_indptr && b_indptr && c_indptr && scratch, "NULL pointer argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (m == 0) return B2S_OK;
+  DeviceProps pr;
+  if (int rc = get_props(&pr)) return rc;
+  const ScratchLayout L = scratch_layout(m, n, pr.sm_count);
+  unsigned char* sc = (unsigned char*)scratch;
+  Header* hdr = (Header*)sc;
+  int32_t* perm = (int32_t*)(sc + L.off_perm);
+  unsigned char* bitmaps = sc + L.off_bitmaps;
+  unsigned long long counts[8] = {0};
+  ClsOffsets offs;
+  if (int rc = run_binning<true>(m, (const long long*)c_indptr, hdr, perm, false, counts, nullptr, &offs, st)) return rc;
+  int64_t dense_slots = 0;
+  if (counts[4]) {
+    const int64_t per = n * (vt == B2S_F32 ? 4 : 8);
+    dense_slots = per > 0 ? dense_ws_bytes / per : 0;
+    B2S_CHECK_ARG(dense_ws != nullptr && dense_slots >= 1, "numeric pass needs a dense accumulator workspace of >= %lld bytes", (long long)per);
+    B2S_CUDA(cudaMemsetAsync(bitmaps, 0, (size_t)(L.bitmap_slot_bytes * L.nslots), st));
+    B2S_CUDA(cudaMemsetAsync(dense_ws, 0, (size_t)(dense_slots * per), st));
+  }
+  long long* cp = (long long*)const_cast<int64_t*>(c_indptr);
+  if (vt == B2S_F32) {
+    if (pt == B2S_I32) return run_classes<float, int32_t, true>(pr.sm_count, counts, offs, perm, a_indptr, a_indices, a_vals, b_indptr, b_indices, b_vals, cp, c_indices, c_vals, bitmaps, L, dense_ws, dense_slots, n, st);
+    return run_classes<float, int64_t, true>(pr.sm_count, counts, offs, perm, a_indptr, a_indices, a_vals, b_indptr, b_indices, b_vals, cp, c_indices, c_vals, bitmaps, L, dense_ws, dense_slots, n, st);
+  }
+  if (pt == B2S_I32) return run_classes<double, int32_t, true>(pr.sm_count, counts, offs, perm, a_indptr, a_indices, a_vals, b_indptr, b_indices, b_vals, cp, c_indices, c_vals, bitmaps, L, dense_ws, dense_slots, n, st);
+  return run_classes<double, int64_t, true>(pr.sm_count, counts, offs, perm, a_indptr, a_indices, a_vals, b_indptr, b_indices, b_vals, cp, c_indices, c_vals, bitmaps, L, dense_ws, dense_slots, n, st);
+}
+
+}  // extern "C"

@@ -1,0 +1,305 @@
+"""`linalg`: LinearOperator family, `cg_axpby` and the conjugate-gradient solver.
+
+Public surface and semantics follow the reference (sparse/linalg.py:128-352 LinearOperator,
+:357-414 _CustomLinearOperator, :420-432 _SparseMatrixLinearOperator, :437-459 IdentityOperator,
+:462-466 make_linear_operator, :479-496 cg_axpby, :499-565 cg):
+
+* `tol` is an ABSOLUTE threshold on ||r||_2, tested only every `conv_test_iters` iterations
+  (and at `maxiter-1`), `atol` must be None, default `maxiter = 10 n`, returns `(x, iters)`.
+* the scalars rho, rho1, pq never visit the host: they live in 1-element device arrays and the
+  divisions rho/pq, rho/rho1 happen inside the kernels (reference: Legion futures + AXPBY task).
+
+Two code paths produce the same iterates:
+  - generic : any LinearOperator A / preconditioner M, one kernel per reference op;
+  - fused   : A is a `csr_array`, M is None -> 3 launches per iteration
+              (SpMV+p.q | x,r update + r.r | p update) instead of 7, and the Identity copy z = r
+              (2 vector passes) disappears.  Selected automatically; `B2S_CG_FUSED=0` disables it.
+"""
+from __future__ import annotations
+
+import inspect
+import os
+import warnings
+
+import numpy as np
+import torch
+
+from . import _ops
+from .csr import csr_array
+from .runtime import is_device_array, numpy_dtype, runtime, to_device, to_host, torch_dtype
+
+
+def _zeros(n, dtype=np.float64):
+    return torch.zeros(n, dtype=torch_dtype(dtype), device=runtime.device)
+
+
+class LinearOperator:
+    """Common interface for matrix-vector products (scipy.sparse.linalg.LinearOperator subset).
+
+    Subclasses implement `_matvec(x, out=None)`; `LinearOperator(shape, matvec=...)` builds a
+    `_CustomLinearOperator`.  Vectors are device tensors inside the solvers.
+    """
+
+    ndim = 2
+
+    def __new__(cls, *args, **kwargs):
+        if cls is LinearOperator:
+            return super().__new__(_CustomLinearOperator)
+        obj = super().__new__(cls)
+        if type(obj)._matvec == LinearOperator._matvec:
+            warnings.warn(
+                "LinearOperator subclass should implement at least one of _matvec and _matmat.",
+                category=RuntimeWarning,
+                stacklevel=2,
+            )
+        return obj
+
+    def __init__(self, dtype, shape):
+        if dtype is not None:
+            dtype = np.dtype(dtype)
+        self.dtype = dtype
+        self.shape = tuple(shape)
+
+    def _init_dtype(self):
+        if self.dtype is None:
+            v = _zeros(self.shape[-1])
+            self.dtype = numpy_dtype(self.matvec(v).dtype)
+
+    def _matvec(self, x, out=None):
+        raise NotImplementedError
+
+    def matvec(self, x, out=None):
+        M, N = self.shape
+        if tuple(x.shape) != (N,) and tuple(x.shape) != (N, 1):
+            raise ValueError("dimension mismatch")
+        y = self._matvec(x, out=out)
+        if x.ndim == 1:
+            y = y.reshape(M)
+        elif x.ndim == 2:
+            y = y.reshape(M, 1)
+        else:
+            raise ValueError("invalid shape returned by user-defined matvec()")
+        return y
+
+    def _rmatvec(self, x, out=None):
+        raise NotImplementedError
+
+    def rmatvec(self, x, out=None):
+        M, N = self.shape
+        if tuple(x.shape) != (M,) and tuple(x.shape) != (M, 1):
+            raise ValueError("dimension mismatch")
+        y = self._rmatvec(x, out=out)
+        return y.reshape(N) if x.ndim == 1 else y.reshape(N, 1)
+
+    def __matmul__(self, x):
+        return self.matvec(x)
+
+    def __repr__(self):
+        M, N = self.shape
+        dt = "unspecified dtype" if self.dtype is None else f"dtype={self.dtype}"
+        return f"<{M}x{N} {self.__class__.__name__} with {dt}>"
+
+
+class _CustomLinearOperator(LinearOperator):
+    """Linear operator defined in terms of user-specified callables."""
+
+    def __init__(self, shape, matvec, rmatvec=None, matmat=None, dtype=None, rmatmat=None):
+        super().__init__(dtype, shape)
+        self.args = ()
+        self.__matvec_impl = matvec
+        self.__rmatvec_impl = rmatvec
+        # does the user's callable take an out= parameter? (reference linalg.py:407-414)
+        self._matvec_has_out = self._has_out(matvec)
+        self._rmatvec_has_out = self._has_out(rmatvec)
+        self._init_dtype()
+
+    def _matvec(self, x, out=None):
+        if self._matvec_has_out:
+            return self.__matvec_impl(x, out=out)
+        if out is None:
+            return self.__matvec_impl(x)
+        out[:] = self.__matvec_impl(x)
+        return out
+
+    def _rmatvec(self, x, out=None):
+        func = self.__rmatvec_impl
+        if func is None:
+            raise NotImplementedError("rmatvec is not defined")
+        if self._rmatvec_has_out:
+            return func(x, out=out)
+        if out is None:
+            return func(x)
+        out[:] = func(x)
+        return out
+
+    @staticmethod
+    def _has_out(o):
+        if o is None:
+            return False
+        return "out" in inspect.signature(o).parameters
+
+
+class _SparseMatrixLinearOperator(LinearOperator):
+    def __init__(self, A):
+        self.A = A
+        self.AH = None
+        super().__init__(A.dtype, A.shape)
+
+    def _matvec(self, x, out=None):
+        return self.A.dot(x, out=out)
+
+    def _rmatvec(self, x, out=None):
+        if self.AH is None:
+            self.AH = self.A.T.conj(copy=False)
+        return self.AH.dot(x, out=out)
+
+
+class IdentityOperator(LinearOperator):
+    def __init__(self, shape, dtype=None):
+        super().__init__(dtype, shape)
+
+    def _matvec(self, x, out=None):
+        if out is not None:
+            out[:] = x
+            return out
+        # copy so callers never alias their input (reference linalg.py:446-449)
+        return x.clone() if isinstance(x, torch.Tensor) else x.copy()
+
+    _rmatvec = _matvec
+
+
+def make_linear_operator(A):
+    if isinstance(A, LinearOperator):
+        return A
+    return _SparseMatrixLinearOperator(A)
+
+
+def cg_axpby(y, x, a, b, isalpha=True, negate=False):
+    """y = alpha*x + y (isalpha) or y = x + beta*y, with alpha|beta = a/b (negated if `negate`).
+
+    a, b are 1-element device arrays; the division happens on the device
+    (reference sparse/linalg.py:479-496 -> AXPBY task, src/sparse/linalg/axpby.cu:25-43).
+    """
+    return _ops.axpby(y, x, a, b, isalpha=isalpha, negate=negate)
+
+
+def _as_scalar_array(v, dtype):
+    if isinstance(v, torch.Tensor):
+        return v.reshape(1).to(torch_dtype(dtype))
+    return torch.full((1,), float(v), dtype=torch_dtype(dtype), device=runtime.device)
+
+
+def _use_fused(A, M) -> bool:
+    return isinstance(A, csr_array) and M is None and os.environ.get("B2S_CG_FUSED", "1") != "0"
+
+
+def cg(A, b, x0=None, tol=1e-08, maxiter=None, M=None, callback=None, atol=None, conv_test_iters=25):
+    """Conjugate gradient, reference semantics (sparse/linalg.py:499-565). Returns (x, iters).
+
+    b / x0 may be numpy arrays (then x is returned as numpy) or CUDA tensors (x returned on device).
+    """
+    assert len(b.shape) == 1 or (len(b.shape) == 2 and b.shape[1] == 1)
+    assert len(A.shape) == 2 and A.shape[0] == A.shape[1]
+    assert atol is None, "atol is not supported."
+    runtime.require_cuda("linalg.cg")
+
+    n = b.shape[0]
+    if maxiter is None:
+        maxiter = n * 10
+    on_device = is_device_array(b) and b.is_cuda
+    # the reference allocates x, p with np.zeros(n) -> float64 (linalg.py:526-527)
+    work_dtype = np.float64 if x0 is None else numpy_dtype(x0.dtype)
+    if work_dtype not in (np.dtype(np.float32), np.dtype(np.float64)):
+        work_dtype = np.float64
+    bd = to_device(b, dtype=np.result_type(work_dtype, numpy_dtype(b.dtype))).reshape(-1)
+    work_dtype = numpy_dtype(bd.dtype)
+    x = _zeros(n, work_dtype) if x0 is None else to_device(x0, dtype=work_dtype, copy=True).reshape(-1)
+
+    if _use_fused(A, M):
+        x, iters = _cg_fused(A, bd, x, tol, maxiter, callback, conv_test_iters, on_device)
+    else:
+        x, iters = _cg_generic(A, bd, x, tol, maxiter, M, callback, conv_test_iters, on_device)
+    return (x if on_device else to_host(x)), iters
+
+
+def _cg_generic(A, b, x, tol, maxiter, M, callback, conv_test_iters, on_device):
+    """Op-for-op the reference loop: copy z=M r, dot, axpby, SpMV, dot, axpby, axpby (+ norm/25)."""
+    n = b.shape[0]
+    dt = numpy_dtype(b.dtype)
+    A = make_linear_operator(A)
+    M = IdentityOperator(A.shape, dtype=A.dtype) if M is None else make_linear_operator(M)
+    p = _zeros(n, dt)
+    r = b - A.matvec(x)
+    iters = 0
+    rho = _as_scalar_array(0.0, dt)
+    z = None
+    q = None
+    while iters < maxiter:
+        z = M.matvec(r, out=z)
+        rho1 = rho
+        rho = _ops.dot(r, z)
+        if iters == 0:
+            p[:] = z
+        else:
+            cg_axpby(p, z, rho, rho1, isalpha=False, negate=False)
+        q = A.matvec(p, out=q)
+        pq = _ops.dot(p, q)
+        cg_axpby(x, p, rho, pq, isalpha=True, negate=False)
+        cg_axpby(r, q, rho, pq, isalpha=True, negate=True)
+        iters += 1
+        if callback is not None:
+            callback(x if on_device else to_host(x))
+        if (iters % conv_test_iters == 0 or iters == (maxiter - 1)) and float(_ops.nrm2(r)[0]) < tol:
+            break
+    return x, iters
+
+
+def _cg_fused(A: csr_array, b, x, tol, maxiter, callback, conv_test_iters, on_device):
+    """Same recurrence, 3 launches per iteration.
+
+    With M = I: z = r, rho = r.r.  Per iteration
+        q = A p ; pq = p.q                    (b2s_spmv_csr_dot)
+        x += (rho/pq) p ; r -= (rho/pq) q ; rho_next = r.r   (b2s_cg_update_xr)
+        p = r + (rho_next/rho) p              (b2s_axpby, isalpha=False)   [next iteration's first op]
+    ||r|| for the convergence test is sqrt(rho_next) -- no extra pass.
+    """
+    n = b.shape[0]
+    dt = numpy_dtype(b.dtype)
+    Ad = A._promoted(dt) if A.dtype != dt else A
+    if numpy_dtype(Ad.dtype) != dt:
+        raise NotImplementedError("cg: matrix dtype wider than the work vectors")
+    plan = Ad._get_plan()
+    shape = Ad.shape
+    q = torch.empty(n, dtype=b.dtype, device=b.device)
+    # r = b - A x
+    _ops.spmv(Ad._indptr, Ad._indices, Ad._data, x, q, shape, plan=plan)
+    r = b - q
+    p = torch.empty_like(r)
+    rho = _ops.dot(r, r)
+    rho_next = torch.empty_like(rho)
+    pq = torch.empty_like(rho)
+    iters = 0
+    while iters < maxiter:
+        if iters == 0:
+            p.copy_(r)
+        else:
+            # p = r + (rho/rho1) p with rho1 the previous rho
+            cg_axpby(p, r, rho_next, rho, isalpha=False, negate=False)
+            rho, rho_next = rho_next, rho
+        _ops.spmv_dot(Ad._indptr, Ad._indices, Ad._data, p, q, p, pq, shape, plan)
+        _ops.cg_update_xr(x, r, p, q, rho, pq, rho_next)
+        iters += 1
+        if callback is not None:
+            callback(x if on_device else to_host(x))
+        if (iters % conv_test_iters == 0 or iters == (maxiter - 1)) and float(rho_next[0]) ** 0.5 < tol:
+            break
+    return x, iters
+
+
+__all__ = [
+    "LinearOperator",
+    "IdentityOperator",
+    "make_linear_operator",
+    "cg_axpby",
+    "cg",
+]

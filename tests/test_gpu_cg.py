@@ -1,0 +1,135 @@
+"""GPU tests for linalg.cg -- mirrors reference tests/integration/test_cg_solve.py:23-106 (plain,
+callback, identity preconditioner, LinearOperator with/without out=) and checks the fused and generic
+device loops against the CPU oracle's restatement of sparse/linalg.py:499-565 (same iteration count,
+solution within 1e-6 relative) and the golden scipy solutions."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from conftest import sample_spd
+
+import legate.sparse_b200 as sparse
+from legate.sparse_b200 import linalg
+
+pytestmark = pytest.mark.gpu
+
+
+def _problem(N):
+    Ad, xs = sample_spd(N, 0.1, 471014)
+    assert np.all(np.linalg.eigvalsh(Ad) > 0)
+    A = sparse.csr_array(Ad)
+    y = A @ xs
+    assert np.allclose(y, Ad @ xs)
+    return Ad, A, y
+
+
+def test_cg_solve():
+    Ad, A, y = _problem(1000)
+    x_pred, iters = linalg.cg(A, y, tol=1e-8)
+    assert np.allclose(A @ x_pred, y)
+    assert np.linalg.norm(y - Ad @ x_pred) < 1e-7
+
+
+def test_cg_solve_with_callback():
+    Ad, A, y = _problem(100)
+    residuals = []
+
+    def callback(x):
+        residuals.append(y - A @ x)
+
+    x_pred, iters = linalg.cg(A, y, tol=1e-8, callback=callback)
+    assert np.allclose(A @ x_pred, y)
+    assert len(residuals) == iters > 0
+
+
+def test_cg_solve_with_identity_preconditioner():
+    Ad, A, y = _problem(1000)
+    x_pred, iters = linalg.cg(A, y, M=sparse.eye(A.shape[0]), tol=1e-8)
+    assert np.allclose(A @ x_pred, y)
+
+
+def test_cg_solve_with_linear_operator():
+    Ad, A, y = _problem(100)
+
+    def matvec(x):
+        return A @ x
+
+    x_pred, iters = linalg.cg(linalg.LinearOperator(A.shape, matvec=matvec), y, tol=1e-8)
+    assert np.allclose(A @ x_pred, y)
+
+    def matvec(x, out=None):  # noqa: F811
+        return A.dot(x, out=out)
+
+    x_pred, iters = linalg.cg(linalg.LinearOperator(A.shape, matvec=matvec), y, tol=1e-8)
+    assert np.allclose(A @ x_pred, y)
+
+
+@pytest.mark.parametrize("fused", ["1", "0"])
+def test_cg_matches_oracle_and_golden(oracle, golden, monkeypatch, fused):
+    monkeypatch.setenv("B2S_CG_FUSED", fused)
+    Ad, A, _ = _problem(100)
+    y = golden["cg100_y"]
+    S = sp.csr_array(Ad)
+    xo, io = oracle.cg(lambda v: oracle.spmv(S.indptr, S.indices, S.data, v), y, tol=1e-8)
+    x, it = linalg.cg(A, y, tol=1e-8)
+    assert it == io
+    assert np.allclose(x, xo, rtol=1e-6, atol=1e-12)
+    assert np.allclose(x, golden["cg100_x"], rtol=1e-6, atol=1e-10)
+
+
+@pytest.mark.parametrize("fused", ["1", "0"])
+def test_cg_laplacian_golden(oracle, golden, monkeypatch, fused):
+    """pde.py operator (negative definite, so alpha < 0), b = ones, tol = 1e-10 as in the example."""
+    monkeypatch.setenv("B2S_CG_FUSED", fused)
+    indptr, indices, data = (golden[f"lap18_{n}"] for n in ("indptr", "indices", "data"))
+    N = indptr.shape[0] - 1
+    A = sparse.csr_array((data, indices, indptr), shape=(N, N))
+    b = np.ones(N)
+    xo, io = oracle.cg(lambda v: oracle.spmv(indptr, indices, data, v), b, tol=1e-10)
+    x, it = linalg.cg(A, b, tol=1e-10)
+    assert it == io and it % 25 == 0
+    assert np.allclose(x, xo, rtol=1e-6, atol=1e-14)
+    assert np.allclose(x, golden["lap18_x"], rtol=1e-6, atol=1e-12)
+    assert np.allclose(A @ x, b)                                       # pde.py:209
+
+
+def test_cg_semantics_maxiter_x0_atol_device():
+    import torch
+
+    Ad, A, y = _problem(100)
+    x, it = linalg.cg(A, y, tol=1e-30, maxiter=7)
+    assert it == 7                                                   # absolute tol never met -> maxiter
+    with pytest.raises(AssertionError):
+        linalg.cg(A, y, atol=1e-5)
+    x0 = np.linalg.solve(Ad, y)
+    x, it = linalg.cg(A, y, x0=x0, tol=1e-6)
+    assert it == 25                                                  # first convergence test is at iteration 25
+    yd = torch.from_numpy(y).cuda()
+    xd, it = linalg.cg(A, yd, tol=1e-8)
+    assert isinstance(xd, torch.Tensor) and xd.is_cuda
+    assert np.allclose(Ad @ xd.cpu().numpy(), y)
+    # float32 system solved in float64 work vectors (reference: np.zeros(n) is float64)
+    x32, _ = linalg.cg(A.astype(np.float32), y, tol=1e-3)
+    assert x32.dtype == np.float64 and np.allclose(Ad @ x32, y, rtol=1e-3, atol=1e-2)
+
+
+def test_pde_example_problem():
+    """examples/pde.py at nx = ny = 130 (N = 16384): solve, acceptance check of pde.py:209, and
+    iteration count equal to the survey's numpy restatement (300)."""
+    nx = ny = 130
+    dx = dy = 1.0 / (nx - 1)
+    a, g = 1.0 / dx**2, 1.0 / dy**2
+    c = -2.0 * a - 2.0 * g
+    diag_a = a * np.ones((nx - 2) * (ny - 2) - 1)
+    diag_a[nx - 3 :: nx - 2] = 0.0
+    diag_g = g * np.ones((nx - 2) * (ny - 3))
+    diag_c = c * np.ones((nx - 2) * (ny - 2))
+    A = sparse.diags([diag_g, diag_a, diag_c, diag_a, diag_g], [-(nx - 2), -1, 0, 1, nx - 2],
+                     dtype=np.float64).tocsc().T
+    N = (nx - 2) * (ny - 2)
+    assert A.shape == (N, N) and A.nnz == 5 * N - 4 * (nx - 2)
+    b = np.ones(N)
+    _ = A.dot(np.zeros(N))
+    x, iters = linalg.cg(A, b, tol=1e-10)
+    assert iters == 300
+    assert np.allclose(A @ x, b)

@@ -1,0 +1,163 @@
+"""GPU parity for CSR x CSR SpGEMM.  Bar (north star): indptr bit-exact, indices bit-exact after
+sort_indices(), values within 1e-6 relative (fp64) -- against the CPU oracle (reference Gustavson,
+spgemm_csr_csr_csr.cc:26-154), the golden scipy products and scipy live.  Mirrors reference
+tests/integration/test_csr_spgemm.py:24-32 and covers every row-size bin of the kernel."""
+import numpy as np
+import pytest
+import scipy.io as sio
+import scipy.sparse as sp
+
+from conftest import MTX_FILES, mtx_path
+
+import legate.sparse_b200 as sparse
+
+pytestmark = pytest.mark.gpu
+
+TYPES = [np.float32, np.float64]
+
+
+def _triple(C):
+    return C.indptr.cpu().numpy().astype(np.int64), C.indices.cpu().numpy().astype(np.int64), C.data.cpu().numpy()
+
+
+def _check_vs_scipy(C, S, rtol):
+    S = S.tocsr()
+    S.sort_indices()
+    ptr, idx, val = _triple(C)
+    assert np.array_equal(ptr, S.indptr), "indptr differs"
+    assert np.array_equal(idx, S.indices), "indices differ"
+    scale = np.abs(S.data).max() if S.nnz else 1.0
+    assert np.allclose(val, S.data, rtol=rtol, atol=rtol * scale)
+
+
+@pytest.mark.parametrize("filename", MTX_FILES)
+@pytest.mark.parametrize("b_type", TYPES)
+@pytest.mark.parametrize("c_type", TYPES)
+def test_csr_csr_csr_spgemm(filename, b_type, c_type):
+    arr = sparse.io.mmread(mtx_path(filename))
+    s = sio.mmread(mtx_path(filename), spmatrix=False).tocsr()
+    res = arr.tocsr().astype(b_type) @ arr.tocsr().astype(c_type)
+    res_sci = s.astype(b_type) @ s.astype(c_type)
+    assert res.dtype == res_sci.dtype
+    assert np.allclose(res.todense(), res_sci.toarray())
+    _check_vs_scipy(res, res_sci, 1e-5 if res.dtype == np.float32 else 1e-12)
+
+
+@pytest.mark.parametrize("key", [n.split(".")[0] for n in MTX_FILES])
+def test_golden_products(golden, oracle, key):
+    ptr, idx, dat = (golden[f"{key}_{n}"] for n in ("indptr", "indices", "data"))
+    n = ptr.shape[0] - 1
+    A = sparse.csr_array((dat, idx, ptr), shape=(n, n))
+    C = A @ A
+    cp, ci, cv = _triple(C)
+    assert np.array_equal(cp, golden[f"{key}_c_indptr"])
+    assert np.array_equal(ci, golden[f"{key}_c_indices"])
+    assert np.allclose(cv, golden[f"{key}_c_data"], rtol=1e-12, atol=0)
+    op, oi, ov = oracle.spgemm((ptr, idx, dat), (ptr, idx, dat), (n, n), (n, n), sort_rows=True)
+    assert np.array_equal(cp, op) and np.array_equal(ci, oi)
+    # warp-per-row bin accumulates in the reference's order -> agree to the last bits (FMA only)
+    assert np.allclose(cv, ov, rtol=1e-14, atol=0)
+
+
+def test_cancellation_zeros_are_kept(oracle):
+    """Reference semantics: structure is symbolic (explicit zeros kept); scipy drops them."""
+    a = (np.array([0, 2, 2]), np.array([1, 0]), np.array([1.0, 1.0]))
+    b = (np.array([0, 3, 4]), np.array([0, 1, 2, 2]), np.array([5.0, 6.0, -1.0, 1.0]))
+    A = sparse.csr_array((a[2], a[1], a[0]), shape=(2, 2))
+    B = sparse.csr_array((b[2], b[1], b[0]), shape=(2, 3))
+    C = A @ B
+    cp, ci, cv = _triple(C)
+    op, oi, ov = oracle.spgemm(a, b, (2, 2), (2, 3), sort_rows=True)
+    assert cp.tolist() == op.tolist() == [0, 3, 3]
+    assert ci.tolist() == oi.tolist() == [0, 1, 2]
+    assert cv.tolist() == ov.tolist() == [5.0, 6.0, 0.0]
+
+
+def _rand(rng, m, n, density, dtype=np.float64):
+    return sp.random(m, n, density=density, random_state=rng, format="csr", dtype=dtype)
+
+
+@pytest.mark.parametrize("dtype", TYPES)
+def test_rectangular_random(dtype):
+    rng = np.random.default_rng(21)
+    A = _rand(rng, 700, 500, 0.02, dtype)
+    B = _rand(rng, 500, 900, 0.03, dtype)
+    C = sparse.csr_array(A) @ sparse.csr_array(B)
+    assert C.shape == (700, 900)
+    _check_vs_scipy(C, A @ B, 1e-4 if dtype == np.float32 else 1e-12)
+
+
+def test_empty_and_degenerate():
+    Z = sparse.csr_array(sp.csr_array((50, 60), dtype=np.float64))
+    B = sparse.csr_array(_rand(np.random.default_rng(1), 60, 40, 0.1))
+    C = Z @ B
+    assert C.nnz == 0 and C.shape == (50, 40) and C.indptr.cpu().numpy().tolist() == [0] * 51
+    I = sparse.eye(60)
+    C2 = I @ B
+    _check_vs_scipy(C2, B.to_scipy_sparse_csr(), 1e-15)
+
+
+def test_banded_microbenchmark_shape():
+    """examples/spgemm_microbenchmark.py:16-39 at n = 20000, 11 nnz/row: C has 21 diagonals."""
+    n, k = 20000, 11
+    offs = [x - k // 2 for x in range(k)]
+    A = sparse.diags([1] * k, offs, shape=(n, n), format="csr", dtype=np.float64)
+    B = A.copy()
+    C = A @ B
+    S = sp.diags([1] * k, offs, shape=(n, n), format="csr", dtype=np.float64)
+    _check_vs_scipy(C, S @ S, 1e-15)
+    assert C.spgemm_info["products"] == int((S @ S).sum()) or C.spgemm_info["products"] > 0
+
+
+def _rmat(scale, ef, seed):
+    """R-MAT (a,b,c,d) = (0.57,0.19,0.19,0.05); duplicate edges summed, values 1.0."""
+    rng = np.random.default_rng(seed)
+    n = 1 << scale
+    m = ef * n
+    rows = np.zeros(m, dtype=np.int64)
+    cols = np.zeros(m, dtype=np.int64)
+    for bit in range(scale):
+        r = rng.random(m)
+        right = (r >= 0.57) & (r < 0.76) | (r >= 0.95)
+        down = r >= 0.76
+        rows |= down.astype(np.int64) << bit
+        cols |= right.astype(np.int64) << bit
+    A = sp.coo_array((np.ones(m), (rows, cols)), shape=(n, n)).tocsr()
+    A.sum_duplicates()
+    A.sort_indices()
+    return A
+
+
+@pytest.mark.parametrize("scale,ef", [(10, 8), (13, 16)])
+def test_rmat_all_bins(oracle, scale, ef):
+    """Power-law rows push work through every bin: warp hash, CTA hash (2 sizes) and the global dense
+    accumulator.  Structure must be bit-exact vs scipy and the oracle."""
+    A = _rmat(scale, ef, 42)
+    S = A @ A
+    G = sparse.csr_array(A)
+    C = G @ G
+    _check_vs_scipy(C, S, 1e-12)
+    lens = np.diff(S.indptr)
+    info = C.spgemm_info
+    assert info["nnz"] == S.nnz
+    assert info["dense_rows"] == int((lens > 8192).sum())
+    op, oi, ov = oracle.spgemm((A.indptr, A.indices, A.data), (A.indptr, A.indices, A.data), A.shape, A.shape,
+                               sort_rows=True)
+    cp, ci, cv = _triple(C)
+    assert np.array_equal(cp, op) and np.array_equal(ci, oi) and np.allclose(cv, ov, rtol=1e-12)
+
+
+def test_forced_dense_bin():
+    """A few very wide rows (nnz(C row) > 8192) exercise the bitmap + dense accumulator path."""
+    rng = np.random.default_rng(5)
+    n = 40000
+    A = _rand(rng, 64, n, 0.0005).tolil()
+    A[3, rng.choice(n, 900, replace=False)] = 1.5
+    A[40, rng.choice(n, 400, replace=False)] = -2.0
+    A = A.tocsr()
+    B = _rand(rng, n, n, 0.0008)
+    S = A @ B
+    assert np.diff(S.indptr).max() > 8192
+    C = sparse.csr_array(A) @ sparse.csr_array(B)
+    assert C.spgemm_info["dense_rows"] >= 1
+    _check_vs_scipy(C, S, 1e-12)

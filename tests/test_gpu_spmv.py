@@ -1,0 +1,245 @@
+"""GPU parity tests for CSR SpMV: CUDA path (through the C ABI) vs the CPU oracle, the golden scipy
+vectors and scipy live.  Mirrors reference tests/integration/test_csr_dot.py:25-45 (files x matrix dtype
+x vector dtype; 1-D, (n,1) and out= forms) and adds the kernel's structural edge cases.
+Tolerance: fp64 1e-12 relative to the row's |A||x| (north star bar is 1e-6); fp32 1e-5."""
+import zlib
+
+import numpy as np
+import pytest
+import scipy.io as sio
+import scipy.sparse as sp
+import torch
+
+from conftest import MTX_FILES, mtx_path
+
+import legate.sparse_b200 as sparse
+from legate.sparse_b200 import _lib, _ops
+
+pytestmark = pytest.mark.gpu
+
+TYPES = [np.float32, np.float64]
+
+
+def _tol(dt):
+    return dict(rtol=1e-5, atol=1e-5) if np.dtype(dt) == np.float32 else dict(rtol=1e-12, atol=1e-12)
+
+
+def _close_rowscaled(y, ref, A_abs_x, dt):
+    """|y - ref| <= eps_budget * (|A||x|)_i : a forward-error bound independent of cancellation."""
+    eps = 2e-6 if np.dtype(dt) == np.float32 else 1e-13
+    err = np.abs(np.asarray(y, dtype=np.float64) - np.asarray(ref, dtype=np.float64))
+    return np.all(err <= eps * (A_abs_x + 1e-300) * 64 + 1e-300)
+
+
+@pytest.mark.parametrize("filename", MTX_FILES)
+@pytest.mark.parametrize("mat_type", TYPES)
+@pytest.mark.parametrize("vec_type", TYPES)
+@pytest.mark.parametrize("col_split", [True, False])
+def test_csr_dot(filename, mat_type, vec_type, col_split):
+    arr = sparse.io.mmread(mtx_path(filename)).tocsr().astype(mat_type)
+    s = sio.mmread(mtx_path(filename), spmatrix=False).tocsr().astype(mat_type)
+    rng = np.random.default_rng(0)
+    vec = rng.random(arr.shape[0]).astype(vec_type)
+    assert np.allclose(arr @ vec, s @ vec)
+    assert np.allclose(arr.dot(vec, spmv_domain_part=col_split), s.dot(vec))
+    out_type = np.result_type(mat_type, vec_type)
+    result_l = np.zeros(arr.shape[0], dtype=out_type)
+    arr.dot(vec, spmv_domain_part=col_split, out=result_l)
+    assert np.allclose(result_l, s.dot(vec))
+    vec = rng.random((arr.shape[0], 1)).astype(vec_type)
+    assert np.allclose(arr @ vec, s @ vec)
+    assert np.allclose(arr.dot(vec), s.dot(vec))
+    result_l = np.zeros((arr.shape[0], 1), dtype=out_type)
+    arr.dot(vec, out=result_l)
+    assert np.allclose(result_l, s.dot(vec))
+    assert (arr @ vec).shape == (arr.shape[0], 1)
+
+
+@pytest.mark.parametrize("key", [n.split(".")[0] for n in MTX_FILES])
+def test_golden_vectors(golden, oracle, key):
+    A = sparse.csr_array((golden[f"{key}_data"], golden[f"{key}_indices"], golden[f"{key}_indptr"]),
+                         shape=(golden[f"{key}_indptr"].shape[0] - 1,) * 2)
+    y = A @ golden[f"{key}_x"]
+    assert np.allclose(y, golden[f"{key}_y"], rtol=1e-13, atol=1e-14)
+    # short rows are reduced sequentially in reference order: expect bit-exact up to FMA contraction
+    yo = oracle.spmv(golden[f"{key}_indptr"], golden[f"{key}_indices"], golden[f"{key}_data"], golden[f"{key}_x"])
+    assert np.allclose(y, yo, rtol=1e-14, atol=1e-15)
+    if key == "test":
+        assert np.array_equal(A @ np.arange(1.0, 6.0), golden["test_kat_y"])
+
+
+def test_wrong_out_dtype_and_shapes():
+    A = sparse.io.mmread(mtx_path("cage4.mtx")).tocsr()
+    with pytest.raises(ValueError, match="not consistent"):
+        A.dot(np.ones(9, dtype=np.float64), out=np.zeros(9, dtype=np.float32))
+    with pytest.raises(AssertionError):
+        A.dot(np.ones(8))
+    with pytest.raises(NotImplementedError):
+        A.dot(np.ones(9, dtype=np.complex128))
+
+
+def test_device_resident_vectors():
+    A = sparse.io.mmread(mtx_path("karate.mtx")).tocsr()
+    s = A.to_scipy_sparse_csr()
+    x = torch.rand(34, dtype=torch.float64, device="cuda")
+    y = A @ x
+    assert isinstance(y, torch.Tensor) and y.is_cuda
+    assert np.allclose(y.cpu().numpy(), s @ x.cpu().numpy())
+    out = torch.zeros(34, dtype=torch.float64, device="cuda")
+    r = A.dot(x, out=out)
+    assert r.data_ptr() == out.data_ptr()
+    assert np.allclose(out.cpu().numpy(), s @ x.cpu().numpy())
+
+
+def _random_csr(rng, nrows, ncols, row_lens, dtype):
+    row_lens = np.asarray(row_lens, dtype=np.int64)
+    indptr = np.zeros(nrows + 1, dtype=np.int64)
+    np.cumsum(row_lens, out=indptr[1:])
+    nnz = int(indptr[-1])
+    indices = rng.integers(0, ncols, nnz)
+    # sort within rows (not required by the kernel, but makes scipy happy); duplicates are fine (summed)
+    rows = np.repeat(np.arange(nrows), row_lens)
+    order = np.lexsort((indices, rows))
+    indices = indices[order]
+    data = rng.standard_normal(nnz).astype(dtype)
+    return indptr, indices, data
+
+
+STRUCTURES = {
+    "uniform5": lambda rng, n: np.full(n, 5),
+    "uniform32": lambda rng, n: np.full(n, 32),
+    "ragged": lambda rng, n: rng.integers(0, 40, n),
+    "mostly_empty": lambda rng, n: (rng.random(n) < 0.05) * rng.integers(1, 9, n),
+    "all_empty": lambda rng, n: np.zeros(n, dtype=np.int64),
+    "one_long_row": lambda rng, n: np.where(np.arange(n) == n // 3, 30000, 3),
+    "long_rows": lambda rng, n: np.where(np.arange(n) % 97 == 0, 6000, 2),
+    "leading_empty_then_long": lambda rng, n: np.where(np.arange(n) == n - 1, 20000, 0),
+    "powerlaw": lambda rng, n: np.minimum((rng.pareto(1.2, n) * 4).astype(np.int64), 50000),
+}
+
+
+@pytest.mark.parametrize("structure", sorted(STRUCTURES))
+@pytest.mark.parametrize("dtype", TYPES)
+@pytest.mark.parametrize("wide", [False, True])
+def test_structures_vs_oracle(oracle, structure, dtype, wide):
+    """Every kernel branch: sequential / sub-warp / warp phase-B, chunk-crossing tails, empty tiles, empty
+    rows, plus int32 and int64 index instantiations -- compared against the CPU oracle."""
+    rng = np.random.default_rng(zlib.crc32(structure.encode()))
+    nrows, ncols = 5003, 4099
+    lens = STRUCTURES[structure](rng, nrows)
+    indptr, indices, data = _random_csr(rng, nrows, ncols, lens, dtype)
+    x = rng.standard_normal(ncols).astype(dtype)
+    idt = torch.int64 if wide else torch.int32
+    d_ptr = torch.from_numpy(indptr).to("cuda", idt)
+    d_idx = torch.from_numpy(indices).to("cuda", idt)
+    d_val = torch.from_numpy(data).cuda()
+    d_x = torch.from_numpy(x).cuda()
+    y = torch.full((nrows,), float("nan"), dtype=d_val.dtype, device="cuda")
+    plan, _ = _ops.spmv_plan(d_ptr, nrows, int(indptr[-1]), dtype)
+    _ops.spmv(d_ptr, d_idx, d_val, d_x, y, (nrows, ncols), plan=plan)
+    ref = oracle.spmv(indptr, indices, data, x)
+    absx = oracle.spmv(indptr, indices, np.abs(data).astype(np.float64), np.abs(x).astype(np.float64))
+    got = y.cpu().numpy()
+    assert not np.isnan(got).any()
+    assert _close_rowscaled(got, ref, absx, dtype), np.abs(got - ref).max()
+    # plan-free kernel (plan=NULL) must agree too
+    y2 = torch.full_like(y, float("nan"))
+    _ops.spmv(d_ptr, d_idx, d_val, d_x, y2, (nrows, ncols), plan=None)
+    assert _close_rowscaled(y2.cpu().numpy(), ref, absx, dtype)
+    # fused dot epilogue: sum_i w_i y_i
+    w = torch.from_numpy(rng.standard_normal(nrows).astype(dtype)).cuda()
+    out = torch.zeros(1, dtype=d_val.dtype, device="cuda")
+    y3 = torch.empty_like(y)
+    _ops.spmv_dot(d_ptr, d_idx, d_val, d_x, y3, w, out, (nrows, ncols), plan)
+    assert torch.equal(y3, y)
+    ref_dot = float(np.dot(w.cpu().numpy().astype(np.float64), got.astype(np.float64)))
+    scale = float(np.dot(np.abs(w.cpu().numpy()).astype(np.float64), absx)) + 1e-300
+    assert abs(float(out[0]) - ref_dot) <= (1e-5 if dtype == np.float32 else 1e-12) * scale
+
+
+def test_unaligned_base_pointers(oracle):
+    """indices/vals views that start at an odd element offset take the scalar-load path."""
+    rng = np.random.default_rng(11)
+    nrows = ncols = 3000
+    indptr, indices, data = _random_csr(rng, nrows, ncols, rng.integers(0, 20, nrows), np.float64)
+    x = rng.standard_normal(ncols)
+    pad_i = torch.zeros(indices.shape[0] + 1, dtype=torch.int32, device="cuda")
+    pad_v = torch.zeros(data.shape[0] + 1, dtype=torch.float64, device="cuda")
+    pad_i[1:] = torch.from_numpy(indices).to("cuda", torch.int32)
+    pad_v[1:] = torch.from_numpy(data).cuda()
+    d_idx, d_val = pad_i[1:], pad_v[1:]
+    assert d_idx.data_ptr() % 16 != 0
+    d_ptr = torch.from_numpy(indptr).to("cuda", torch.int32)
+    y = torch.empty(nrows, dtype=torch.float64, device="cuda")
+    plan, _ = _ops.spmv_plan(d_ptr, nrows, int(indptr[-1]), np.float64)
+    _ops.spmv(d_ptr, d_idx, d_val, torch.from_numpy(x).cuda(), y, (nrows, ncols), plan=plan)
+    assert np.allclose(y.cpu().numpy(), oracle.spmv(indptr, indices, data, x), rtol=1e-12, atol=1e-12)
+
+
+@pytest.mark.parametrize("cfg", range(8))
+@pytest.mark.parametrize("dtype", TYPES)
+def test_all_tile_configs(oracle, cfg, dtype):
+    rng = np.random.default_rng(100 + cfg)
+    nrows = ncols = 20011
+    lens = np.where(np.arange(nrows) % 501 == 0, 9000, rng.integers(0, 12, nrows))
+    indptr, indices, data = _random_csr(rng, nrows, ncols, lens, dtype)
+    x = rng.standard_normal(ncols).astype(dtype)
+    try:
+        _lib.check(_lib.lib.b2s_spmv_set_config(cfg, cfg % 3))
+        A = sparse.csr_array((data, indices, indptr), shape=(nrows, ncols))
+        y = A @ x
+    finally:
+        _lib.check(_lib.lib.b2s_spmv_set_config(0, 0))
+    ref = oracle.spmv(indptr, indices, data, x)
+    absx = oracle.spmv(indptr, indices, np.abs(data).astype(np.float64), np.abs(x).astype(np.float64))
+    assert _close_rowscaled(y, ref, absx, dtype)
+
+
+def _laplacian_5pt(n1, n2, dtype=np.float64):
+    """pde.py:124-163 operator on an n1 x n2 interior grid, assembled directly in CSR."""
+    N = n1 * n2
+    i = np.arange(N, dtype=np.int64)
+    a = float((n1 + 1) ** 2)
+    g = float((n2 + 1) ** 2)
+    c = -2 * a - 2 * g
+    cols = np.stack([i - n1, i - 1, i, i + 1, i + n1], axis=1)
+    vals = np.tile(np.array([g, a, c, a, g], dtype=dtype), (N, 1))
+    valid = np.ones((N, 5), dtype=bool)
+    valid[:, 0] = i >= n1
+    valid[:, 1] = (i % n1) != 0
+    valid[:, 3] = (i % n1) != n1 - 1
+    valid[:, 4] = i < N - n1
+    indptr = np.zeros(N + 1, dtype=np.int64)
+    np.cumsum(valid.sum(axis=1), out=indptr[1:])
+    return indptr, cols[valid], vals[valid], N
+
+
+def test_large_laplacian_properties():
+    """BASELINE config 2 at full size (N ~ 10M, nnz ~ 50M, fp64): size-independent properties.
+    A*1 has a closed form (row sums), A is symmetric (x.Ay == y.Ax), linear, and must equal the
+    plan-free kernel."""
+    n1 = n2 = 3162
+    indptr, indices, data, N = _laplacian_5pt(n1, n2)
+    assert N == 9998244 and indptr[-1] == 5 * N - 4 * n1 == 49978572
+    A = sparse.csr_array((data, indices, indptr), shape=(N, N))
+    ones = torch.ones(N, dtype=torch.float64, device="cuda")
+    y1 = (A @ ones).cpu().numpy()
+    rowsum = np.add.reduceat(data, indptr[:-1])
+    assert np.allclose(y1, rowsum, rtol=1e-13, atol=1e-6)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    x = torch.rand(N, dtype=torch.float64, device="cuda", generator=g)
+    z = torch.rand(N, dtype=torch.float64, device="cuda", generator=g)
+    Ax, Az = A @ x, A @ z
+    lhs, rhs = float(torch.dot(z, Ax)), float(torch.dot(x, Az))
+    assert abs(lhs - rhs) <= 1e-10 * abs(lhs)
+    Axz = A @ (2.0 * x - 3.0 * z)
+    assert torch.allclose(Axz, 2.0 * Ax - 3.0 * Az, rtol=1e-11, atol=1e-4)
+    y2 = torch.empty_like(Ax)
+    _ops.spmv(A.indptr, A.indices, A.data, x, y2, A.shape, plan=None)
+    assert torch.allclose(Ax, y2, rtol=1e-13, atol=1e-7)
+    # spot-check 1000 random rows against a direct numpy evaluation
+    rows = np.random.default_rng(1).integers(0, N, 1000)
+    xh = x.cpu().numpy()
+    for r in rows[:1000]:
+        lo, hi = indptr[r], indptr[r + 1]
+        assert abs(float(Ax[r]) - float(np.dot(data[lo:hi], xh[indices[lo:hi]]))) <= 1e-8 * abs(data[lo:hi]).max()
