@@ -331,7 +331,11 @@ class csr_array:
                     if isinstance(out, torch.Tensor):
                         out.reshape(-1).copy_(y)
                     else:
-                        out.reshape(-1)[...] = to_host(y)
+                        flat = out.reshape(-1)
+                        if flat.flags.c_contiguous and np.shares_memory(flat, out):
+                            torch.from_numpy(flat).copy_(y)  # D2H straight into the caller's (pinned) buffer
+                        else:
+                            flat[...] = to_host(y)
                 result = out
             if other_originally_sparse:
                 return csr_array(np.asarray(to_host(result)).reshape(self.shape[0], -1))

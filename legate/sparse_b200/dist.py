@@ -1,0 +1,300 @@
+"""Multi-GPU: 1-D row-block sharding of CSR matrices and vectors, one process per GPU.
+
+Replaces the reference's partitioning layer (sparse/partition.py, sparse/csr.py:238-246, spmv()
+:930-968) and Legion's implicit copies with an explicit static plan:
+
+* rows   : rank p owns rows [p*T, min((p+1)*T, N)), T = ceil(N/P)            (csr.py:242-245)
+* nnz    : the contiguous indices/vals slice [indptr[p*T], indptr[(p+1)*T))   (CompressedImagePartition,
+           partition.py:56-128) with indptr rebased to 0
+* x      : each shard reads x only inside its column window [min col, max col] (MinMaxImagePartition,
+           partition.py:139-208).  Before an SpMV every rank fills that window of its full-length x
+           buffer: either by an all-gather of the T-padded shards (dense/random matrices) or by point-to-
+           point pieces of exactly the window (stencil/banded matrices: two halo messages).
+* scalars: CG dot products are all-reduced (sum) as 1-element device tensors; they never visit the host
+           between convergence checks (linalg.py:539-555 keeps them in futures).
+
+Collectives go through `torch.distributed` (NCCL on GPUs; gloo on CPU for the host-logic tests).  The
+local compute is always the C-ABI kernels via `_ops`.
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _ops
+from .csr import csr_array
+from .runtime import numpy_dtype, runtime, to_device, to_host, torch_dtype
+
+
+def init_process_group(backend: str | None = None) -> None:
+    """Initialise torch.distributed from the torchrun environment (RANK/WORLD_SIZE/LOCAL_RANK/MASTER_*)
+    and bind this process to its GPU.  The reference does the equivalent at import when more than one GPU is
+    present (sparse/runtime.py:84-87)."""
+    if dist.is_initialized():
+        return
+    if backend is None:
+        backend = "nccl" if torch.cuda.is_available() else "gloo"
+    if torch.cuda.is_available():
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29512")
+    kwargs = {}
+    if backend == "nccl":
+        kwargs["device_id"] = torch.device("cuda", torch.cuda.current_device())
+    dist.init_process_group(backend=backend, **kwargs)
+
+
+def world():
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+class RowBlockPlan:
+    """Static 1-D row-block partition of N rows over P ranks (reference csr.py:238-246)."""
+
+    def __init__(self, nrows: int, nranks: int):
+        self.nrows = int(nrows)
+        self.nranks = int(nranks)
+        self.tile = (self.nrows + self.nranks - 1) // self.nranks if self.nranks > 0 else 0
+
+    def rows(self, rank: int):
+        lo = min(rank * self.tile, self.nrows)
+        hi = min(lo + self.tile, self.nrows)
+        return lo, hi
+
+    def owner(self, row: int) -> int:
+        return min(row // self.tile, self.nranks - 1) if self.tile else 0
+
+    @property
+    def padded(self) -> int:
+        return self.tile * self.nranks
+
+
+def _intersect(a_lo, a_hi, b_lo, b_hi):
+    lo, hi = max(a_lo, b_lo), min(a_hi, b_hi)
+    return (lo, hi) if hi > lo else None
+
+
+class dist_csr_array:
+    """A row shard of a global square-or-rectangular CSR matrix.
+
+    `local` holds rows [row_lo, row_hi) with GLOBAL column ids.  Vectors are sharded the same way
+    (ncols is partitioned by the same plan as nrows for the square matrices of the hot path; for
+    rectangular ones x is partitioned by its own RowBlockPlan over ncols)."""
+
+    def __init__(self, local: csr_array, global_shape, rank=None, nranks=None, group=None):
+        r, w = world()
+        self.rank = r if rank is None else rank
+        self.nranks = w if nranks is None else nranks
+        self.group = group
+        self.local = local
+        self.shape = tuple(int(s) for s in global_shape)
+        self.dtype = local.dtype
+        self.row_plan = RowBlockPlan(self.shape[0], self.nranks)
+        self.col_plan = RowBlockPlan(self.shape[1], self.nranks)
+        self.row_lo, self.row_hi = self.row_plan.rows(self.rank)
+        assert local.shape == (self.row_hi - self.row_lo, self.shape[1]), (local.shape, self.shape)
+        self._xbuf = {}
+        self._build_exchange()
+
+    # -- construction -------------------------------------------------------------------------------
+    @classmethod
+    def from_global(cls, A, rank=None, nranks=None):
+        """Slice this rank's shard out of a replicated global matrix (scipy CSR or csr_array). Used by
+        tests and small problems; large runs assemble shards directly (gallery.*(row_lo=, row_hi=))."""
+        import scipy.sparse as sp
+
+        r, w = world()
+        rank = r if rank is None else rank
+        nranks = w if nranks is None else nranks
+        S = A.to_scipy_sparse_csr() if isinstance(A, csr_array) else sp.csr_array(A)
+        plan = RowBlockPlan(S.shape[0], nranks)
+        lo, hi = plan.rows(rank)
+        klo, khi = int(S.indptr[lo]), int(S.indptr[hi])
+        local = csr_array((S.data[klo:khi], S.indices[klo:khi], S.indptr[lo : hi + 1] - klo),
+                          shape=(hi - lo, S.shape[1]))
+        return cls(local, S.shape, rank=rank, nranks=nranks)
+
+    # -- exchange plan --------------------------------------------------------------------------------
+    def _build_exchange(self):
+        """Column window of this shard + who sends what to whom."""
+        idx = self.local.indices
+        if idx.numel():
+            lo, hi = int(idx.min()), int(idx.max()) + 1
+        else:
+            lo, hi = 0, 0
+        self.window = (lo, hi)
+        wins = [None] * self.nranks
+        if self.nranks > 1:
+            dist.all_gather_object(wins, (lo, hi), group=self.group)
+        else:
+            wins[0] = (lo, hi)
+        self.windows = wins
+        my_lo, my_hi = self.col_plan.rows(self.rank)
+        self.my_cols = (my_lo, my_hi)
+        # pieces of MY x rows that peer q reads; pieces of q's x rows that I read
+        self.sends = []
+        self.recvs = []
+        for q in range(self.nranks):
+            if q == self.rank:
+                continue
+            s = _intersect(*wins[q], my_lo, my_hi) if wins[q][1] > wins[q][0] else None
+            if s:
+                self.sends.append((q, s[0], s[1]))
+            qlo, qhi = self.col_plan.rows(q)
+            r = _intersect(lo, hi, qlo, qhi) if hi > lo else None
+            if r:
+                self.recvs.append((q, r[0], r[1]))
+        need = sum(b - a for _, a, b in self.recvs)
+        total_need = need
+        if self.nranks > 1:
+            t = torch.tensor([need], dtype=torch.int64, device=self._comm_device())
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+            total_need = int(t.item())
+        mode = os.environ.get("B2S_EXCHANGE", "auto")
+        if mode == "auto":
+            # all-gather moves (P-1)*T elements into every rank; use p2p windows when they are much smaller
+            mode = "p2p" if total_need * 4 < (self.nranks - 1) * self.col_plan.tile else "allgather"
+        self.exchange_mode = mode if self.nranks > 1 else "none"
+        self.recv_elems = need
+
+    def _comm_device(self):
+        return runtime.device
+
+    # -- vectors ----------------------------------------------------------------------------------------
+    def new_full_vector(self, dtype=None) -> torch.Tensor:
+        """Full-length x buffer (padded to P*T so the all-gather lands in place).  The buffer is offset
+        inside its allocation so that this rank's own slice starts 16-byte aligned (the vector kernels
+        then take their 128-bit path on the shard views)."""
+        dt = torch_dtype(self.dtype if dtype is None else dtype)
+        n = max(self.col_plan.padded, 1)
+        base = torch.zeros(n + 4, dtype=dt, device=runtime.device)
+        per16 = 16 // base.element_size()
+        off = (-self.my_cols[0]) % per16
+        return base[off : off + n]
+
+    def local_view(self, full: torch.Tensor) -> torch.Tensor:
+        lo, hi = self.my_cols
+        return full[lo:hi]
+
+    def scatter_vector(self, v_global) -> torch.Tensor:
+        """This rank's shard of a replicated global vector (as a view into a fresh full buffer)."""
+        full = self.new_full_vector(numpy_dtype(v_global.dtype) if hasattr(v_global, "dtype") else None)
+        lo, hi = self.my_cols
+        full[lo:hi] = to_device(v_global[lo:hi], dtype=numpy_dtype(full.dtype))
+        return full
+
+    def exchange(self, full: torch.Tensor) -> None:
+        """Make full[window] valid on every rank, given that full[my_cols] is valid."""
+        if self.exchange_mode == "none":
+            return
+        if self.exchange_mode == "allgather":
+            lo, hi = self.my_cols
+            T = self.col_plan.tile
+            src = full[self.rank * T : (self.rank + 1) * T]
+            dist.all_gather_into_tensor(full, src, group=self.group)
+            return
+        ops = []
+        for q, a, b in self.recvs:
+            ops.append(dist.P2POp(dist.irecv, full[a:b], q, group=self.group))
+        for q, a, b in self.sends:
+            ops.append(dist.P2POp(dist.isend, full[a:b], q, group=self.group))
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+
+    # -- SpMV ---------------------------------------------------------------------------------------------
+    def dot(self, x_full: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+        """y_local = A_local @ x.  `x_full` is a full-length buffer whose my_cols slice is current."""
+        self.exchange(x_full)
+        A = self.local
+        if out is None:
+            out = torch.empty(A.shape[0], dtype=x_full.dtype, device=x_full.device)
+        _ops.spmv(A.indptr, A.indices, A.data, x_full[: A.shape[1]], out, A.shape, plan=A._get_plan())
+        return out
+
+    def dot_fused(self, x_full, out, w, dot_out):
+        """y_local = A_local @ x and dot_out = all-reduced sum_i w_i y_i."""
+        self.exchange(x_full)
+        A = self.local
+        _ops.spmv_dot(A.indptr, A.indices, A.data, x_full[: A.shape[1]], out, w, dot_out, A.shape, A._get_plan())
+        allreduce_scalar(dot_out, self.group)
+        return out
+
+    def matvec_global(self, x_global):
+        """Convenience for tests: replicated x in, replicated y out (numpy)."""
+        full = self.scatter_vector(np.asarray(x_global, dtype=self.dtype))
+        y = self.dot(full)
+        return gather_vector(y, self.row_plan, self.rank, self.group)
+
+
+def allreduce_scalar(t: torch.Tensor, group=None) -> torch.Tensor:
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t
+
+
+def gather_vector(v_local: torch.Tensor, plan: RowBlockPlan, rank: int, group=None) -> np.ndarray:
+    """All ranks receive the concatenated global vector (host numpy)."""
+    if plan.nranks == 1:
+        return to_host(v_local)
+    T = plan.tile
+    pad = torch.zeros(T, dtype=v_local.dtype, device=v_local.device)
+    pad[: v_local.shape[0]] = v_local
+    full = torch.empty(T * plan.nranks, dtype=v_local.dtype, device=v_local.device)
+    dist.all_gather_into_tensor(full, pad, group=group)
+    return to_host(full[: plan.nrows])
+
+
+def cg(A: dist_csr_array, b_local, x0_local=None, tol=1e-08, maxiter=None, callback=None, conv_test_iters=25):
+    """Row-sharded conjugate gradient: the fused loop of linalg._cg_fused with the SpMV input exchanged
+    per iteration and the two inner products all-reduced.  Same semantics as linalg.cg (absolute tol,
+    test every conv_test_iters, returns (x_local, iters)); every rank returns its shard of x."""
+    assert A.shape[0] == A.shape[1]
+    n_global = A.shape[0]
+    if maxiter is None:
+        maxiter = n_global * 10
+    dt = np.result_type(np.float64 if x0_local is None else numpy_dtype(x0_local.dtype), numpy_dtype(b_local.dtype))
+    Al = A.local if A.local.dtype == dt else A.local._promoted(dt)  # same structure, promoted values
+    b = to_device(b_local, dtype=dt).reshape(-1)
+    n = b.shape[0]
+    x = torch.zeros(n, dtype=b.dtype, device=b.device) if x0_local is None else to_device(x0_local, dtype=dt, copy=True)
+    p_full = A.new_full_vector(dt)
+    p = A.local_view(p_full)
+    q = torch.empty(n, dtype=b.dtype, device=b.device)
+    plan = Al._get_plan()
+
+    def spmv_into(full, out):
+        A.exchange(full)
+        _ops.spmv(Al.indptr, Al.indices, Al.data, full[: Al.shape[1]], out, Al.shape, plan=plan)
+
+    # r = b - A x
+    p.copy_(x)
+    spmv_into(p_full, q)
+    r = b - q
+    rho = _ops.dot(r, r)
+    allreduce_scalar(rho, A.group)
+    rho_next = torch.empty_like(rho)
+    pq = torch.empty_like(rho)
+    iters = 0
+    while iters < maxiter:
+        if iters == 0:
+            p.copy_(r)
+        else:
+            _ops.axpby(p, r, rho_next, rho, isalpha=False, negate=False)
+            rho, rho_next = rho_next, rho
+        A.exchange(p_full)
+        _ops.spmv_dot(Al.indptr, Al.indices, Al.data, p_full[: Al.shape[1]], q, p, pq, Al.shape, plan)
+        allreduce_scalar(pq, A.group)
+        _ops.cg_update_xr(x, r, p, q, rho, pq, rho_next)
+        allreduce_scalar(rho_next, A.group)
+        iters += 1
+        if callback is not None:
+            callback(x)
+        if (iters % conv_test_iters == 0 or iters == (maxiter - 1)) and float(rho_next[0]) ** 0.5 < tol:
+            break
+    return x, iters

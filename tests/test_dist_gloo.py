@@ -1,0 +1,164 @@
+"""world_size-2 (and 3) CPU tests of the multi-GPU host logic over the gloo backend: row-block plan,
+column windows, the all-gather and point-to-point x exchanges, all-reduced CG scalars.  The per-shard
+compute is swapped for the CPU oracle here (tests only) -- on the GPU box the same code drives the CUDA
+kernels (tests/test_gpu_dist.py)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import scipy.io as sio
+import scipy.sparse as sp
+import torch
+import torch.multiprocessing as mp
+
+from conftest import ROOT, mtx_path, sample_spd
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _patch_ops_with_oracle():
+    """Route the leaf launchers to the CPU oracle (CPU tensors in, CPU tensors out)."""
+    from legate.sparse_b200 import _ops, csr as csr_mod
+    from oracle import oracle as orc
+
+    def spmv(indptr, indices, data, x, y, shape, plan=None):
+        y[:] = torch.from_numpy(orc.spmv(indptr.numpy(), indices.numpy(), data.numpy(), x.numpy()[: shape[1]]))
+        return y
+
+    def spmv_dot(indptr, indices, data, x, y, w, out, shape, plan):
+        spmv(indptr, indices, data, x, y, shape)
+        out[:] = torch.from_numpy(orc.dot(w.numpy(), y.numpy()))
+        return y
+
+    def axpby(y, x, a, b, isalpha=True, negate=False):
+        yy = y.numpy().copy()
+        orc.axpby(yy, x.numpy(), a.numpy(), b.numpy(), isalpha=isalpha, negate=negate)
+        y[:] = torch.from_numpy(yy)
+        return y
+
+    def dot(x, y, out=None):
+        r = torch.from_numpy(orc.dot(x.numpy(), y.numpy()))
+        if out is not None:
+            out[:] = r
+            return out
+        return r
+
+    def cg_update_xr(x, r, p, q, rho, pq, rr_out):
+        axpby(x, p, rho, pq, True, False)
+        axpby(r, q, rho, pq, True, True)
+        rr_out[:] = torch.from_numpy(orc.dot(r.numpy(), r.numpy()))
+        return rr_out
+
+    _ops.spmv, _ops.spmv_dot, _ops.axpby, _ops.dot, _ops.cg_update_xr = spmv, spmv_dot, axpby, dot, cg_update_xr
+    csr_mod.csr_array._get_plan = lambda self: None
+
+
+def _worker(rank, world, port, case, q):
+    try:
+        sys.path.insert(0, ROOT)
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                          LOCAL_RANK=str(rank))
+        import torch.distributed as dist
+        from legate.sparse_b200 import dist as bd
+
+        bd.init_process_group("gloo")
+        _patch_ops_with_oracle()
+        out = {}
+        if case == "spmv":
+            for name in ("karate.mtx", "GlossGT.mtx", "cage4.mtx"):
+                S = sio.mmread(mtx_path(name), spmatrix=False).tocsr().astype(np.float64)
+                x = np.random.default_rng(3).random(S.shape[1])
+                for mode in ("allgather", "p2p"):
+                    os.environ["B2S_EXCHANGE"] = mode
+                    A = bd.dist_csr_array.from_global(S)
+                    assert A.exchange_mode == mode
+                    y = A.matvec_global(x)
+                    assert np.allclose(y, S @ x, rtol=1e-13), (name, mode)
+                    lo, hi = A.row_plan.rows(rank)
+                    if hi > lo and S.indptr[hi] > S.indptr[lo]:
+                        seg = S.indices[S.indptr[lo] : S.indptr[hi]]
+                        assert A.window == (seg.min(), seg.max() + 1)
+            # banded matrix: the auto heuristic must choose the p2p halo exchange and move only the halo
+            os.environ["B2S_EXCHANGE"] = "auto"
+            n = 4000
+            S = sp.diags([1.0, 2.0, 3.0], [-37, 0, 37], shape=(n, n), format="csr")
+            A = bd.dist_csr_array.from_global(S)
+            assert A.exchange_mode == "p2p"
+            assert A.recv_elems <= 2 * 37
+            x = np.random.default_rng(4).random(n)
+            assert np.allclose(A.matvec_global(x), S @ x, rtol=1e-13)
+            # dense-ish random matrix: windows span everything -> all-gather
+            S = sp.random(300, 300, density=0.2, random_state=np.random.default_rng(9), format="csr")
+            A = bd.dist_csr_array.from_global(S)
+            assert A.exchange_mode == "allgather"
+            assert np.allclose(A.matvec_global(x[:300]), S @ x[:300], rtol=1e-12)
+            out["ok"] = True
+        elif case == "cg":
+            from oracle import oracle as orc
+
+            Ad, xs = sample_spd(200, 0.1, 471014)
+            S = sp.csr_array(Ad)
+            y = S @ xs
+            for mode in ("allgather", "p2p"):
+                os.environ["B2S_EXCHANGE"] = mode
+                A = bd.dist_csr_array.from_global(S)
+                lo, hi = A.row_plan.rows(rank)
+                xl, iters = bd.cg(A, y[lo:hi], tol=1e-8)
+                xg = bd.gather_vector(xl, A.row_plan, rank)
+                xo, io = orc.cg(lambda v: orc.spmv(S.indptr, S.indices, S.data, v), y, tol=1e-8)
+                assert iters == io, (iters, io)
+                assert np.allclose(xg, xo, rtol=1e-9, atol=1e-13)
+                assert np.allclose(S @ xg, y)
+            out["ok"] = True
+        dist.barrier()
+        dist.destroy_process_group()
+        q.put((rank, out))
+    except Exception as exc:  # pragma: no cover
+        import traceback
+
+        q.put((rank, {"error": f"{exc}\n{traceback.format_exc()}"}))
+
+
+def _run(world, case):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, case, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=240) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, out in results:
+        assert "error" not in out, f"rank {rank}: {out.get('error')}"
+        assert out.get("ok")
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_spmv_gloo(world):
+    _run(world, "spmv")
+
+
+def test_sharded_cg_gloo():
+    _run(2, "cg")
+
+
+def test_row_block_plan_matches_oracle(oracle, golden):
+    from legate.sparse_b200.dist import RowBlockPlan
+
+    indptr = golden["GlossGT_indptr"]
+    n = indptr.shape[0] - 1
+    for P in (1, 2, 3, 5, 8, 100):
+        plan = RowBlockPlan(n, P)
+        for r in range(P):
+            lo, hi, _, _ = oracle.row_block(indptr, r, P)
+            assert plan.rows(r) == (lo, hi)
