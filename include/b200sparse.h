@@ -65,18 +65,21 @@ int64_t     b2s_ws_bytes(void);
  * fixed-size tiles.  Stands in for the partitions the reference computes once per store
  * and caches (sparse/partition.py:56-128 CompressedImagePartition,
  * src/sparse/partition/fast_image_range.cu:27-54).
- * b2s_spmv_plan_tiles: number of tiles T for this matrix/value type; the plan buffer
- * holds (T+1) int32.  b2s_spmv_plan_build fills it (device, async). */
+ * b2s_spmv_plan_tiles: number of tiles T for this matrix/value type;
+ * b2s_spmv_plan_bytes: size of the plan buffer ((T+1) 16-byte entries {first nnz, first row});
+ * b2s_spmv_plan_build fills it (device, async).  The buffer must be 16-byte aligned. */
 int64_t     b2s_spmv_plan_tiles(int vt, int64_t nrows, int64_t nnz);
+int64_t     b2s_spmv_plan_bytes(int vt, int64_t nrows, int64_t nnz);
 int         b2s_spmv_plan_build(int vt, int pt, int64_t nrows, int64_t nnz,
-                                const void* indptr, int32_t* plan, void* stream);
+                                const void* indptr, void* plan, void* stream);
 
 /* y = A x  (alpha=1, beta=0 as spmv.cu:79-80).  `plan` may be NULL: then a plan-free
  * row-per-lane-group kernel is used (slower on short rows).  x has ncols entries,
- * y has nrows entries; y must not alias x. */
+ * y has nrows entries; y must not alias x.  With a plan the TMA-staged persistent kernel
+ * runs when indptr/indices/vals are 16-byte aligned (always true for whole allocations). */
 int         b2s_spmv_csr(int vt, int it, int pt, int64_t nrows, int64_t ncols, int64_t nnz,
                          const void* indptr, const void* indices, const void* vals,
-                         const void* x, void* y, const int32_t* plan, void* stream);
+                         const void* x, void* y, const void* plan, void* stream);
 
 /* y = A x and *dot_out = sum_i w[i] * y[i] in one pass (CG: q = A p, pq = p.q;
  * sparse/linalg.py:549-550 fused).  w has nrows entries (for a row shard it is the
@@ -84,7 +87,7 @@ int         b2s_spmv_csr(int vt, int it, int pt, int64_t nrows, int64_t ncols, i
 int         b2s_spmv_csr_dot(int vt, int it, int pt, int64_t nrows, int64_t ncols, int64_t nnz,
                              const void* indptr, const void* indices, const void* vals,
                              const void* x, void* y, const void* w, void* dot_out,
-                             const int32_t* plan, void* ws, void* stream);
+                             const void* plan, void* ws, void* stream);
 
 /* ---- CG vector kernels ---------------------------------------------------------------
  * b2s_axpby replaces AXPBY::gpu_variant (src/sparse/linalg/axpby.cu:25-62):

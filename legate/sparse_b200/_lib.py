@@ -26,6 +26,7 @@ SIGNATURES = {
     "b2s_device_info": (c_i32, [c_i32, c_vp]),
     "b2s_ws_bytes": (c_i64, []),
     "b2s_spmv_plan_tiles": (c_i64, [c_i32, c_i64, c_i64]),
+    "b2s_spmv_plan_bytes": (c_i64, [c_i32, c_i64, c_i64]),
     "b2s_spmv_plan_build": (c_i32, [c_i32, c_i32, c_i64, c_i64, c_vp, c_vp, c_vp]),
     "b2s_spmv_csr": (c_i32, [c_i32, c_i32, c_i32, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "b2s_spmv_csr_dot": (c_i32, [c_i32, c_i32, c_i32, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp,
@@ -46,6 +47,7 @@ SIGNATURES = {
     # tuning hooks (not in the public header)
     "b2s_spmv_set_config": (c_i32, [c_i32, c_i32]),
     "b2s_spmv_get_config": (c_i32, []),
+    "b2s_spmv_num_configs": (c_i32, []),
 }
 
 

@@ -30,11 +30,11 @@ def _chk_dev(*ts):
 
 # ---- SpMV -----------------------------------------------------------------------------------------
 def spmv_plan(indptr: torch.Tensor, nrows: int, nnz: int, vdtype) -> tuple[torch.Tensor, int]:
-    """Build the tile plan for a CSR structure. Returns (plan int32[T+1], config id)."""
+    """Build the tile plan for a CSR structure. Returns (plan buffer of 16-byte entries, config id)."""
     _chk_dev(indptr)
     vt = vt_code(vdtype)
-    ntiles = int(L.b2s_spmv_plan_tiles(vt, nrows, nnz))
-    plan = torch.empty(ntiles + 1, dtype=torch.int32, device=indptr.device)
+    nbytes = int(L.b2s_spmv_plan_bytes(vt, nrows, nnz))
+    plan = torch.empty(max(nbytes, 16) // 4, dtype=torch.int32, device=indptr.device)
     _lib.check(L.b2s_spmv_plan_build(vt, idx_code(indptr.dtype), nrows, nnz, ptr(indptr), ptr(plan), _stream()),
                "b2s_spmv_plan_build")
     return plan, int(L.b2s_spmv_get_config())

@@ -1,22 +1,24 @@
 // spmv.cu -- CSR SpMV for sm_100a.
 //
 // Replaces CSRSpMVRowSplit::gpu_variant (reference src/sparse/array/csr/spmv.cu:24-123, a
-// cusparseSpMV call) with a hand-written row-blocked ("merge-path tiles rounded to row
-// boundaries") kernel:
+// cusparseSpMV call) with hand-written row-blocked ("merge-path tiles rounded to row boundaries")
+// kernels:
 //
-//   plan   : the (rows + nnz) work list is cut into tiles of T merge items; tile t owns the rows
-//            whose start position indptr[r] + r falls in [t*T, (t+1)*T).  Every tile therefore has
-//            <= T rows, and all of its rows except possibly the last fit in one shared-memory
-//            chunk of CAP = T + 4 nonzeros.  The plan is (ntiles + 1) int32 row boundaries.
-//   phase A: the CTA streams the tile's contiguous nnz range with 128-bit evict-first loads of
-//            indices/vals, gathers x through the read-only path and parks vals[k]*x[col[k]] in
-//            shared memory (fully coalesced regardless of row lengths).
-//   tail   : a last row longer than the chunk is finished by the whole CTA straight from global
-//            memory (block reduction) -- so no cross-CTA carries, no atomics, no fix-up pass.
-//   phase B: 2^s lanes per row (s chosen per tile from its mean row length) reduce the parked
-//            products: sequential for short rows (same order as the reference's CPU loop,
-//            spmv.cc:36-44), warp-shuffle tree for long rows.  Optional fused epilogue: the CG
-//            inner product sum_i w[i]*y[i] (deterministic two-stage grid reduction).
+//   plan   : the (rows + nnz) work list is cut into tiles of T merge items; tile t owns the rows whose
+//            start position indptr[r] + r falls in [t*T, (t+1)*T).  Every tile therefore has <= T rows and
+//            all of its rows except possibly the last fit in one shared-memory chunk of CAP = T + 4
+//            nonzeros.  The plan is (ntiles + 1) 16-byte entries {first nnz, first row}.
+//   kind 1 (default, "TMA"): persistent CTAs; one producer thread streams each tile's indices / vals /
+//            indptr slices into a ring of shared-memory stages with cp.async.bulk (TMA, evict-first L2
+//            hint) completing on mbarriers, running STAGES tiles ahead of the consumer warps, which
+//            gather x through the read-only path, overwrite vals with vals[k]*x[col[k]] in place and reduce.
+//   kind 0 ("LDG"): the same tile processed with 128-bit register loads, one tile per CTA.
+//   tail   : a last row longer than the chunk is finished by the whole CTA straight from global memory
+//            (block reduction) -- so no cross-CTA carries, no atomics, no fix-up pass.
+//   reduce : 2^s lanes per row (s chosen per tile from its row length) reduce the parked products:
+//            sequential for short rows (same order as the reference's CPU loop, spmv.cc:36-44),
+//            warp-shuffle tree for long rows.  Optional fused epilogue: the CG inner product
+//            sum_i w[i]*y[i] (deterministic two-stage grid reduction).
 //
 // HBM-bound by construction: algorithmic bytes per launch are
 //   nnz*(sizeof V + sizeof I) + (nrows+1)*sizeof P + ncols*sizeof V + nrows*sizeof V.
@@ -24,60 +26,116 @@
 
 namespace b2s {
 
+struct __align__(16) PlanEntry {
+  long long k;   // first nonzero of the tile's first row
+  int row;       // first row of the tile
+  int pad;
+};
+
 // ---------------------------------------------------------------------------------------------
-// Tile configurations.  CAP = 4*THREADS*GROUPS nonzeros staged per chunk; T = CAP - 4 merge items.
+// Tile configurations.  X(ID, KIND, A, B, C, D)
+//   KIND 0 (LDG) : A = THREADS, B = GROUPS (4-nnz groups per thread), C = MINB, D = SCALAR mapping flag
+//                  CAP = 4*A*B
+//   KIND 1 (TMA) : A = consumer warps, B = 16-byte groups per consumer thread, C = STAGES, D = MINB
+//                  CAP = (16/sizeof V) * 32*A * B
+// T = CAP - 4 merge items per tile.  Config 0 is the default and is instantiated for every index type;
+// the others (tuning sweeps, tools/, b2s_spmv_set_config) only for int32 indices/indptr.
 // ---------------------------------------------------------------------------------------------
-// MINB = CTAs/SM promised to the compiler (register cap = 65536 / (THREADS*MINB)).
-// X(ID, THREADS, GROUPS, MINB).  Config 0 is the default and the only one instantiated for
-// int64 index/indptr types; the others exist for tuning sweeps (tools/, b2s_spmv_set_config).
 #define B2S_SPMV_CONFIGS(X) \
-  X(0, 256, 4, 3)           \
-  X(1, 256, 2, 4)           \
-  X(2, 128, 4, 6)           \
-  X(3, 256, 4, 4)           \
-  X(4, 256, 4, 2)           \
-  X(5, 512, 2, 2)           \
-  X(6, 256, 8, 2)           \
-  X(7, 128, 8, 4)
-struct TileCfgRt { int threads, groups, minb; };
+  X(0, 1, 4, 4, 2, 6)       \
+  X(1, 0, 128, 4, 6, 0)     \
+  X(2, 0, 256, 4, 3, 0)     \
+  X(3, 0, 128, 2, 8, 1)     \
+  X(4, 1, 4, 6, 2, 4)       \
+  X(5, 1, 4, 8, 2, 3)       \
+  X(6, 1, 4, 3, 2, 8)       \
+  X(7, 1, 4, 2, 2, 10)      \
+  X(8, 1, 2, 4, 2, 12)      \
+  X(9, 1, 2, 8, 2, 8)       \
+  X(10, 1, 3, 4, 2, 8)      \
+  X(11, 1, 4, 4, 2, 7)      \
+  X(12, 1, 8, 2, 2, 4)      \
+  X(13, 1, 6, 4, 2, 4)      \
+  X(14, 1, 4, 4, 3, 4)      \
+  X(15, 1, 2, 6, 2, 10)
+struct TileCfgRt { int kind, a, b, c, d; };
 static const TileCfgRt kCfgs[] = {
-#define X(ID, TH, GR, MB) {TH, GR, MB},
+#define X(ID, K, A, B, C, D) {K, A, B, C, D},
     B2S_SPMV_CONFIGS(X)
 #undef X
 };
 static constexpr int kNumCfgs = sizeof(kCfgs) / sizeof(kCfgs[0]);
-static int g_cfg = 0;          // selected configuration (b2s_spmv_set_config)
-static int g_waves = 0;        // 0 = one tile per CTA; >0 = grid-stride with waves*SMs*occupancy CTAs
+static int g_cfg = 0;    // selected configuration (b2s_spmv_set_config)
+static int g_waves = 0;  // LDG kind: 0 = one tile per CTA; >0 = grid-stride with waves*SMs*occupancy CTAs
+                         // TMA kind: CTAs per SM multiplier override (0 = occupancy)
 
-static inline int cfg_cap(int c) { return 4 * kCfgs[c].threads * kCfgs[c].groups; }
-static inline int cfg_T(int c) { return cfg_cap(c) - 4; }
+static inline int cfg_cap(int c, int vt) {
+  const TileCfgRt& k = kCfgs[c];
+  if (k.kind == 0) return 4 * k.a * k.b;
+  return (vt == B2S_F32 ? 4 : 2) * 32 * k.a * k.b;
+}
+static inline int cfg_T(int c, int vt) { return cfg_cap(c, vt) - 4; }
 
 // ---------------------------------------------------------------------------------------------
-// Plan kernel: plan[t] = first row r with indptr[r] + r >= t*T ; plan[ntiles] = nrows.
+// Plan kernel: plan[t] = {indptr[r], r} for the first row r with indptr[r] + r >= t*T;
+// plan[ntiles] = {nnz, nrows}.
 // ---------------------------------------------------------------------------------------------
 template <typename P>
 __global__ void spmv_plan_kernel(int64_t nrows, const P* __restrict__ indptr, int64_t T, int64_t ntiles,
-                                 int32_t* __restrict__ plan) {
+                                 PlanEntry* __restrict__ plan) {
   int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t > ntiles) return;
-  if (t == ntiles) { plan[t] = (int32_t)nrows; return; }
-  const int64_t target = t * T;
   int64_t lo = 0, hi = nrows;  // answer in [0, nrows]
-  while (lo < hi) {
-    int64_t mid = (lo + hi) >> 1;
-    if ((int64_t)indptr[mid] + mid >= target) hi = mid; else lo = mid + 1;
+  if (t == ntiles) {
+    lo = nrows;
+  } else {
+    const int64_t target = t * T;
+    while (lo < hi) {
+      int64_t mid = (lo + hi) >> 1;
+      if ((int64_t)indptr[mid] + mid >= target) hi = mid; else lo = mid + 1;
+    }
   }
-  plan[t] = (int32_t)lo;
+  PlanEntry e;
+  e.k = (long long)indptr[lo];
+  e.row = (int)lo;
+  e.pad = 0;
+  plan[t] = e;
+}
+
+__device__ __forceinline__ PlanEntry ld_plan(const PlanEntry* p) {
+  int4 v = __ldg(reinterpret_cast<const int4*>(p));
+  PlanEntry e;
+  e.k = ((long long)(unsigned)v.x) | ((long long)v.y << 32);
+  e.row = v.z;
+  e.pad = v.w;
+  return e;
+}
+
+// lanes-per-row rule shared by both kernels
+__device__ __forceinline__ int lanes_per_row_shift(int64_t nnz_t, int nr) {
+  // lanes per row g = 2^gshift, uniform over the tile.  With row length L the parked products of
+  // consecutive rows sit L apart, so g = (largest power of two dividing L) makes the per-row reads
+  // bank-conflict free; g is then raised until no lane loops more than ~12 times.  g = 1 walks a row
+  // sequentially, i.e. in the reference's accumulation order (spmv.cc:36-44).
+  int gshift = 0;
+  const int L = (int)((nnz_t + nr - 1) / nr);
+  if (L > 0) {
+    if (nnz_t == (int64_t)L * nr) {
+      while (gshift < 5 && ((L >> gshift) & 1) == 0) gshift++;
+    }
+    while (gshift < 5 && (L >> gshift) > 12) gshift++;
+  }
+  return gshift;
 }
 
 // ---------------------------------------------------------------------------------------------
-// Tiled SpMV kernel.
+// KIND 0: LDG tile kernel.
 // ---------------------------------------------------------------------------------------------
-template <typename V, typename I, typename P, int THREADS, int GROUPS, int MINB, bool DOT>
+template <typename V, typename I, typename P, int THREADS, int GROUPS, int MINB, bool SCALAR, bool DOT>
 __global__ void __launch_bounds__(THREADS, MINB)
 spmv_tile_kernel(int64_t ntiles, const P* __restrict__ indptr, const I* __restrict__ indices,
                  const V* __restrict__ vals, const V* __restrict__ x, V* __restrict__ y,
-                 const int32_t* __restrict__ plan, int vec_ok, const V* __restrict__ w, V* dot_out, void* ws) {
+                 const PlanEntry* __restrict__ plan, int vec_ok, const V* __restrict__ w, V* dot_out, void* ws) {
   constexpr int CAP = 4 * THREADS * GROUPS;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   V* prod = reinterpret_cast<V*>(smem_raw);                                  // CAP values
@@ -90,17 +148,18 @@ spmv_tile_kernel(int64_t ntiles, const P* __restrict__ indptr, const I* __restri
   double dot_acc = 0.0;
 
   for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
-    const int r0 = plan[t], r1 = plan[t + 1];
+    const PlanEntry e0 = ld_plan(plan + t), e1 = ld_plan(plan + t + 1);
+    const int r0 = e0.row, r1 = e1.row;
     const int nr = r1 - r0;
     if (nr <= 0) continue;  // block-uniform: tile lies inside a long row owned by an earlier tile
-    const int64_t k0 = (int64_t)indptr[r0];
-    const int64_t k1 = (int64_t)indptr[r1];
+    const int64_t k0 = e0.k;
+    const int64_t k1 = e1.k;
     const int64_t kb = k0 & ~(int64_t)3;           // 16-byte aligned chunk base
     const int off = (int)(k0 - kb);
     const int64_t kce = (k1 < kb + CAP) ? k1 : kb + CAP;  // end of the staged chunk
     const bool has_tail = k1 > kce;
 
-    __syncthreads();  // previous tile's phase B is done with prod/sptr
+    __syncthreads();  // previous tile's reduce phase is done with prod/sptr
 
     // row offsets of this tile, relative to k0, clamped to the chunk (uint16: CAP <= 32768)
     for (int j = tid; j <= nr; j += THREADS) {
@@ -110,7 +169,30 @@ spmv_tile_kernel(int64_t ntiles, const P* __restrict__ indptr, const I* __restri
     }
 
     // ---- phase A: stream nnz [k0, kce) -> prod[k - kb] ---------------------------------------
-    if (vec_ok) {
+    if (SCALAR) {
+      constexpr int ITEMS = 4 * GROUPS;
+      I c[ITEMS];
+      V a[ITEMS];
+#pragma unroll
+      for (int j = 0; j < ITEMS; j++) {
+        const int64_t k = kb + tid + THREADS * j;
+        const bool in = (k >= k0) && (k < kce);
+        c[j] = in ? ld_stream(indices + k) : (I)0;
+        a[j] = in ? ld_stream(vals + k) : (V)0;
+      }
+      V xv[ITEMS];
+#pragma unroll
+      for (int j = 0; j < ITEMS; j++) {
+        const int64_t k = kb + tid + THREADS * j;
+        const bool in = (k >= k0) && (k < kce);
+        xv[j] = in ? __ldg(x + c[j]) : (V)0;
+      }
+#pragma unroll
+      for (int j = 0; j < ITEMS; j++) {
+        const int e = tid + THREADS * j;
+        if (kb + e < kce) prod[e] = a[j] * xv[j];
+      }
+    } else if (vec_ok) {
       I c[GROUPS][4];
       V a[GROUPS][4];
 #pragma unroll
@@ -142,8 +224,21 @@ spmv_tile_kernel(int64_t ntiles, const P* __restrict__ indptr, const I* __restri
       for (int g = 0; g < GROUPS; g++) {
         const int e = 4 * (tid + THREADS * g);
         if (kb + e < kce) {
+          if constexpr (sizeof(V) == 8) {
+            // 32 B per lane = two 16-byte stores.  Lanes 4..7 of each quarter-warp write their upper half
+            // first, so the eight lanes of one store wavefront cover eight distinct 16-byte bank groups
+            // (plain lane order would be a 2-way conflict: lane stride 32 B).
+            const double p0 = a[g][0] * xv[g][0], p1 = a[g][1] * xv[g][1];
+            const double p2 = a[g][2] * xv[g][2], p3 = a[g][3] * xv[g][3];
+            const bool h = (tid >> 2) & 1;
+            const double2 lo = make_double2(p0, p1), hi = make_double2(p2, p3);
+            double2* dst = reinterpret_cast<double2*>(prod + e);
+            dst[h ? 1 : 0] = h ? hi : lo;
+            dst[h ? 0 : 1] = h ? lo : hi;
+          } else {
 #pragma unroll
-          for (int q = 0; q < 4; q++) prod[e + q] = a[g][q] * xv[g][q];
+            for (int q = 0; q < 4; q++) prod[e + q] = a[g][q] * xv[g][q];
+          }
         }
       }
     } else {
@@ -173,14 +268,8 @@ spmv_tile_kernel(int64_t ntiles, const P* __restrict__ indptr, const I* __restri
     }
     __syncthreads();
 
-    // ---- phase B: per-row reduction of the parked products ----------------------------------------
-    // lanes per row: 1 for short rows (sequential, reference order), else pow2 >= mean row length
-    const int64_t nnz_t = k1 - k0;
-    int gshift = 0;
-    if (nnz_t > 6 * (int64_t)nr) {
-      const int avg = (int)((nnz_t + nr - 1) / nr);
-      while ((1 << gshift) < avg && gshift < 5) gshift++;
-    }
+    // ---- reduce: per-row sums of the parked products ----------------------------------------------
+    const int gshift = lanes_per_row_shift(k1 - k0, nr);
     const int g = 1 << gshift;
     const int lig = tid & (g - 1);
     const int grp = tid >> gshift;
@@ -199,6 +288,285 @@ spmv_tile_kernel(int64_t ntiles, const P* __restrict__ indptr, const I* __restri
         y[r0 + j] = sum;
         if (DOT) dot_acc += (double)sum * (double)w[r0 + j];
       }
+    }
+  }
+
+  if (DOT) {
+    double part = block_sum<THREADS>(dot_acc, red);
+    if (grid_reduce_is_last<THREADS>(ws, part, red, &s_flag)) {
+      double total = grid_reduce_final<THREADS>(ws, red);
+      if (tid == 0) *dot_out = (V)total;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// KIND 1: TMA-staged persistent kernel (cp.async.bulk + mbarrier ring, warp-specialised).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "B2S_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra B2S_DONE;\n"
+      "bra B2S_WAIT;\n"
+      "B2S_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+// global -> shared bulk copy (TMA engine), completion counted in bytes on `bar`
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar,
+                                         uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+      ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+struct __align__(16) TileMeta {
+  long long k0, k1, kb;
+  int r0, nr, rb, pad;
+};
+
+template <typename V, typename I, typename P, int NC, int G, int STAGES>
+struct TmaLayout {
+  static constexpr int CT = NC * 32;
+  static constexpr int EPT = 16 / (int)sizeof(V);
+  static constexpr int CAP = EPT * CT * G;
+  static constexpr int T = CAP - 4;
+  static constexpr int RPN = ((T + 1 + 3 + 3) / 4) * 4;  // row-pointer slice capacity (incl. alignment slack)
+  static constexpr int COLS_B = CAP * (int)sizeof(I);
+  static constexpr int VALS_B = CAP * (int)sizeof(V);
+  static constexpr int RP_B = RPN * (int)sizeof(P);
+  static constexpr int STAGE_B = COLS_B + VALS_B + RP_B;
+  static constexpr int META_OFF = STAGES * STAGE_B;
+  static constexpr int BAR_OFF = META_OFF + STAGES * (int)sizeof(TileMeta);
+  static constexpr int TOTAL = BAR_OFF + 2 * STAGES * 8;
+};
+
+template <typename V, typename I, typename P, int NC, int G, int STAGES, int MINB, bool DOT>
+__global__ void __launch_bounds__((NC + 1) * 32, MINB)
+spmv_tma_kernel(int64_t ntiles, int64_t nrows, int64_t nnz, const P* __restrict__ indptr,
+                const I* __restrict__ indices, const V* __restrict__ vals, const V* __restrict__ x,
+                V* __restrict__ y, const PlanEntry* __restrict__ plan, const V* __restrict__ w, V* dot_out, void* ws) {
+  using LY = TmaLayout<V, I, P, NC, G, STAGES>;
+  constexpr int CT = LY::CT, EPT = LY::EPT, CAP = LY::CAP;
+  constexpr int THREADS = (NC + 1) * 32;
+  extern __shared__ __align__(128) unsigned char smem_dyn[];
+  unsigned char* smem_raw = smem_dyn;
+  TileMeta* metas = reinterpret_cast<TileMeta*>(smem_raw + LY::META_OFF);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + LY::BAR_OFF);
+  uint64_t* empty = full + STAGES;
+  __shared__ double red[32];
+  __shared__ double cred[NC];
+  __shared__ bool s_flag;
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  double dot_acc = 0.0;
+
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; s++) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], NC);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  if (warp == 0) {
+    // ===== producer: lane 0 drives the TMA engine, STAGES tiles ahead of the consumers; the other lanes
+    // walk the same loop so the warp stays converged for the block-wide barrier of the DOT epilogue =====
+    const uint64_t pol = l2_evict_first_policy();
+    const int64_t nnz4 = nnz & ~(int64_t)3;
+    const int64_t np1 = nrows + 1;
+    const int64_t rp4 = np1 & ~(int64_t)3;
+    int it = 0;
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+      const PlanEntry e0 = ld_plan(plan + t), e1 = ld_plan(plan + t + 1);
+      const int nr = e1.row - e0.row;
+      if (nr <= 0) continue;  // warp-uniform
+      if (lane == 0) {
+        const int s = it % STAGES;
+        const uint32_t par = (uint32_t)((it / STAGES) & 1);
+        mbar_wait(&empty[s], par ^ 1u);
+        unsigned char* st = smem_raw + (size_t)s * LY::STAGE_B;
+        I* scols = reinterpret_cast<I*>(st);
+        V* svals = reinterpret_cast<V*>(st + LY::COLS_B);
+        P* srp = reinterpret_cast<P*>(st + LY::COLS_B + LY::VALS_B);
+        const int64_t k0 = e0.k, k1 = e1.k;
+        const int64_t kb = k0 & ~(int64_t)3;
+        const int64_t kce = (k1 < kb + CAP) ? k1 : kb + CAP;
+        int64_t kend = (kce + 3) & ~(int64_t)3;  // bulk range [kb, kend): whole 16-byte groups inside the array
+        if (kend > nnz4) kend = nnz4;
+        if (kend < kb) kend = kb;
+        const int64_t r0 = e0.row, r1 = e1.row;
+        const int64_t rb = r0 & ~(int64_t)3;
+        int64_t rend = (r1 + 1 + 3) & ~(int64_t)3;  // row pointers [rb, rend) by bulk copy
+        if (rend > rp4) rend = rp4;
+        if (rend < rb) rend = rb;
+        TileMeta m;
+        m.k0 = k0; m.k1 = k1; m.kb = kb; m.r0 = (int)r0; m.nr = nr; m.rb = (int)rb; m.pad = 0;
+        metas[s] = m;
+        // the (at most 3) trailing elements that do not fill a 16-byte group at the very end of an array
+        for (int64_t k = kend; k < kce; k++) { scols[k - kb] = indices[k]; svals[k - kb] = vals[k]; }
+        for (int64_t r = rend; r <= r1; r++) srp[r - rb] = indptr[r];
+        const uint32_t nb = (uint32_t)(kend - kb);
+        const uint32_t nrp = (uint32_t)(rend - rb);
+        const uint32_t bytes = nb * (uint32_t)(sizeof(I) + sizeof(V)) + nrp * (uint32_t)sizeof(P);
+        if (bytes) {
+          mbar_arrive_expect_tx(&full[s], bytes);
+          if (nb) {
+            bulk_g2s(scols, indices + kb, nb * (uint32_t)sizeof(I), &full[s], pol);
+            bulk_g2s(svals, vals + kb, nb * (uint32_t)sizeof(V), &full[s], pol);
+          }
+          if (nrp) bulk_g2s(srp, indptr + rb, nrp * (uint32_t)sizeof(P), &full[s], pol);
+        } else {
+          mbar_arrive(&full[s]);
+        }
+      }
+      __syncwarp();
+      it++;
+    }
+    if (lane == 0) {
+      // sentinel: tells the consumers there is no more work
+      const int s = it % STAGES;
+      const uint32_t par = (uint32_t)((it / STAGES) & 1);
+      mbar_wait(&empty[s], par ^ 1u);
+      TileMeta m;
+      m.k0 = m.k1 = m.kb = 0; m.r0 = 0; m.nr = -1; m.rb = 0; m.pad = 0;
+      metas[s] = m;
+      mbar_arrive(&full[s]);
+    }
+    __syncwarp();
+  } else {
+    // ===== consumers =====
+    const int ctid = tid - 32;
+    const int cwarp = warp - 1;
+    int it = 0;
+    while (true) {
+      const int s = it % STAGES;
+      const uint32_t par = (uint32_t)((it / STAGES) & 1);
+      mbar_wait(&full[s], par);
+      const TileMeta m = metas[s];
+      if (m.nr < 0) break;
+      unsigned char* st = smem_raw + (size_t)s * LY::STAGE_B;
+      const I* scols = reinterpret_cast<const I*>(st);
+      V* svals = reinterpret_cast<V*>(st + LY::COLS_B);
+      const P* srp = reinterpret_cast<const P*>(st + LY::COLS_B + LY::VALS_B) + (m.r0 - m.rb);
+      const int64_t k0 = m.k0, k1 = m.k1, kb = m.kb;
+      const int nr = m.nr, r0 = m.r0;
+      const int off = (int)(k0 - kb);
+      const int64_t kce = (k1 < kb + CAP) ? k1 : kb + CAP;
+      const bool has_tail = k1 > kce;
+      const int lo = off, hi = (int)(kce - kb);  // valid slots [lo, hi)
+
+      // ---- products in place: svals[e] *= x[scols[e]] ------------------------------------------------
+      {
+        I c[G][EPT];
+        V a[G][EPT];
+#pragma unroll
+        for (int g = 0; g < G; g++) {
+          const int e = EPT * (ctid + CT * g);
+#pragma unroll
+          for (int q = 0; q < EPT; q++) { c[g][q] = scols[e + q]; a[g][q] = svals[e + q]; }
+        }
+        V xv[G][EPT];
+#pragma unroll
+        for (int g = 0; g < G; g++) {
+          const int e = EPT * (ctid + CT * g);
+#pragma unroll
+          for (int q = 0; q < EPT; q++) {
+            const bool in = (e + q >= lo) && (e + q < hi);
+            xv[g][q] = in ? __ldg(x + c[g][q]) : (V)0;
+          }
+        }
+#pragma unroll
+        for (int g = 0; g < G; g++) {
+          const int e = EPT * (ctid + CT * g);
+          if (e < hi) {
+#pragma unroll
+            for (int q = 0; q < EPT; q++) svals[e + q] = a[g][q] * xv[g][q];
+          }
+        }
+      }
+
+      // ---- tail of an over-long last row, straight from global ------------------------------------------
+      V tail_sum = (V)0;
+      if (has_tail) {
+        V ts0 = 0, ts1 = 0;
+        int64_t k = kce + ctid;
+        for (; k + CT < k1; k += 2 * CT) {
+          I c0 = ld_stream(indices + k), c1 = ld_stream(indices + k + CT);
+          V a0 = ld_stream(vals + k), a1 = ld_stream(vals + k + CT);
+          ts0 += a0 * __ldg(x + c0);
+          ts1 += a1 * __ldg(x + c1);
+        }
+        for (; k < k1; k += CT) ts0 += ld_stream(vals + k) * __ldg(x + ld_stream(indices + k));
+        double v = warp_sum((double)(ts0 + ts1));
+        named_bar_sync(2, CT);  // cred free
+        if (lane == 0) cred[cwarp] = v;
+        named_bar_sync(2, CT);
+        double tot = 0.0;
+#pragma unroll
+        for (int q = 0; q < NC; q++) tot += cred[q];
+        tail_sum = (V)tot;
+      }
+      named_bar_sync(1, CT);  // all products of this stage are parked
+
+      // ---- reduce ----------------------------------------------------------------------------------------
+      const int gshift = lanes_per_row_shift(k1 - k0, nr);
+      const int g = 1 << gshift;
+      const int lig = ctid & (g - 1);
+      const int grp = ctid >> gshift;
+      const int ngrp = CT >> gshift;
+      const V* pr = svals + off;
+      const int64_t lim = kce - k0;
+      for (int base = 0; base < nr; base += ngrp) {
+        const int j = base + grp;
+        const bool active = j < nr;
+        int sidx = 0, eidx = 0;
+        if (active) {
+          const int64_t a0 = (int64_t)srp[j] - k0, a1 = (int64_t)srp[j + 1] - k0;
+          sidx = (int)(a0 < lim ? a0 : lim);
+          eidx = (int)(a1 < lim ? a1 : lim);
+        }
+        V sum = 0;
+        for (int k = sidx + lig; k < eidx; k += g) sum += pr[k];
+        for (int o = g >> 1; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        if (active && lig == 0) {
+          if (has_tail && j == nr - 1) sum += tail_sum;
+          y[r0 + j] = sum;
+          if (DOT) dot_acc += (double)sum * (double)w[r0 + j];
+        }
+      }
+      // release the stage: generic-proxy writes (products) must be ordered before the TMA refills it
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[s]);
+      it++;
     }
   }
 
@@ -239,13 +607,23 @@ spmv_rowgroup_kernel(int64_t nrows, const P* __restrict__ indptr, const I* __res
 // ---------------------------------------------------------------------------------------------
 // Host-side launchers
 // ---------------------------------------------------------------------------------------------
-template <typename V, typename I, typename P, int THREADS, int GROUPS, int MINB, bool DOT>
-static int launch_tile(int64_t ntiles, const void* indptr, const void* indices, const void* vals,
-                       const void* x, void* y, const int32_t* plan, int vec_ok, const void* w, void* dot_out,
-                       void* ws, cudaStream_t st) {
+struct SpmvArgs {
+  int64_t ntiles, nrows, nnz;
+  const void *indptr, *indices, *vals, *x;
+  void* y;
+  const PlanEntry* plan;
+  int vec_ok;
+  const void* w;
+  void* dot_out;
+  void* ws;
+  cudaStream_t st;
+};
+
+template <typename V, typename I, typename P, int THREADS, int GROUPS, int MINB, bool SCALAR, bool DOT>
+static int launch_ldg(const SpmvArgs& a) {
   constexpr int CAP = 4 * THREADS * GROUPS;
   constexpr int T = CAP - 4;
-  auto kern = spmv_tile_kernel<V, I, P, THREADS, GROUPS, MINB, DOT>;
+  auto kern = spmv_tile_kernel<V, I, P, THREADS, GROUPS, MINB, SCALAR, DOT>;
   const size_t smem = sizeof(V) * CAP + sizeof(uint16_t) * (T + 2);
   static bool attr_done = false;  // per instantiation
   static int occ = 0;
@@ -257,30 +635,68 @@ static int launch_tile(int64_t ntiles, const void* indptr, const void* indices, 
   }
   DeviceProps pr;
   if (int rc = get_props(&pr)) return rc;
-  int64_t grid = ntiles;
+  int64_t grid = a.ntiles;
   if (DOT || g_waves > 0) {
-    const int waves = g_waves > 0 ? g_waves : 4;
+    const int waves = g_waves > 0 ? g_waves : 2;
     int64_t cap = (int64_t)pr.sm_count * occ * waves;
     if (DOT && cap > WS_MAX_PARTIALS) cap = WS_MAX_PARTIALS;
     if (grid > cap) grid = cap;
   }
   if (grid > 2147483647LL) grid = 2147483647LL;
-  kern<<<(unsigned)grid, THREADS, smem, st>>>(ntiles, (const P*)indptr, (const I*)indices, (const V*)vals,
-                                              (const V*)x, (V*)y, plan, vec_ok, (const V*)w, (V*)dot_out, ws);
+  kern<<<(unsigned)grid, THREADS, smem, a.st>>>(a.ntiles, (const P*)a.indptr, (const I*)a.indices, (const V*)a.vals,
+                                                (const V*)a.x, (V*)a.y, a.plan, a.vec_ok, (const V*)a.w,
+                                                (V*)a.dot_out, a.ws);
   B2S_LAUNCH_CHECK();
   return B2S_OK;
 }
 
+template <typename V, typename I, typename P, int NC, int G, int STAGES, int MINB, bool DOT>
+static int launch_tma(const SpmvArgs& a) {
+  using LY = TmaLayout<V, I, P, NC, G, STAGES>;
+  constexpr int THREADS = (NC + 1) * 32;
+  auto kern = spmv_tma_kernel<V, I, P, NC, G, STAGES, MINB, DOT>;
+  const size_t smem = LY::TOTAL;
+  static bool attr_done = false;
+  static int occ = 0;
+  if (!attr_done) {
+    B2S_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B2S_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, smem));
+    if (occ < 1) occ = 1;
+    attr_done = true;
+  }
+  DeviceProps pr;
+  if (int rc = get_props(&pr)) return rc;
+  int per_sm = occ;
+  if (g_waves > 0 && g_waves < occ) per_sm = g_waves;
+  int64_t grid = (int64_t)pr.sm_count * per_sm;
+  if (grid > a.ntiles) grid = a.ntiles;
+  if (DOT && grid > WS_MAX_PARTIALS) grid = WS_MAX_PARTIALS;
+  if (grid < 1) grid = 1;
+  kern<<<(unsigned)grid, THREADS, smem, a.st>>>(a.ntiles, a.nrows, a.nnz, (const P*)a.indptr, (const I*)a.indices,
+                                                (const V*)a.vals, (const V*)a.x, (V*)a.y, a.plan, (const V*)a.w,
+                                                (V*)a.dot_out, a.ws);
+  B2S_LAUNCH_CHECK();
+  return B2S_OK;
+}
+
+template <typename V, typename I, typename P, int KIND, int A, int B, int C, int D, bool DOT>
+static int launch_cfg(const SpmvArgs& a) {
+  if constexpr (KIND == 0) {
+    return launch_ldg<V, I, P, A, B, C, (D != 0), DOT>(a);
+  } else {
+    // the bulk copies need 16-byte aligned array bases; otherwise fall back to the LDG kernel's scalar path
+    // with the same tile size (same plan)
+    return launch_tma<V, I, P, A, B, C, D, DOT>(a);
+  }
+}
+
 template <typename V, typename I, typename P, bool DOT>
-static int dispatch_cfg(int cfg, int64_t ntiles, const void* indptr, const void* indices, const void* vals,
-                        const void* x, void* y, const int32_t* plan, int vec_ok, const void* w, void* dot_out,
-                        void* ws, cudaStream_t st) {
-#define B2S_CFG_CASE(ID, TH, GR, MB)                                                                     \
-  case ID:                                                                                               \
-    if constexpr (ID == 0 || (sizeof(I) == 4 && sizeof(P) == 4))                                         \
-      return launch_tile<V, I, P, TH, GR, MB, DOT>(ntiles, indptr, indices, vals, x, y, plan, vec_ok, w, \
-                                                   dot_out, ws, st);                                     \
-    else                                                                                                 \
+static int dispatch_cfg(int cfg, const SpmvArgs& a) {
+#define B2S_CFG_CASE(ID, K, A, B, C, D)                                  \
+  case ID:                                                               \
+    if constexpr (ID == 0 || (sizeof(I) == 4 && sizeof(P) == 4))         \
+      return launch_cfg<V, I, P, K, A, B, C, D, DOT>(a);                 \
+    else                                                                 \
       break;
   switch (cfg) {
     B2S_SPMV_CONFIGS(B2S_CFG_CASE)
@@ -292,13 +708,11 @@ static int dispatch_cfg(int cfg, int64_t ntiles, const void* indptr, const void*
 }
 
 template <typename V, bool DOT>
-static int dispatch_idx(int it, int pt, int cfg, int64_t ntiles, const void* indptr, const void* indices,
-                        const void* vals, const void* x, void* y, const int32_t* plan, int vec_ok,
-                        const void* w, void* dot_out, void* ws, cudaStream_t st) {
-  if (it == B2S_I32 && pt == B2S_I32) return dispatch_cfg<V, int32_t, int32_t, DOT>(cfg, ntiles, indptr, indices, vals, x, y, plan, vec_ok, w, dot_out, ws, st);
-  if (it == B2S_I32 && pt == B2S_I64) return dispatch_cfg<V, int32_t, int64_t, DOT>(cfg, ntiles, indptr, indices, vals, x, y, plan, vec_ok, w, dot_out, ws, st);
-  if (it == B2S_I64 && pt == B2S_I32) return dispatch_cfg<V, int64_t, int32_t, DOT>(cfg, ntiles, indptr, indices, vals, x, y, plan, vec_ok, w, dot_out, ws, st);
-  if (it == B2S_I64 && pt == B2S_I64) return dispatch_cfg<V, int64_t, int64_t, DOT>(cfg, ntiles, indptr, indices, vals, x, y, plan, vec_ok, w, dot_out, ws, st);
+static int dispatch_idx(int it, int pt, int cfg, const SpmvArgs& a) {
+  if (it == B2S_I32 && pt == B2S_I32) return dispatch_cfg<V, int32_t, int32_t, DOT>(cfg, a);
+  if (it == B2S_I32 && pt == B2S_I64) return dispatch_cfg<V, int32_t, int64_t, DOT>(cfg, a);
+  if (it == B2S_I64 && pt == B2S_I32) return dispatch_cfg<V, int64_t, int32_t, DOT>(cfg, a);
+  if (it == B2S_I64 && pt == B2S_I64) return dispatch_cfg<V, int64_t, int64_t, DOT>(cfg, a);
   set_error("bad index type codes it=%d pt=%d", it, pt);
   return B2S_EINVAL;
 }
@@ -354,7 +768,7 @@ using namespace b2s;
 
 extern "C" {
 
-// Debug/tuning hooks (not part of the documented ABI; used by tools/sweep scripts).
+// Debug/tuning hooks (not part of the documented ABI; used by tools/ sweep scripts).
 int b2s_spmv_set_config(int cfg, int waves) {
   if (cfg < 0 || cfg >= kNumCfgs) { set_error("config %d out of range [0,%d)", cfg, kNumCfgs); return B2S_EINVAL; }
   g_cfg = cfg;
@@ -362,34 +776,39 @@ int b2s_spmv_set_config(int cfg, int waves) {
   return B2S_OK;
 }
 int b2s_spmv_get_config(void) { return g_cfg; }
+int b2s_spmv_num_configs(void) { return kNumCfgs; }
 
 int64_t b2s_spmv_plan_tiles(int vt, int64_t nrows, int64_t nnz) {
-  (void)vt;
   if (nrows <= 0 || nnz < 0) return 0;
-  const int64_t T = cfg_T(g_cfg);
+  const int64_t T = cfg_T(g_cfg, vt);
   return (nrows + nnz + T - 1) / T;
 }
 
-int b2s_spmv_plan_build(int vt, int pt, int64_t nrows, int64_t nnz, const void* indptr, int32_t* plan,
-                        void* stream) {
+int64_t b2s_spmv_plan_bytes(int vt, int64_t nrows, int64_t nnz) {
+  return (b2s_spmv_plan_tiles(vt, nrows, nnz) + 1) * (int64_t)sizeof(PlanEntry);
+}
+
+int b2s_spmv_plan_build(int vt, int pt, int64_t nrows, int64_t nnz, const void* indptr, void* plan, void* stream) {
+  B2S_CHECK_ARG(vt == B2S_F32 || vt == B2S_F64, "bad value type code %d", vt);
   B2S_CHECK_ARG(pt == B2S_I32 || pt == B2S_I64, "bad indptr type code %d", pt);
   B2S_CHECK_ARG(nrows >= 0 && nnz >= 0, "negative dimension");
   B2S_CHECK_ARG(nrows < 2147483647LL, "nrows >= 2^31-1 is not supported");
   const int64_t ntiles = b2s_spmv_plan_tiles(vt, nrows, nnz);
   if (ntiles == 0) return B2S_OK;
   B2S_CHECK_ARG(indptr != nullptr && plan != nullptr, "indptr/plan is NULL");
+  B2S_CHECK_ARG(aligned16(plan), "plan buffer must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
-  const int64_t T = cfg_T(g_cfg);
+  const int64_t T = cfg_T(g_cfg, vt);
   const unsigned grid = (unsigned)((ntiles + 1 + 255) / 256);
-  if (pt == B2S_I32) spmv_plan_kernel<int32_t><<<grid, 256, 0, st>>>(nrows, (const int32_t*)indptr, T, ntiles, plan);
-  else               spmv_plan_kernel<int64_t><<<grid, 256, 0, st>>>(nrows, (const int64_t*)indptr, T, ntiles, plan);
+  if (pt == B2S_I32) spmv_plan_kernel<int32_t><<<grid, 256, 0, st>>>(nrows, (const int32_t*)indptr, T, ntiles, (PlanEntry*)plan);
+  else               spmv_plan_kernel<int64_t><<<grid, 256, 0, st>>>(nrows, (const int64_t*)indptr, T, ntiles, (PlanEntry*)plan);
   B2S_LAUNCH_CHECK();
   return B2S_OK;
 }
 
 static int spmv_impl(int vt, int it, int pt, int64_t nrows, int64_t ncols, int64_t nnz, const void* indptr,
                      const void* indices, const void* vals, const void* x, void* y, const void* w, void* dot_out,
-                     const int32_t* plan, void* ws, void* stream, bool dot) {
+                     const void* plan, void* ws, void* stream, bool dot) {
   if (int rc = check_common(vt, it, pt, nrows, ncols, nnz, indptr, indices, vals, x, y)) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   if (dot) {
@@ -405,26 +824,41 @@ static int spmv_impl(int vt, int it, int pt, int64_t nrows, int64_t ncols, int64
     if (vt == B2S_F32) return dispatch_rowgroup<float>(it, pt, nrows, nnz, indptr, indices, vals, x, y, st);
     return dispatch_rowgroup<double>(it, pt, nrows, nnz, indptr, indices, vals, x, y, st);
   }
-  const int64_t ntiles = b2s_spmv_plan_tiles(vt, nrows, nnz);
-  const int vec_ok = (nnz == 0) || (aligned16(indices) && aligned16(vals));
-  if (vt == B2S_F32) {
-    if (dot) return dispatch_idx<float, true>(it, pt, g_cfg, ntiles, indptr, indices, vals, x, y, plan, vec_ok, w, dot_out, ws, st);
-    return dispatch_idx<float, false>(it, pt, g_cfg, ntiles, indptr, indices, vals, x, y, plan, vec_ok, nullptr, nullptr, nullptr, st);
+  B2S_CHECK_ARG(aligned16(plan), "plan buffer must be 16-byte aligned");
+  SpmvArgs a;
+  a.ntiles = b2s_spmv_plan_tiles(vt, nrows, nnz);
+  a.nrows = nrows; a.nnz = nnz;
+  a.indptr = indptr; a.indices = indices; a.vals = vals; a.x = x; a.y = y;
+  a.plan = (const PlanEntry*)plan;
+  a.vec_ok = (nnz == 0) || (aligned16(indices) && aligned16(vals));
+  a.w = dot ? w : nullptr; a.dot_out = dot ? dot_out : nullptr; a.ws = dot ? ws : nullptr;
+  a.st = st;
+  int cfg = g_cfg;
+  if (kCfgs[cfg].kind == 1 && !(a.vec_ok && aligned16(indptr))) {
+    // TMA bulk copies need 16-byte aligned bases.  Unaligned views are served by the plan-free kernel
+    // (plus a separate dot) -- correct, just not the fast path.
+    int rc = (vt == B2S_F32) ? dispatch_rowgroup<float>(it, pt, nrows, nnz, indptr, indices, vals, x, y, st)
+                             : dispatch_rowgroup<double>(it, pt, nrows, nnz, indptr, indices, vals, x, y, st);
+    if (rc || !dot) return rc;
+    return b2s_dot(vt, nrows, w, y, dot_out, ws, stream);
   }
-  if (dot) return dispatch_idx<double, true>(it, pt, g_cfg, ntiles, indptr, indices, vals, x, y, plan, vec_ok, w, dot_out, ws, st);
-  return dispatch_idx<double, false>(it, pt, g_cfg, ntiles, indptr, indices, vals, x, y, plan, vec_ok, nullptr, nullptr, nullptr, st);
+  if (vt == B2S_F32) {
+    if (dot) return dispatch_idx<float, true>(it, pt, cfg, a);
+    return dispatch_idx<float, false>(it, pt, cfg, a);
+  }
+  if (dot) return dispatch_idx<double, true>(it, pt, cfg, a);
+  return dispatch_idx<double, false>(it, pt, cfg, a);
 }
 
 int b2s_spmv_csr(int vt, int it, int pt, int64_t nrows, int64_t ncols, int64_t nnz, const void* indptr,
-                 const void* indices, const void* vals, const void* x, void* y, const int32_t* plan,
-                 void* stream) {
+                 const void* indices, const void* vals, const void* x, void* y, const void* plan, void* stream) {
   return spmv_impl(vt, it, pt, nrows, ncols, nnz, indptr, indices, vals, x, y, nullptr, nullptr, plan, nullptr,
                    stream, false);
 }
 
 int b2s_spmv_csr_dot(int vt, int it, int pt, int64_t nrows, int64_t ncols, int64_t nnz, const void* indptr,
                      const void* indices, const void* vals, const void* x, void* y, const void* w, void* dot_out,
-                     const int32_t* plan, void* ws, void* stream) {
+                     const void* plan, void* ws, void* stream) {
   return spmv_impl(vt, it, pt, nrows, ncols, nnz, indptr, indices, vals, x, y, w, dot_out, plan, ws, stream, true);
 }
 

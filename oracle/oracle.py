@@ -72,13 +72,15 @@ def num_threads() -> int:
     return int(lib().orc_num_threads())
 
 
-def spmv(indptr, indices, data, x, omp: bool = False) -> np.ndarray:
-    """y = A @ x; A and x are first promoted to a common dtype (sparse/csr.py:493)."""
+def spmv(indptr, indices, data, x, omp: bool = False, out=None) -> np.ndarray:
+    """y = A @ x; A and x are first promoted to a common dtype (sparse/csr.py:493).
+    `out` (optional, right dtype/shape) avoids re-allocating y on every call (csr.py:509-513)."""
     indptr, indices = _c(indptr), _c(indices)
     dt = np.result_type(data.dtype, x.dtype)
     data, x = _c(data, dt), _c(x, dt)
     nrows = indptr.shape[0] - 1
-    y = np.empty(nrows, dtype=dt)
+    y = np.empty(nrows, dtype=dt) if out is None else out
+    assert y.dtype == dt and y.shape == (nrows,) and y.flags.c_contiguous
     fn = lib().orc_spmv_csr_omp if omp else lib().orc_spmv_csr
     rc = fn(_vt(dt), _wide(indices), _wide(indptr), ctypes.c_int64(nrows), _p(indptr), _p(indices),
             _p(data), _p(x), _p(y))

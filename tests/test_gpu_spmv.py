@@ -176,7 +176,7 @@ def test_unaligned_base_pointers(oracle):
     assert np.allclose(y.cpu().numpy(), oracle.spmv(indptr, indices, data, x), rtol=1e-12, atol=1e-12)
 
 
-@pytest.mark.parametrize("cfg", range(8))
+@pytest.mark.parametrize("cfg", range(16))
 @pytest.mark.parametrize("dtype", TYPES)
 def test_all_tile_configs(oracle, cfg, dtype):
     rng = np.random.default_rng(100 + cfg)
@@ -184,6 +184,7 @@ def test_all_tile_configs(oracle, cfg, dtype):
     lens = np.where(np.arange(nrows) % 501 == 0, 9000, rng.integers(0, 12, nrows))
     indptr, indices, data = _random_csr(rng, nrows, ncols, lens, dtype)
     x = rng.standard_normal(ncols).astype(dtype)
+    assert _lib.lib.b2s_spmv_num_configs() == 16
     try:
         _lib.check(_lib.lib.b2s_spmv_set_config(cfg, cfg % 3))
         A = sparse.csr_array((data, indices, indptr), shape=(nrows, ncols))

@@ -1,0 +1,20 @@
+#!/bin/bash
+# usage: tools/ncu_cfgs.sh <workload> "<cfg:waves> <cfg:waves> ..."   -> gpurun_out/ncu_cfgs_<workload>.txt
+wl=$1; shift
+mkdir -p gpurun_out
+M=gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,l1tex__data_pipe_lsu_wavefronts.sum,l1tex__data_pipe_lsu_wavefronts_mem_shared.sum,l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed,sm__warps_active.avg.pct_of_peak_sustained_active,smsp__issue_active.avg.pct_of_peak_sustained_active,sm__inst_executed.sum,l1tex__t_sector_hit_rate.pct,l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum,l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum,lts__t_sector_hit_rate.pct,smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio,smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio,smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio,smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio,smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio,smsp__average_warps_issue_stalled_wait_per_issue_active.ratio,smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio,launch__registers_per_thread,launch__occupancy_limit_registers,launch__occupancy_limit_shared_mem,launch__grid_size
+out=gpurun_out/ncu_cfgs_${wl}.txt
+for cw in $*; do
+  cfg=${cw%%:*}; waves=${cw##*:}
+  echo "=== $wl cfg $cfg waves $waves" >> $out
+  ncu --metrics $M --clock-control none -k regex:spmv_ -s 3 -c 1 --csv python tools/prof_spmv.py $wl $cfg $waves 2>/dev/null | python -c "
+import csv,sys
+rows=[r for r in csv.reader(sys.stdin) if len(r)>10]
+if len(rows)>=2:
+    h=rows[0]; 
+    for r in rows[1:]:
+        d=dict(zip(h,r))
+        print(f\"{d.get('Metric Name',''):90s} {d.get('Metric Value',''):>16s} {d.get('Metric Unit','')}\")
+" >> $out
+done
+cat $out

@@ -81,7 +81,7 @@ def copy_bw(out):
 if __name__ == "__main__":
     os.makedirs("gpurun_out", exist_ok=True)
     which = sys.argv[1:] or ["l5", "banded", "r32", "r32w", "r32f64"]
-    cfgs = list(range(8))
+    cfgs = list(range(int(_lib.lib.b2s_spmv_num_configs())))
     waves = [0, 2, 4]
     with open("gpurun_out/sweep_spmv.txt", "a") as out:
         out.write(f"# {time.ctime()} {torch.cuda.get_device_name(0)} {sparse.runtime.device_info()}\n")
@@ -95,4 +95,4 @@ if __name__ == "__main__":
         if "r32w" in which:
             run("R32 fp32 window 64K", gallery.random_fixed(10_000_000, 10_000_000, 32, np.float32, window=65536), cfgs, [0], out)
         if "r32f64" in which:
-            run("R32 fp64 random 10M", gallery.random_fixed(10_000_000, 10_000_000, 32, np.float64), [0, 1, 4], [0], out)
+            run("R32 fp64 random 10M", gallery.random_fixed(10_000_000, 10_000_000, 32, np.float64), cfgs, [0], out)
