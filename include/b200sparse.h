@@ -61,29 +61,39 @@ int64_t     b2s_ws_bytes(void);
 /* ---- CSR SpMV  (replaces CSRSpMVRowSplit::gpu_variant -> cusparseSpMV,
  *                 src/sparse/array/csr/spmv.cu:24-123,181-184) ---------------------- */
 
-/* Tiled plan: the row-block / merge-path split of the (rows + nnz) work list into
- * fixed-size tiles.  Stands in for the partitions the reference computes once per store
- * and caches (sparse/partition.py:56-128 CompressedImagePartition,
- * src/sparse/partition/fast_image_range.cu:27-54).
- * b2s_spmv_plan_tiles: number of tiles T for this matrix/value type;
- * b2s_spmv_plan_bytes: size of the plan buffer ((T+1) 16-byte entries {first nnz, first row});
- * b2s_spmv_plan_build fills it (device, async).  The buffer must be 16-byte aligned. */
+/* SpMV plan: the row-block / merge-path split of the (rows + nnz) work list into fixed-size
+ * tiles, plus the kernel choice.  Stands in for the partitions the reference computes once
+ * per store and caches (sparse/partition.py:56-128 CompressedImagePartition,
+ * src/sparse/partition/fast_image_range.cu:27-54, bounds_from_partitioned_coordinates.cu).
+ *   b2s_spmv_plan_bytes : size of the DEVICE buffer the caller provides (16-byte aligned);
+ *   b2s_spmv_plan_create: fills it, samples the column locality of the matrix (mean number
+ *       of distinct 128-byte x lines per 32 consecutive nonzeros) to choose between the
+ *       TMA-staged tile kernel and the row-group kernel, and returns a small HOST handle.
+ *       syncs the stream once (the reference's partition tasks also block, fast_image_range.cu:27-54).
+ *   b2s_spmv_plan_destroy: frees the host handle (never the device buffer).
+ *   b2s_spmv_plan_info  : out[0]=tile config id, out[1]=1 if row-group kernel, out[2]=tiles,
+ *                         out[3]=1000*lines-per-warp statistic. */
 int64_t     b2s_spmv_plan_tiles(int vt, int64_t nrows, int64_t nnz);
 int64_t     b2s_spmv_plan_bytes(int vt, int64_t nrows, int64_t nnz);
-int         b2s_spmv_plan_build(int vt, int pt, int64_t nrows, int64_t nnz,
-                                const void* indptr, void* plan, void* stream);
+int         b2s_spmv_plan_create(int vt, int it, int pt, int64_t nrows, int64_t ncols, int64_t nnz,
+                                 const void* indptr, const void* indices, void* plan_buf_dev,
+                                 void* stream, void** plan_out);
+int         b2s_spmv_plan_destroy(void* plan);
+int         b2s_spmv_plan_info(const void* plan, int64_t* out4_host);
 
 /* y = A x  (alpha=1, beta=0 as spmv.cu:79-80).  `plan` may be NULL: then a plan-free
- * row-per-lane-group kernel is used (slower on short rows).  x has ncols entries,
- * y has nrows entries; y must not alias x.  With a plan the TMA-staged persistent kernel
- * runs when indptr/indices/vals are 16-byte aligned (always true for whole allocations). */
+ * row-per-lane-group kernel is used (slower on short rows).  `plan` is the HOST handle
+ * from b2s_spmv_plan_create (it must match vt/it/pt and the dimensions).  x has ncols
+ * entries, y has nrows entries; y must not alias x.  The TMA-staged kernel needs
+ * indptr/indices/vals 16-byte aligned (true for whole allocations); otherwise the
+ * row-group kernel runs. */
 int         b2s_spmv_csr(int vt, int it, int pt, int64_t nrows, int64_t ncols, int64_t nnz,
                          const void* indptr, const void* indices, const void* vals,
                          const void* x, void* y, const void* plan, void* stream);
 
 /* y = A x and *dot_out = sum_i w[i] * y[i] in one pass (CG: q = A p, pq = p.q;
  * sparse/linalg.py:549-550 fused).  w has nrows entries (for a row shard it is the
- * shard's slice of p).  dot_out: one value of type vt on the device.  Requires plan. */
+ * shard's slice of p).  dot_out: one value of type vt on the device. */
 int         b2s_spmv_csr_dot(int vt, int it, int pt, int64_t nrows, int64_t ncols, int64_t nnz,
                              const void* indptr, const void* indices, const void* vals,
                              const void* x, void* y, const void* w, void* dot_out,

@@ -27,7 +27,10 @@ SIGNATURES = {
     "b2s_ws_bytes": (c_i64, []),
     "b2s_spmv_plan_tiles": (c_i64, [c_i32, c_i64, c_i64]),
     "b2s_spmv_plan_bytes": (c_i64, [c_i32, c_i64, c_i64]),
-    "b2s_spmv_plan_build": (c_i32, [c_i32, c_i32, c_i64, c_i64, c_vp, c_vp, c_vp]),
+    "b2s_spmv_plan_create": (c_i32, [c_i32, c_i32, c_i32, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp,
+                                     ctypes.POINTER(c_vp)]),
+    "b2s_spmv_plan_destroy": (c_i32, [c_vp]),
+    "b2s_spmv_plan_info": (c_i32, [c_vp, c_vp]),
     "b2s_spmv_csr": (c_i32, [c_i32, c_i32, c_i32, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "b2s_spmv_csr_dot": (c_i32, [c_i32, c_i32, c_i32, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp,
                                  c_vp, c_vp, c_vp, c_vp]),
@@ -48,6 +51,7 @@ SIGNATURES = {
     "b2s_spmv_set_config": (c_i32, [c_i32, c_i32]),
     "b2s_spmv_get_config": (c_i32, []),
     "b2s_spmv_num_configs": (c_i32, []),
+    "b2s_spmv_plan_set_kernel": (c_i32, [c_vp, c_i32]),
 }
 
 

@@ -29,15 +29,45 @@ def _chk_dev(*ts):
 
 
 # ---- SpMV -----------------------------------------------------------------------------------------
-def spmv_plan(indptr: torch.Tensor, nrows: int, nnz: int, vdtype) -> tuple[torch.Tensor, int]:
-    """Build the tile plan for a CSR structure. Returns (plan buffer of 16-byte entries, config id)."""
-    _chk_dev(indptr)
+class SpmvPlan:
+    """Host handle + device buffer of a b2s SpMV plan (see include/b200sparse.h)."""
+
+    def __init__(self, handle: int, buf: torch.Tensor):
+        self.handle = handle
+        self.buf = buf
+        out = (_lib.c_i64 * 4)()
+        _lib.check(L.b2s_spmv_plan_info(handle, out), "b2s_spmv_plan_info")
+        self.config, self.rowgroup, self.tiles, self.lines_per_warp = int(out[0]), bool(out[1]), int(out[2]), out[3] / 1000.0
+
+    def set_kernel(self, rowgroup: bool):
+        _lib.check(L.b2s_spmv_plan_set_kernel(self.handle, int(bool(rowgroup))), "b2s_spmv_plan_set_kernel")
+        self.rowgroup = bool(rowgroup)
+
+    def __del__(self):
+        h, self.handle = getattr(self, "handle", None), None
+        if h:
+            try:
+                L.b2s_spmv_plan_destroy(h)
+            except Exception:
+                pass
+
+
+def _plan_handle(plan):
+    return None if plan is None else plan.handle
+
+
+def spmv_plan(indptr: torch.Tensor, indices: torch.Tensor, shape, nnz: int, vdtype) -> SpmvPlan:
+    """Build the SpMV plan for a CSR structure (tile boundaries + kernel choice)."""
+    _chk_dev(indptr, indices)
     vt = vt_code(vdtype)
+    nrows, ncols = shape
     nbytes = int(L.b2s_spmv_plan_bytes(vt, nrows, nnz))
-    plan = torch.empty(max(nbytes, 16) // 4, dtype=torch.int32, device=indptr.device)
-    _lib.check(L.b2s_spmv_plan_build(vt, idx_code(indptr.dtype), nrows, nnz, ptr(indptr), ptr(plan), _stream()),
-               "b2s_spmv_plan_build")
-    return plan, int(L.b2s_spmv_get_config())
+    buf = torch.empty(max(nbytes, 16) // 4, dtype=torch.int32, device=indptr.device)
+    out = _lib.c_vp()
+    _lib.check(L.b2s_spmv_plan_create(vt, idx_code(indices.dtype), idx_code(indptr.dtype), nrows, ncols, nnz,
+                                      ptr(indptr), ptr(indices), ptr(buf), _stream(), ctypes.byref(out)),
+               "b2s_spmv_plan_create")
+    return SpmvPlan(int(out.value), buf)
 
 
 def spmv(indptr, indices, data, x, y, shape, plan=None):
@@ -48,14 +78,14 @@ def spmv(indptr, indices, data, x, y, shape, plan=None):
     assert x.dtype == data.dtype == y.dtype and x.is_contiguous() and y.is_contiguous()
     assert x.shape[0] == ncols and y.shape[0] == nrows
     _lib.check(L.b2s_spmv_csr(vt_code(data.dtype), idx_code(indices.dtype), idx_code(indptr.dtype), nrows, ncols,
-                              nnz, ptr(indptr), ptr(indices), ptr(data), ptr(x), ptr(y), ptr(plan), _stream()),
+                              nnz, ptr(indptr), ptr(indices), ptr(data), ptr(x), ptr(y), _plan_handle(plan), _stream()),
                "b2s_spmv_csr")
     return y
 
 
 def spmv_dot(indptr, indices, data, x, y, w, out, shape, plan):
     """y = A @ x and out[0] = w . y in one launch."""
-    _chk_dev(indptr, indices, data, x, y, w, out, plan)
+    _chk_dev(indptr, indices, data, x, y, w, out)
     nrows, ncols = shape
     nnz = data.shape[0]
     assert x.dtype == data.dtype == y.dtype == w.dtype == out.dtype
@@ -63,7 +93,7 @@ def spmv_dot(indptr, indices, data, x, y, w, out, shape, plan):
     ws = runtime.workspace()
     _lib.check(L.b2s_spmv_csr_dot(vt_code(data.dtype), idx_code(indices.dtype), idx_code(indptr.dtype), nrows,
                                   ncols, nnz, ptr(indptr), ptr(indices), ptr(data), ptr(x), ptr(y), ptr(w),
-                                  ptr(out), ptr(plan), ptr(ws), _stream()), "b2s_spmv_csr_dot")
+                                  ptr(out), _plan_handle(plan), ptr(ws), _stream()), "b2s_spmv_csr_dot")
     return y
 
 

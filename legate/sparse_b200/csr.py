@@ -251,9 +251,10 @@ class csr_array:
         its image partitions per store the same way, sparse/partition.py:96-120)."""
         from . import _lib
 
-        key = (self._indptr.data_ptr(), int(_lib.lib.b2s_spmv_get_config()), self.dtype.itemsize)
+        key = (self._indptr.data_ptr(), self._indices.data_ptr(), int(_lib.lib.b2s_spmv_get_config()),
+               self.dtype.itemsize, self.nnz)
         if self._plan is None or self._plan_key != key:
-            self._plan, _ = _ops.spmv_plan(self._indptr, self.shape[0], self.nnz, self.dtype)
+            self._plan = _ops.spmv_plan(self._indptr, self._indices, self.shape, self.nnz, self.dtype)
             self._plan_key = key
         return self._plan
 

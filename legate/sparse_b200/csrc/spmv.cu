@@ -65,9 +65,12 @@ static const TileCfgRt kCfgs[] = {
 #undef X
 };
 static constexpr int kNumCfgs = sizeof(kCfgs) / sizeof(kCfgs[0]);
-static int g_cfg = 0;    // selected configuration (b2s_spmv_set_config)
+static int g_cfg = -1;   // -1 = automatic (by value type); >= 0 forced by b2s_spmv_set_config
 static int g_waves = 0;  // LDG kind: 0 = one tile per CTA; >0 = grid-stride with waves*SMs*occupancy CTAs
-                         // TMA kind: CTAs per SM multiplier override (0 = occupancy)
+                         // TMA kind: CTAs per SM cap (0 = occupancy)
+static constexpr int kDefaultCfgF64 = 0;   // 4 consumer warps x 4 groups, 2 stages, 6 CTAs/SM (CAP 1024)
+static constexpr int kDefaultCfgF32 = 6;   // 4 consumer warps x 3 groups, 2 stages, 8 CTAs/SM (CAP 1536)
+static inline int resolve_cfg(int vt) { return g_cfg >= 0 ? g_cfg : (vt == B2S_F32 ? kDefaultCfgF32 : kDefaultCfgF64); }
 
 static inline int cfg_cap(int c, int vt) {
   const TileCfgRt& k = kCfgs[c];
@@ -113,18 +116,13 @@ __device__ __forceinline__ PlanEntry ld_plan(const PlanEntry* p) {
 
 // lanes-per-row rule shared by both kernels
 __device__ __forceinline__ int lanes_per_row_shift(int64_t nnz_t, int nr) {
-  // lanes per row g = 2^gshift, uniform over the tile.  With row length L the parked products of
-  // consecutive rows sit L apart, so g = (largest power of two dividing L) makes the per-row reads
-  // bank-conflict free; g is then raised until no lane loops more than ~12 times.  g = 1 walks a row
-  // sequentially, i.e. in the reference's accumulation order (spmv.cc:36-44).
+  // lanes per row g = 2^gshift, uniform over the tile: the largest power of two <= L/6 (L = mean row
+  // length), i.e. every lane adds ~6..12 parked products sequentially before the shuffle tree.  Short rows
+  // (L < 12) get g = 1: a plain sequential walk in the reference's accumulation order (spmv.cc:36-44).
+  // (One lane per element -- g = L -- is instruction-bound: ~40 instructions per 32 nonzeros.)
   int gshift = 0;
   const int L = (int)((nnz_t + nr - 1) / nr);
-  if (L > 0) {
-    if (nnz_t == (int64_t)L * nr) {
-      while (gshift < 5 && ((L >> gshift) & 1) == 0) gshift++;
-    }
-    while (gshift < 5 && (L >> gshift) > 12) gshift++;
-  }
+  while (gshift < 5 && (L >> (gshift + 1)) >= 6) gshift++;
   return gshift;
 }
 
@@ -694,7 +692,7 @@ template <typename V, typename I, typename P, bool DOT>
 static int dispatch_cfg(int cfg, const SpmvArgs& a) {
 #define B2S_CFG_CASE(ID, K, A, B, C, D)                                  \
   case ID:                                                               \
-    if constexpr (ID == 0 || (sizeof(I) == 4 && sizeof(P) == 4))         \
+    if constexpr (ID == kDefaultCfgF64 || ID == kDefaultCfgF32 || (sizeof(I) == 4 && sizeof(P) == 4)) \
       return launch_cfg<V, I, P, K, A, B, C, D, DOT>(a);                 \
     else                                                                 \
       break;
@@ -764,14 +762,48 @@ static int check_common(int vt, int it, int pt, int64_t nrows, int64_t ncols, in
 
 }  // namespace b2s
 
+namespace b2s {
+
+// Column-locality statistic: mean number of distinct 128-byte lines of x touched by 32 consecutive
+// nonzeros (one warp-wide gather), sampled at up to 4096 evenly spaced positions.  ~5 for stencils,
+// 32 for uniformly random columns.  Scattered matrices are L1-tag-bound and want many resident warps,
+// so they are routed to the row-group kernel instead of the staged-tile kernel.
+template <typename I>
+__global__ void __launch_bounds__(256)
+spmv_locality_kernel(int64_t nnz, const I* __restrict__ indices, int elem_shift, int64_t nsamples,
+                     unsigned long long* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (w >= nsamples) return;
+  const int64_t p = (nnz - 32) * w / nsamples;
+  const long long line = ((long long)indices[p + lane] << elem_shift) >> 7;
+  const unsigned m = __match_any_sync(0xffffffffu, line);
+  const unsigned leaders = __ballot_sync(0xffffffffu, (__ffs(m) - 1) == lane);
+  if (lane == 0) atomicAdd(out, (unsigned long long)__popc(leaders));
+}
+
+struct PlanHandle {
+  uint32_t magic;
+  int vt, it, pt;
+  int cfg;          // tile configuration the device plan was built for
+  int use_rowgroup; // 1: matrix judged scattered -> plan-free row-group kernel
+  int64_t nrows, ncols, nnz, ntiles;
+  double lines_per_warp;
+  const PlanEntry* dev;
+};
+static constexpr uint32_t kPlanMagic = 0xB2005A17u;
+
+}  // namespace b2s
+
 using namespace b2s;
 
 extern "C" {
 
 // Debug/tuning hooks (not part of the documented ABI; used by tools/ sweep scripts).
+// cfg < 0 restores automatic selection.
 int b2s_spmv_set_config(int cfg, int waves) {
-  if (cfg < 0 || cfg >= kNumCfgs) { set_error("config %d out of range [0,%d)", cfg, kNumCfgs); return B2S_EINVAL; }
-  g_cfg = cfg;
+  if (cfg >= kNumCfgs) { set_error("config %d out of range [0,%d)", cfg, kNumCfgs); return B2S_EINVAL; }
+  g_cfg = cfg < 0 ? -1 : cfg;
   g_waves = waves < 0 ? 0 : waves;
   return B2S_OK;
 }
@@ -780,29 +812,83 @@ int b2s_spmv_num_configs(void) { return kNumCfgs; }
 
 int64_t b2s_spmv_plan_tiles(int vt, int64_t nrows, int64_t nnz) {
   if (nrows <= 0 || nnz < 0) return 0;
-  const int64_t T = cfg_T(g_cfg, vt);
+  const int64_t T = cfg_T(resolve_cfg(vt), vt);
   return (nrows + nnz + T - 1) / T;
 }
 
 int64_t b2s_spmv_plan_bytes(int vt, int64_t nrows, int64_t nnz) {
-  return (b2s_spmv_plan_tiles(vt, nrows, nnz) + 1) * (int64_t)sizeof(PlanEntry);
+  // (ntiles + 1) entries + one 16-byte slot for the locality statistic
+  return (b2s_spmv_plan_tiles(vt, nrows, nnz) + 2) * (int64_t)sizeof(PlanEntry);
 }
 
-int b2s_spmv_plan_build(int vt, int pt, int64_t nrows, int64_t nnz, const void* indptr, void* plan, void* stream) {
-  B2S_CHECK_ARG(vt == B2S_F32 || vt == B2S_F64, "bad value type code %d", vt);
-  B2S_CHECK_ARG(pt == B2S_I32 || pt == B2S_I64, "bad indptr type code %d", pt);
-  B2S_CHECK_ARG(nrows >= 0 && nnz >= 0, "negative dimension");
-  B2S_CHECK_ARG(nrows < 2147483647LL, "nrows >= 2^31-1 is not supported");
-  const int64_t ntiles = b2s_spmv_plan_tiles(vt, nrows, nnz);
-  if (ntiles == 0) return B2S_OK;
-  B2S_CHECK_ARG(indptr != nullptr && plan != nullptr, "indptr/plan is NULL");
-  B2S_CHECK_ARG(aligned16(plan), "plan buffer must be 16-byte aligned");
+int b2s_spmv_plan_create(int vt, int it, int pt, int64_t nrows, int64_t ncols, int64_t nnz, const void* indptr,
+                         const void* indices, void* plan_buf, void* stream, void** plan_out) {
+  B2S_CHECK_ARG(plan_out != nullptr, "plan_out is NULL");
+  *plan_out = nullptr;
+  if (int rc = check_common(vt, it, pt, nrows, ncols, nnz, indptr, indices, indices, plan_out, plan_out)) return rc;
+  B2S_CHECK_ARG(plan_buf != nullptr && aligned16(plan_buf), "plan buffer must be non-NULL and 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
-  const int64_t T = cfg_T(g_cfg, vt);
-  const unsigned grid = (unsigned)((ntiles + 1 + 255) / 256);
-  if (pt == B2S_I32) spmv_plan_kernel<int32_t><<<grid, 256, 0, st>>>(nrows, (const int32_t*)indptr, T, ntiles, (PlanEntry*)plan);
-  else               spmv_plan_kernel<int64_t><<<grid, 256, 0, st>>>(nrows, (const int64_t*)indptr, T, ntiles, (PlanEntry*)plan);
-  B2S_LAUNCH_CHECK();
+  const int cfg = resolve_cfg(vt);
+  const int64_t ntiles = b2s_spmv_plan_tiles(vt, nrows, nnz);
+  PlanEntry* dev = (PlanEntry*)plan_buf;
+  unsigned long long* stat = (unsigned long long*)(dev + ntiles + 1);
+  double lines = 0.0;
+  if (ntiles > 0) {
+    const int64_t T = cfg_T(cfg, vt);
+    const unsigned grid = (unsigned)((ntiles + 1 + 255) / 256);
+    if (pt == B2S_I32) spmv_plan_kernel<int32_t><<<grid, 256, 0, st>>>(nrows, (const int32_t*)indptr, T, ntiles, dev);
+    else               spmv_plan_kernel<int64_t><<<grid, 256, 0, st>>>(nrows, (const int64_t*)indptr, T, ntiles, dev);
+    B2S_LAUNCH_CHECK();
+    if (nnz >= 64) {
+      int64_t ns = nnz / 32;
+      if (ns > 4096) ns = 4096;
+      B2S_CUDA(cudaMemsetAsync(stat, 0, 16, st));
+      const unsigned g2 = (unsigned)((ns * 32 + 255) / 256);
+      const int shift = vt == B2S_F32 ? 2 : 3;
+      if (it == B2S_I32) spmv_locality_kernel<int32_t><<<g2, 256, 0, st>>>(nnz, (const int32_t*)indices, shift, ns, stat);
+      else               spmv_locality_kernel<int64_t><<<g2, 256, 0, st>>>(nnz, (const int64_t*)indices, shift, ns, stat);
+      B2S_LAUNCH_CHECK();
+      unsigned long long total = 0;
+      B2S_CUDA(cudaMemcpyAsync(&total, stat, sizeof(total), cudaMemcpyDeviceToHost, st));
+      B2S_CUDA(cudaStreamSynchronize(st));
+      lines = (double)total / (double)ns;
+    }
+  }
+  PlanHandle* h = new PlanHandle();
+  h->magic = kPlanMagic;
+  h->vt = vt; h->it = it; h->pt = pt; h->cfg = cfg;
+  h->use_rowgroup = lines > 16.0 ? 1 : 0;
+  h->nrows = nrows; h->ncols = ncols; h->nnz = nnz; h->ntiles = ntiles;
+  h->lines_per_warp = lines;
+  h->dev = dev;
+  *plan_out = h;
+  return B2S_OK;
+}
+
+int b2s_spmv_plan_destroy(void* plan) {
+  PlanHandle* h = (PlanHandle*)plan;
+  if (!h) return B2S_OK;
+  B2S_CHECK_ARG(h->magic == kPlanMagic, "not a b2s spmv plan handle");
+  h->magic = 0;
+  delete h;
+  return B2S_OK;
+}
+
+/* out[0] = tile config, out[1] = 1 if the row-group kernel is selected, out[2] = ntiles,
+ * out[3] = 1000 * mean distinct x lines per 32 consecutive nonzeros */
+int b2s_spmv_plan_info(const void* plan, int64_t* out4_host) {
+  const PlanHandle* h = (const PlanHandle*)plan;
+  B2S_CHECK_ARG(h && h->magic == kPlanMagic && out4_host, "bad plan handle / out pointer");
+  out4_host[0] = h->cfg; out4_host[1] = h->use_rowgroup; out4_host[2] = h->ntiles;
+  out4_host[3] = (int64_t)(h->lines_per_warp * 1000.0);
+  return B2S_OK;
+}
+
+/* force the kernel family for a plan: 0 = staged tiles, 1 = row-group (tools / tests) */
+int b2s_spmv_plan_set_kernel(void* plan, int use_rowgroup) {
+  PlanHandle* h = (PlanHandle*)plan;
+  B2S_CHECK_ARG(h && h->magic == kPlanMagic, "bad plan handle");
+  h->use_rowgroup = use_rowgroup ? 1 : 0;
   return B2S_OK;
 }
 
@@ -812,7 +898,6 @@ static int spmv_impl(int vt, int it, int pt, int64_t nrows, int64_t ncols, int64
   if (int rc = check_common(vt, it, pt, nrows, ncols, nnz, indptr, indices, vals, x, y)) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   if (dot) {
-    B2S_CHECK_ARG(plan != nullptr, "b2s_spmv_csr_dot requires a plan");
     B2S_CHECK_ARG(ws != nullptr && dot_out != nullptr, "ws/dot_out is NULL");
     B2S_CHECK_ARG(nrows == 0 || w != nullptr, "w is NULL");
   }
@@ -820,34 +905,35 @@ static int spmv_impl(int vt, int it, int pt, int64_t nrows, int64_t ncols, int64
     if (dot) B2S_CUDA(cudaMemsetAsync(dot_out, 0, vt == B2S_F32 ? 4 : 8, st));
     return B2S_OK;
   }
-  if (plan == nullptr) {
-    if (vt == B2S_F32) return dispatch_rowgroup<float>(it, pt, nrows, nnz, indptr, indices, vals, x, y, st);
-    return dispatch_rowgroup<double>(it, pt, nrows, nnz, indptr, indices, vals, x, y, st);
+  const PlanHandle* h = (const PlanHandle*)plan;
+  if (h) {
+    B2S_CHECK_ARG(h->magic == kPlanMagic, "plan is not a handle from b2s_spmv_plan_create");
+    B2S_CHECK_ARG(h->vt == vt && h->it == it && h->pt == pt && h->nrows == nrows && h->ncols == ncols && h->nnz == nnz,
+                  "plan was created for a different matrix (types or dimensions differ)");
   }
-  B2S_CHECK_ARG(aligned16(plan), "plan buffer must be 16-byte aligned");
-  SpmvArgs a;
-  a.ntiles = b2s_spmv_plan_tiles(vt, nrows, nnz);
-  a.nrows = nrows; a.nnz = nnz;
-  a.indptr = indptr; a.indices = indices; a.vals = vals; a.x = x; a.y = y;
-  a.plan = (const PlanEntry*)plan;
-  a.vec_ok = (nnz == 0) || (aligned16(indices) && aligned16(vals));
-  a.w = dot ? w : nullptr; a.dot_out = dot ? dot_out : nullptr; a.ws = dot ? ws : nullptr;
-  a.st = st;
-  int cfg = g_cfg;
-  if (kCfgs[cfg].kind == 1 && !(a.vec_ok && aligned16(indptr))) {
-    // TMA bulk copies need 16-byte aligned bases.  Unaligned views are served by the plan-free kernel
-    // (plus a separate dot) -- correct, just not the fast path.
+  const bool aligned = (nnz == 0) || (aligned16(indices) && aligned16(vals));
+  bool rowgroup = (h == nullptr) || h->use_rowgroup;
+  if (h && !rowgroup && kCfgs[h->cfg].kind == 1 && !(aligned && aligned16(indptr))) rowgroup = true;  // TMA needs 16-byte aligned bases
+  if (rowgroup) {
     int rc = (vt == B2S_F32) ? dispatch_rowgroup<float>(it, pt, nrows, nnz, indptr, indices, vals, x, y, st)
                              : dispatch_rowgroup<double>(it, pt, nrows, nnz, indptr, indices, vals, x, y, st);
     if (rc || !dot) return rc;
     return b2s_dot(vt, nrows, w, y, dot_out, ws, stream);
   }
+  SpmvArgs a;
+  a.ntiles = h->ntiles;
+  a.nrows = nrows; a.nnz = nnz;
+  a.indptr = indptr; a.indices = indices; a.vals = vals; a.x = x; a.y = y;
+  a.plan = h->dev;
+  a.vec_ok = aligned ? 1 : 0;
+  a.w = dot ? w : nullptr; a.dot_out = dot ? dot_out : nullptr; a.ws = dot ? ws : nullptr;
+  a.st = st;
   if (vt == B2S_F32) {
-    if (dot) return dispatch_idx<float, true>(it, pt, cfg, a);
-    return dispatch_idx<float, false>(it, pt, cfg, a);
+    if (dot) return dispatch_idx<float, true>(it, pt, h->cfg, a);
+    return dispatch_idx<float, false>(it, pt, h->cfg, a);
   }
-  if (dot) return dispatch_idx<double, true>(it, pt, cfg, a);
-  return dispatch_idx<double, false>(it, pt, cfg, a);
+  if (dot) return dispatch_idx<double, true>(it, pt, h->cfg, a);
+  return dispatch_idx<double, false>(it, pt, h->cfg, a);
 }
 
 int b2s_spmv_csr(int vt, int it, int pt, int64_t nrows, int64_t ncols, int64_t nnz, const void* indptr,

@@ -135,7 +135,8 @@ def test_structures_vs_oracle(oracle, structure, dtype, wide):
     d_val = torch.from_numpy(data).cuda()
     d_x = torch.from_numpy(x).cuda()
     y = torch.full((nrows,), float("nan"), dtype=d_val.dtype, device="cuda")
-    plan, _ = _ops.spmv_plan(d_ptr, nrows, int(indptr[-1]), dtype)
+    plan = _ops.spmv_plan(d_ptr, d_idx, (nrows, ncols), int(indptr[-1]), dtype)
+    plan.set_kernel(False)  # exercise the staged-tile kernel even when the matrix is judged scattered
     _ops.spmv(d_ptr, d_idx, d_val, d_x, y, (nrows, ncols), plan=plan)
     ref = oracle.spmv(indptr, indices, data, x)
     absx = oracle.spmv(indptr, indices, np.abs(data).astype(np.float64), np.abs(x).astype(np.float64))
@@ -171,7 +172,7 @@ def test_unaligned_base_pointers(oracle):
     assert d_idx.data_ptr() % 16 != 0
     d_ptr = torch.from_numpy(indptr).to("cuda", torch.int32)
     y = torch.empty(nrows, dtype=torch.float64, device="cuda")
-    plan, _ = _ops.spmv_plan(d_ptr, nrows, int(indptr[-1]), np.float64)
+    plan = _ops.spmv_plan(d_ptr, d_idx, (nrows, ncols), int(indptr[-1]), np.float64)
     _ops.spmv(d_ptr, d_idx, d_val, torch.from_numpy(x).cuda(), y, (nrows, ncols), plan=plan)
     assert np.allclose(y.cpu().numpy(), oracle.spmv(indptr, indices, data, x), rtol=1e-12, atol=1e-12)
 
@@ -188,9 +189,12 @@ def test_all_tile_configs(oracle, cfg, dtype):
     try:
         _lib.check(_lib.lib.b2s_spmv_set_config(cfg, cfg % 3))
         A = sparse.csr_array((data, indices, indptr), shape=(nrows, ncols))
+        plan = A._get_plan()
+        assert plan.config == cfg
+        plan.set_kernel(False)
         y = A @ x
     finally:
-        _lib.check(_lib.lib.b2s_spmv_set_config(0, 0))
+        _lib.check(_lib.lib.b2s_spmv_set_config(-1, 0))
     ref = oracle.spmv(indptr, indices, data, x)
     absx = oracle.spmv(indptr, indices, np.abs(data).astype(np.float64), np.abs(x).astype(np.float64))
     assert _close_rowscaled(y, ref, absx, dtype)
@@ -244,3 +248,34 @@ def test_large_laplacian_properties():
     for r in rows[:1000]:
         lo, hi = indptr[r], indptr[r + 1]
         assert abs(float(Ax[r]) - float(np.dot(data[lo:hi], xh[indices[lo:hi]]))) <= 1e-8 * abs(data[lo:hi]).max()
+
+
+def test_plan_kernel_choice_by_column_locality():
+    """Stencil / banded matrices go to the TMA-staged tile kernel, uniformly random columns to the
+    row-group kernel (they are L1-tag-bound: 32 distinct x lines per warp-wide gather)."""
+    from legate.sparse_b200 import gallery
+
+    L5 = gallery.laplacian_5pt(300, 300, np.float64)
+    B = gallery.banded(100000, 11, np.float64)
+    R = gallery.random_fixed(100000, 100000, 32, np.float32)
+    pl, pb, pr = L5._get_plan(), B._get_plan(), R._get_plan()
+    assert not pl.rowgroup and pl.lines_per_warp < 12
+    assert not pb.rowgroup and pb.lines_per_warp < 6
+    assert pr.rowgroup and pr.lines_per_warp > 28
+    # both kernel families give the same answer on the same plan
+    x = torch.rand(100000, dtype=torch.float32, device="cuda")
+    y1 = R @ x
+    pr.set_kernel(False)
+    y2 = R @ x
+    assert torch.allclose(y1, y2, rtol=1e-4, atol=1e-4)
+
+
+def test_plan_rejects_mismatched_matrix():
+    from legate.sparse_b200 import gallery
+
+    A = gallery.banded(1000, 5, np.float64)
+    B = gallery.banded(2000, 5, np.float64)
+    x = torch.rand(2000, dtype=torch.float64, device="cuda")
+    y = torch.empty(2000, dtype=torch.float64, device="cuda")
+    with pytest.raises(_lib.B200SparseError, match="different matrix"):
+        _ops.spmv(B.indptr, B.indices, B.data, x, y, B.shape, plan=A._get_plan())

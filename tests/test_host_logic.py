@@ -38,7 +38,7 @@ def test_abi_version_and_sizes():
     assert _lib.lib.b2s_spmv_plan_tiles(1, 0, 0) == 0
     t = _lib.lib.b2s_spmv_plan_tiles(1, 1000, 5000)
     assert t >= 1 and t == -(-6000 // 1020)  # default config: CAP 1024 for fp64
-    assert _lib.lib.b2s_spmv_plan_bytes(1, 1000, 5000) == (t + 1) * 16
+    assert _lib.lib.b2s_spmv_plan_bytes(1, 1000, 5000) == (t + 2) * 16
 
 
 def test_abi_argument_validation_without_gpu():

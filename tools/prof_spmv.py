@@ -20,8 +20,8 @@ elif wl == "r32":
     A = gallery.random_fixed(10_000_000, 10_000_000, 32, np.float32)
 else:
     raise SystemExit("unknown workload")
-_lib.check(_lib.lib.b2s_spmv_set_config(cfg, waves))
-plan = None if cfg < 0 else _ops.spmv_plan(A.indptr, A.shape[0], A.nnz, A.dtype)[0]
+_lib.check(_lib.lib.b2s_spmv_set_config(cfg, waves))  # cfg < 0: automatic
+plan = A._get_plan()
 x = torch.rand(A.shape[1], dtype=A.data.dtype, device="cuda")
 y = torch.empty(A.shape[0], dtype=A.data.dtype, device="cuda")
 for _ in range(iters):
