@@ -70,6 +70,24 @@ def laplacian_host(n1, n2):
     return indptr, cols[valid].astype(np.int32), vals[valid], N
 
 
+def calibrate_threads(orc, indptr, indices, data, x, y):
+    """Pick the OpenMP thread count that runs the CPU SpMV fastest on this host (all logical CPUs is not always
+    best: SMT siblings / cgroup quotas).  Returns the chosen count; the oracle is left configured with it."""
+    ncpu = os.cpu_count() or 1
+    cands = sorted({max(1, ncpu), max(1, ncpu // 2), max(1, ncpu // 4), min(ncpu, 8)}, reverse=True)
+    best, best_t = cands[0], float("inf")
+    for n in cands:
+        orc.set_num_threads(n)
+        orc.spmv(indptr, indices, data, x, omp=True, out=y)
+        t = time.perf_counter()
+        orc.spmv(indptr, indices, data, x, omp=True, out=y)
+        dt = time.perf_counter() - t
+        if dt < best_t:
+            best, best_t = n, dt
+    orc.set_num_threads(best)
+    return best
+
+
 def cpu_spmv_rate(budget_s, indptr=None, indices=None, data=None, min_reps=3, max_reps=400):
     """OpenMP CPU oracle (reference spmv_omp.cc:36-45 restated) on the L5 matrix; returns GFLOP/s etc."""
     from oracle import oracle as orc
@@ -81,6 +99,7 @@ def cpu_spmv_rate(budget_s, indptr=None, indices=None, data=None, min_reps=3, ma
     x = np.random.default_rng(0).random(n)
     y = np.zeros(n)
     orc.spmv(indptr, indices, data, x, omp=True, out=y)  # warm-up (page faults, thread pool)
+    calibrate_threads(orc, indptr, indices, data, x, y)
     reps, t0 = 0, time.perf_counter()
     times = []
     while reps < max_reps and (reps < min_reps or time.perf_counter() - t0 < budget_s):
@@ -161,6 +180,8 @@ def run_reference(args):
     x = np.random.default_rng(0).random(n)
     nnz = int(indptr[-1])
     y = np.zeros(n)
+    orc.spmv(indptr, indices, data, x, omp=True, out=y)
+    calibrate_threads(orc, indptr, indices, data, x, y)
     tw = time.perf_counter()
     for _ in range(max(args.warmup, 1)):
         orc.spmv(indptr, indices, data, x, omp=True, out=y)
@@ -336,10 +357,11 @@ def run_gpu(args):
                    "index_bytes": 4, "indptr_bytes": 4, "partition": f"1-D row blocks x{world}",
                    "x_exchange": A.exchange_mode, "halo_elems_per_rank": A.recv_elems,
                    "l2": "inputs larger than L2 (matrix stream 600 MB + x/y 160 MB per step vs 126 MB L2); no flush",
-                   "tile_config": int(sparse._lib.lib.b2s_spmv_get_config())},
+                   "tile_config": int(spmv_plan.config), "kernel_family": "rowgroup" if spmv_plan.rowgroup else "tma-tiles",
+                   "x_lines_per_warp_gather": spmv_plan.lines_per_warp},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": B,
-                     "kernel": "b2s::spmv_tile_kernel", "kernel_ms": kern_ms},
+                     "kernel": "b2s::spmv_tma_kernel<double,int,int,4,4,2,6>", "kernel_ms": kern_ms},
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_gf, "unit": "GFLOP/s", "h2d_bytes_per_step": int(x_host.numel() * 8) * world,
                 "d2h_bytes_per_step": int(y_host.numel() * 8) * world, "steps": e2e_steps,

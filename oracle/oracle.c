@@ -44,6 +44,15 @@ static inline void st_idx(void* p, int wide, int64_t i, int64_t v)
 
 int orc_version(void) { return 1; }
 
+void orc_set_num_threads(int n)
+{
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 int orc_num_threads(void)
 {
 #ifdef _OPENMP

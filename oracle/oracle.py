@@ -72,6 +72,10 @@ def num_threads() -> int:
     return int(lib().orc_num_threads())
 
 
+def set_num_threads(n: int) -> None:
+    lib().orc_set_num_threads(int(n))
+
+
 def spmv(indptr, indices, data, x, omp: bool = False, out=None) -> np.ndarray:
     """y = A @ x; A and x are first promoted to a common dtype (sparse/csr.py:493).
     `out` (optional, right dtype/shape) avoids re-allocating y on every call (csr.py:509-513)."""
