@@ -225,6 +225,14 @@ class dist_csr_array:
         allreduce_scalar(dot_out, self.group)
         return out
 
+    # -- exchange / all-reduce interface used by linalg._cg_fused_loop -------------------------------------------
+    def new_p(self, n, like):
+        full = self.new_full_vector(numpy_dtype(like.dtype))
+        return full, self.local_view(full)
+
+    def allreduce(self, t):
+        return allreduce_scalar(t, self.group)
+
     def matvec_global(self, x_global):
         """Convenience for tests: replicated x in, replicated y out (numpy)."""
         full = self.scatter_vector(np.asarray(x_global, dtype=self.dtype))
@@ -251,9 +259,11 @@ def gather_vector(v_local: torch.Tensor, plan: RowBlockPlan, rank: int, group=No
 
 
 def cg(A: dist_csr_array, b_local, x0_local=None, tol=1e-08, maxiter=None, callback=None, conv_test_iters=25):
-    """Row-sharded conjugate gradient: the fused loop of linalg._cg_fused with the SpMV input exchanged
+    """Row-sharded conjugate gradient: the fused loop of linalg._cg_fused_loop with the SpMV input exchanged
     per iteration and the two inner products all-reduced.  Same semantics as linalg.cg (absolute tol,
     test every conv_test_iters, returns (x_local, iters)); every rank returns its shard of x."""
+    from .linalg import _cg_fused_loop
+
     assert A.shape[0] == A.shape[1]
     n_global = A.shape[0]
     if maxiter is None:
@@ -263,38 +273,4 @@ def cg(A: dist_csr_array, b_local, x0_local=None, tol=1e-08, maxiter=None, callb
     b = to_device(b_local, dtype=dt).reshape(-1)
     n = b.shape[0]
     x = torch.zeros(n, dtype=b.dtype, device=b.device) if x0_local is None else to_device(x0_local, dtype=dt, copy=True)
-    p_full = A.new_full_vector(dt)
-    p = A.local_view(p_full)
-    q = torch.empty(n, dtype=b.dtype, device=b.device)
-    plan = Al._get_plan()
-
-    def spmv_into(full, out):
-        A.exchange(full)
-        _ops.spmv(Al.indptr, Al.indices, Al.data, full[: Al.shape[1]], out, Al.shape, plan=plan)
-
-    # r = b - A x
-    p.copy_(x)
-    spmv_into(p_full, q)
-    r = b - q
-    rho = _ops.dot(r, r)
-    allreduce_scalar(rho, A.group)
-    rho_next = torch.empty_like(rho)
-    pq = torch.empty_like(rho)
-    iters = 0
-    while iters < maxiter:
-        if iters == 0:
-            p.copy_(r)
-        else:
-            _ops.axpby(p, r, rho_next, rho, isalpha=False, negate=False)
-            rho, rho_next = rho_next, rho
-        A.exchange(p_full)
-        _ops.spmv_dot(Al.indptr, Al.indices, Al.data, p_full[: Al.shape[1]], q, p, pq, Al.shape, plan)
-        allreduce_scalar(pq, A.group)
-        _ops.cg_update_xr(x, r, p, q, rho, pq, rho_next)
-        allreduce_scalar(rho_next, A.group)
-        iters += 1
-        if callback is not None:
-            callback(x)
-        if (iters % conv_test_iters == 0 or iters == (maxiter - 1)) and float(rho_next[0]) ** 0.5 < tol:
-            break
-    return x, iters
+    return _cg_fused_loop(Al, A, b, x, tol, maxiter, callback, conv_test_iters, True)

@@ -254,46 +254,138 @@ def _cg_generic(A, b, x, tol, maxiter, M, callback, conv_test_iters, on_device):
     return x, iters
 
 
-def _cg_fused(A: csr_array, b, x, tol, maxiter, callback, conv_test_iters, on_device):
-    """Same recurrence, 3 launches per iteration.
+class _LocalComm:
+    """Single-GPU stand-in for the exchange/all-reduce interface of dist.dist_csr_array."""
 
-    With M = I: z = r, rho = r.r.  Per iteration
-        q = A p ; pq = p.q                    (b2s_spmv_csr_dot)
-        x += (rho/pq) p ; r -= (rho/pq) q ; rho_next = r.r   (b2s_cg_update_xr)
-        p = r + (rho_next/rho) p              (b2s_axpby, isalpha=False)   [next iteration's first op]
-    ||r|| for the convergence test is sqrt(rho_next) -- no extra pass.
-    """
-    n = b.shape[0]
+    def new_p(self, n, like):
+        p = torch.empty(n, dtype=like.dtype, device=like.device)
+        return p, p
+
+    def exchange(self, p_full):
+        return None
+
+    def allreduce(self, t):
+        return t
+
+
+def _cg_fused(A: csr_array, b, x, tol, maxiter, callback, conv_test_iters, on_device):
     dt = numpy_dtype(b.dtype)
     Ad = A._promoted(dt) if A.dtype != dt else A
     if numpy_dtype(Ad.dtype) != dt:
         raise NotImplementedError("cg: matrix dtype wider than the work vectors")
+    return _cg_fused_loop(Ad, _LocalComm(), b, x, tol, maxiter, callback, conv_test_iters, on_device)
+
+
+def _cg_fused_loop(Ad: csr_array, comm, b, x, tol, maxiter, callback, conv_test_iters, on_device):
+    """Fused CG recurrence, 3 kernel launches per iteration (+ exchange / 2 scalar all-reduces when sharded).
+
+    With M = I: z = r, rho = r.r.  Per iteration
+        p = r + (rho/rho_prev) p              (b2s_axpby, isalpha=False)            [skipped at k = 0: p = r]
+        [x-window exchange of p]
+        q = A p ; pq = p.q                    (b2s_spmv_csr_dot)                    [all-reduce pq]
+        x += (rho/pq) p ; r -= (rho/pq) q ; rr = r.r   (b2s_cg_update_xr)           [all-reduce rr]
+        rho_prev <- rho ; rho <- rr
+    ||r|| for the convergence test is sqrt(rho) -- no extra pass.  All scalars stay on the device; the host
+    reads one of them every `conv_test_iters` iterations (reference cadence, linalg.py:559-563).
+
+    Iterations k >= 1 are identical, so they are captured once in a CUDA graph and replayed (removes the
+    per-launch CPU cost, which dominates once the per-GPU shard is small); `B2S_CG_GRAPH=0` disables it.
+    """
+    n = b.shape[0]
     plan = Ad._get_plan()
     shape = Ad.shape
     q = torch.empty(n, dtype=b.dtype, device=b.device)
+    p_full, p = comm.new_p(n, b)
+    xin = p_full[: shape[1]]
+
     # r = b - A x
-    _ops.spmv(Ad._indptr, Ad._indices, Ad._data, x, q, shape, plan=plan)
+    p.copy_(x)
+    comm.exchange(p_full)
+    _ops.spmv(Ad._indptr, Ad._indices, Ad._data, xin, q, shape, plan=plan)
     r = b - q
-    p = torch.empty_like(r)
     rho = _ops.dot(r, r)
-    rho_next = torch.empty_like(rho)
+    comm.allreduce(rho)
+    rho_prev = torch.ones_like(rho)
+    rr = torch.empty_like(rho)
     pq = torch.empty_like(rho)
+
+    def tail_of_iteration():
+        comm.exchange(p_full)
+        _ops.spmv_dot(Ad._indptr, Ad._indices, Ad._data, xin, q, p, pq, shape, plan)
+        comm.allreduce(pq)
+        _ops.cg_update_xr(x, r, p, q, rho, pq, rr)
+        comm.allreduce(rr)
+        rho_prev.copy_(rho)
+        rho.copy_(rr)
+
+    def generic_iteration():
+        cg_axpby(p, r, rho, rho_prev, isalpha=False, negate=False)
+        tail_of_iteration()
+
+    def converged(iters):
+        return (iters % conv_test_iters == 0 or iters == (maxiter - 1)) and float(rho[0]) ** 0.5 < tol
+
     iters = 0
+    if maxiter <= 0:
+        return x, iters
+    # iteration 0: p = r (no alias: p is updated in place later, reference linalg.py:541-544)
+    p.copy_(r)
+    tail_of_iteration()
+    iters = 1
+    if callback is not None:
+        callback(x if on_device else to_host(x))
+    if converged(iters):
+        return x, iters
+
+    graph = None
+    if os.environ.get("B2S_CG_GRAPH", "1") != "0" and maxiter - iters >= 4 and b.is_cuda:
+        graph = _try_capture(generic_iteration)
     while iters < maxiter:
-        if iters == 0:
-            p.copy_(r)
+        if graph is not None:
+            graph.replay()
         else:
-            # p = r + (rho/rho1) p with rho1 the previous rho
-            cg_axpby(p, r, rho_next, rho, isalpha=False, negate=False)
-            rho, rho_next = rho_next, rho
-        _ops.spmv_dot(Ad._indptr, Ad._indices, Ad._data, p, q, p, pq, shape, plan)
-        _ops.cg_update_xr(x, r, p, q, rho, pq, rho_next)
+            generic_iteration()
         iters += 1
         if callback is not None:
             callback(x if on_device else to_host(x))
-        if (iters % conv_test_iters == 0 or iters == (maxiter - 1)) and float(rho_next[0]) ** 0.5 < tol:
+        if converged(iters):
             break
     return x, iters
+
+
+def _try_capture(fn):
+    """Capture `fn` (kernel launches on the current stream) into a CUDA graph; None if capture fails.
+
+    The iteration is idempotent-unsafe (it updates x, r, p in place), so it cannot be 'warmed up' by simply
+    running it; all kernels and workspaces it uses were already exercised by iteration 0 and the setup SpMV.
+    """
+    cur = torch.cuda.current_stream()
+    try:
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            runtime.workspace()  # allocate the reduction workspace of the capture stream before capturing
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side):
+            fn()
+        torch.cuda.synchronize()
+        return _GraphOnCurrent(g)
+    except Exception as exc:  # pragma: no cover - depends on driver / NCCL capture support
+        warnings.warn(f"CUDA graph capture of the CG iteration failed ({exc}); running eagerly", RuntimeWarning)
+        try:
+            torch.cuda.synchronize()
+        except Exception:
+            pass
+        return None
+
+
+class _GraphOnCurrent:
+    def __init__(self, g):
+        self.g = g
+
+    def replay(self):
+        self.g.replay()
 
 
 __all__ = [
