@@ -19,9 +19,11 @@
 
 namespace b2s {
 
-constexpr int NCLS = 5;                 // 0: empty, 1: <=128 (warp), 2: <=1024 (CTA), 3: <=8192 (CTA), 4: larger
-constexpr int64_t CLS1_MAX = 128, CLS2_MAX = 1024, CLS3_MAX = 8192;
-constexpr int TBL1 = 256, TBL2 = 2048, TBL3 = 16384;
+// row bins: 0 empty | 1: <=32 (warp, 64-slot table) | 2: <=128 (warp, 256) | 3: <=1024 (CTA, 2048) |
+//           4: <=8192 (CTA, 16384) | 5: larger (global bitmap + dense accumulator)
+constexpr int NCLS = 6;
+constexpr int64_t CLS0_MAX = 32, CLS1_MAX = 128, CLS2_MAX = 1024, CLS3_MAX = 8192;
+constexpr int TBL0 = 64, TBL1 = 256, TBL2 = 2048, TBL3 = 16384;
 constexpr int SCAN_BLOCK = 1024;        // elements per scan block (256 threads x 4)
 
 struct Header {                          // first 256 bytes of scratch (device)
@@ -56,7 +58,7 @@ static ScratchLayout scratch_layout(int64_t m, int64_t n, int sm_count) {
 }
 
 __host__ __device__ __forceinline__ int classify(long long v) {
-  return v == 0 ? 0 : (v <= CLS1_MAX ? 1 : (v <= CLS2_MAX ? 2 : (v <= CLS3_MAX ? 3 : 4)));
+  return v == 0 ? 0 : (v <= CLS0_MAX ? 1 : (v <= CLS1_MAX ? 2 : (v <= CLS2_MAX ? 3 : (v <= CLS3_MAX ? 4 : 5))));
 }
 
 __device__ __forceinline__ unsigned hash_col(int32_t c, int bits) {
@@ -107,10 +109,24 @@ bin_count_kernel(int64_t m, const long long* __restrict__ src, Header* hdr, int 
   if (threadIdx.x == 0) s_flops = 0;
   __syncthreads();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  long long v = 0;
+  int c = -1;
   if (i < m) {
-    const long long v = FROM_INDPTR ? (src[i + 1] - src[i]) : src[i];
-    atomicAdd(&s_cnt[classify(v)], 1ull);
-    if (add_flops && v) atomicAdd(&s_flops, (unsigned long long)v);
+    v = FROM_INDPTR ? (src[i + 1] - src[i]) : src[i];
+    c = classify(v);
+  }
+  // warp-aggregated: one shared-memory atomic per (warp, class) instead of one per row
+#pragma unroll
+  for (int k = 0; k < NCLS; k++) {
+    const unsigned b = __ballot_sync(0xffffffffu, c == k);
+    if (lane == 0 && b) atomicAdd(&s_cnt[k], (unsigned long long)__popc(b));
+  }
+  if (add_flops) {
+    long long f = v;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) f += __shfl_xor_sync(0xffffffffu, f, o);
+    if (lane == 0 && f) atomicAdd(&s_flops, (unsigned long long)f);
   }
   __syncthreads();
   if (threadIdx.x < NCLS && s_cnt[threadIdx.x]) atomicAdd(&hdr->counts[threadIdx.x], s_cnt[threadIdx.x]);
@@ -211,6 +227,25 @@ scan_add_kernel(int64_t n, long long* __restrict__ data, const long long* __rest
     if (base + q < n) data[base + q] += add;
 }
 
+// block-wide exclusive scan of one int per thread; results in s_excl[0..THREADS), returns the total.
+// s_excl / s_wsum are shared scratch; ends with a barrier so s_excl is readable by every thread.
+template <int THREADS>
+__device__ __forceinline__ int block_exclusive_scan(int v, int* s_excl, int* s_wsum) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  int incl = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+  __syncthreads();  // previous users of s_wsum / s_excl are done
+  if (lane == 31) s_wsum[wid] = incl;
+  __syncthreads();
+  int woff = 0, total = 0;
+#pragma unroll
+  for (int w = 0; w < THREADS / 32; w++) { const int x = s_wsum[w]; if (w < wid) woff += x; total += x; }
+  s_excl[threadIdx.x] = woff + incl - v;
+  __syncthreads();
+  return total;
+}
+
 // ---- bitonic sort of (key,val) pairs in shared memory ------------------------------------------------------
 template <typename V, typename SyncF>
 __device__ __forceinline__ void bitonic_sort_kv(int32_t* keys, V* vals, int n, int tid, int nthreads, SyncF sync) {
@@ -234,17 +269,17 @@ __device__ __forceinline__ void bitonic_sort_kv(int32_t* keys, V* vals, int n, i
 
 // ---- class 1: warp per row ---------------------------------------------------------------------------------
 // NUMERIC=false: count distinct columns -> row_nnz[row]; NUMERIC=true: accumulate, sort, write.
-template <typename V, typename P, bool NUMERIC>
+template <typename V, typename P, int TBL, int BITS, int CMAX, bool NUMERIC>
 __global__ void __launch_bounds__(256)
 spgemm_warp_kernel(int64_t count, const int32_t* __restrict__ perm, const P* __restrict__ a_ptr,
                    const int32_t* __restrict__ a_idx, const V* __restrict__ a_val, const P* __restrict__ b_ptr,
                    const int32_t* __restrict__ b_idx, const V* __restrict__ b_val, long long* __restrict__ c_ptr,
                    int32_t* __restrict__ c_idx, V* __restrict__ c_val) {
   constexpr int WARPS = 8;
-  __shared__ int32_t s_keys[WARPS][TBL1];
-  __shared__ V s_vals[NUMERIC ? WARPS : 1][NUMERIC ? TBL1 : 1];
-  __shared__ int32_t s_ck[NUMERIC ? WARPS : 1][NUMERIC ? (int)CLS1_MAX : 1];
-  __shared__ V s_cv[NUMERIC ? WARPS : 1][NUMERIC ? (int)CLS1_MAX : 1];
+  __shared__ int32_t s_keys[WARPS][TBL];
+  __shared__ V s_vals[NUMERIC ? WARPS : 1][NUMERIC ? TBL : 1];
+  __shared__ int32_t s_ck[NUMERIC ? WARPS : 1][NUMERIC ? CMAX : 1];
+  __shared__ V s_cv[NUMERIC ? WARPS : 1][NUMERIC ? CMAX : 1];
   __shared__ int s_n[WARPS];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int64_t gw = (int64_t)blockIdx.x * WARPS + wid;
@@ -252,23 +287,71 @@ spgemm_warp_kernel(int64_t count, const int32_t* __restrict__ perm, const P* __r
   int32_t* keys = s_keys[wid];
   for (int64_t it = gw; it < count; it += nw) {
     const int32_t row = perm[it];
-    for (int i = lane; i < TBL1; i += 32) { keys[i] = -1; if (NUMERIC) s_vals[wid][i] = (V)0; }
+    for (int i = lane; i < TBL; i += 32) { keys[i] = -1; if (NUMERIC) s_vals[wid][i] = (V)0; }
     if (lane == 0) s_n[wid] = 0;
     __syncwarp();
     int fresh_cnt = 0;
     const int64_t alo = (int64_t)a_ptr[row], ahi = (int64_t)a_ptr[row + 1];
-    for (int64_t ka = alo; ka < ahi; ka++) {
-      const int32_t kk = a_idx[ka];
-      const int64_t blo = (int64_t)b_ptr[kk], bhi = (int64_t)b_ptr[kk + 1];
+    // Flattened expansion: 32 A-entries are fetched at once (one round of dependent loads instead of one
+    // per entry), their B-row lengths are warp-scanned, and the products are then enumerated 32 at a time
+    // in (A entry, B entry) order -- the reference's Gustavson order (spgemm_csr_csr_csr.cc:128-152).
+    for (int64_t base = alo; base < ahi; base += 32) {
+      const int64_t ka = base + lane;
+      const bool valid = ka < ahi;
+      int32_t kk = 0;
+      long long blo = 0;
+      int len = 0;
       V av = (V)0;
-      if (NUMERIC) av = a_val[ka];
-      for (int64_t jb = blo + lane; jb < bhi; jb += 32) {
-        bool fresh;
-        const int slot = hash_insert<TBL1, 8>(keys, b_idx[jb], &fresh);
-        fresh_cnt += fresh ? 1 : 0;
-        if (NUMERIC) atomicAdd(&s_vals[wid][slot], av * b_val[jb]);
+      if (valid) {
+        kk = a_idx[ka];
+        blo = (long long)b_ptr[kk];
+        len = (int)((long long)b_ptr[kk + 1] - blo);
+        if (NUMERIC) av = a_val[ka];
       }
-      __syncwarp();  // order accumulation steps: per-column sums follow the A-row order
+      int incl = len;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+      const int excl = incl - len;
+      const int total = __shfl_sync(0xffffffffu, incl, 31);
+      for (int p0 = 0; p0 < total; p0 += 32) {
+        const int p = p0 + lane;
+        const bool active = p < total;
+        int t = 0;  // owner = largest t with excl_t <= p (skips empty B rows)
+#pragma unroll
+        for (int st = 16; st > 0; st >>= 1) {
+          const int cand = t + st;
+          const int e = __shfl_sync(0xffffffffu, excl, cand & 31);
+          if (cand < 32 && e <= p) t = cand;
+        }
+        const long long o_blo = __shfl_sync(0xffffffffu, blo, t);
+        const int o_excl = __shfl_sync(0xffffffffu, excl, t);
+        V o_av = (V)0;
+        if (NUMERIC) o_av = __shfl_sync(0xffffffffu, av, t);
+        int slot = -1;
+        V prod = (V)0;
+        if (active) {
+          const long long jb = o_blo + (p - o_excl);
+          bool fresh;
+          slot = hash_insert<TBL, BITS>(keys, b_idx[jb], &fresh);
+          fresh_cnt += fresh ? 1 : 0;
+          if (NUMERIC) prod = o_av * b_val[jb];
+        }
+        if (NUMERIC) {
+          // lanes that hit the same column are summed by the lowest of them in lane (= product) order, so the
+          // result is deterministic and follows the reference's accumulation order; no atomics on the values
+          const unsigned m = __match_any_sync(0xffffffffu, slot);
+          const int leader = __ffs(m) - 1;
+          unsigned rem = m;
+          V acc = (V)0;
+          while (__any_sync(0xffffffffu, rem != 0)) {
+            const int src = rem ? (__ffs(rem) - 1) : lane;
+            const V v = __shfl_sync(0xffffffffu, prod, src);
+            if (rem) { acc += v; rem &= rem - 1; }
+          }
+          if (slot >= 0 && lane == leader) s_vals[wid][slot] += acc;
+        }
+        __syncwarp();
+      }
     }
     if (!NUMERIC) {
 #pragma unroll
@@ -276,12 +359,17 @@ spgemm_warp_kernel(int64_t count, const int32_t* __restrict__ perm, const P* __r
       if (lane == 0) c_ptr[row] = fresh_cnt;
     } else {
       // compact -> sort pow2 >= n -> write
-      for (int i = lane; i < TBL1; i += 32) {
+      for (int i = lane; i < TBL; i += 32) {
         const int32_t k = keys[i];
+        const unsigned occ = __ballot_sync(0xffffffffu, k != -1);
+        const int basep = s_n[wid];
         if (k != -1) {
-          const int p = atomicAdd(&s_n[wid], 1);
+          const int p = basep + __popc(occ & ((1u << lane) - 1));
           s_ck[wid][p] = k; s_cv[wid][p] = s_vals[wid][i];
         }
+        __syncwarp();
+        if (lane == 0) s_n[wid] = basep + __popc(occ);
+        __syncwarp();
       }
       __syncwarp();
       const int n = s_n[wid];
@@ -308,8 +396,12 @@ spgemm_cta_kernel(int64_t count, const int32_t* __restrict__ perm, const P* __re
   int32_t* keys = reinterpret_cast<int32_t*>(smem_raw);
   V* vals = reinterpret_cast<V*>(smem_raw + sizeof(int32_t) * TBL);
   __shared__ double red[32];
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  constexpr int NWARPS = THREADS / 32;
+  __shared__ int s_excl[THREADS];
+  __shared__ int s_wsum[THREADS / 32];
+  __shared__ long long s_blo[THREADS];
+  __shared__ V s_av[NUMERIC ? THREADS : 1];
+  __shared__ int s_cnt;
+  const int tid = threadIdx.x;
   for (int64_t it = blockIdx.x; it < count; it += gridDim.x) {
     const int32_t row = perm[it];
     __syncthreads();
@@ -317,28 +409,66 @@ spgemm_cta_kernel(int64_t count, const int32_t* __restrict__ perm, const P* __re
     __syncthreads();
     int fresh_cnt = 0;
     const int64_t alo = (int64_t)a_ptr[row], ahi = (int64_t)a_ptr[row + 1];
-    for (int64_t ka = alo + wid; ka < ahi; ka += NWARPS) {
-      const int32_t kk = a_idx[ka];
-      const int64_t blo = (int64_t)b_ptr[kk], bhi = (int64_t)b_ptr[kk + 1];
-      V av = (V)0;
-      if (NUMERIC) av = a_val[ka];
-      for (int64_t jb = blo + lane; jb < bhi; jb += 32) {
+    // flattened expansion, THREADS A-entries per round (see spgemm_warp_kernel)
+    for (int64_t base = alo; base < ahi; base += THREADS) {
+      const int64_t ka = base + tid;
+      int len = 0;
+      if (ka < ahi) {
+        const int32_t kk = a_idx[ka];
+        const long long blo = (long long)b_ptr[kk];
+        len = (int)((long long)b_ptr[kk + 1] - blo);
+        s_blo[tid] = blo;
+        if (NUMERIC) s_av[tid] = a_val[ka];
+      }
+      const int total = block_exclusive_scan<THREADS>(len, s_excl, s_wsum);
+      for (int p = tid; p < total; p += THREADS) {
+        int lo = 0, hi = THREADS - 1;  // largest t with s_excl[t] <= p
+        while (lo < hi) {
+          const int mid = (lo + hi + 1) >> 1;
+          if (s_excl[mid] <= p) lo = mid; else hi = mid - 1;
+        }
+        const long long jb = s_blo[lo] + (p - s_excl[lo]);
         bool fresh;
         const int slot = hash_insert<TBL, BITS>(keys, b_idx[jb], &fresh);
         fresh_cnt += fresh ? 1 : 0;
-        if (NUMERIC) atomicAdd(&vals[slot], av * b_val[jb]);
+        if (NUMERIC) atomicAdd(&vals[slot], s_av[lo] * b_val[jb]);
       }
+      __syncthreads();
     }
     if (!NUMERIC) {
       double tot = block_sum<THREADS>((double)fresh_cnt, red);
       if (tid == 0) c_ptr[row] = (long long)(tot + 0.5);
     } else {
       __syncthreads();
-      for (int i = tid; i < TBL; i += THREADS) if (keys[i] == -1) keys[i] = INT_MAX;
-      __syncthreads();
-      bitonic_sort_kv<V>(keys, vals, TBL, tid, THREADS, [] { __syncthreads(); });
+      // compact the occupied slots into the row's output range (unsorted), reload them at the front of the
+      // table and sort only the smallest power of two >= n entries (the table itself is 2x..16x larger)
       const long long base = c_ptr[row];
       const int n = (int)(c_ptr[row + 1] - base);
+      if (tid == 0) s_cnt = 0;
+      __syncthreads();
+      for (int i0 = 0; i0 < TBL; i0 += THREADS) {
+        const int i = i0 + tid;
+        const int32_t k = keys[i];
+        const unsigned occ = __ballot_sync(0xffffffffu, k != -1);
+        int wbase = 0;
+        if ((tid & 31) == 0 && occ) wbase = atomicAdd(&s_cnt, __popc(occ));
+        wbase = __shfl_sync(0xffffffffu, wbase, 0);
+        if (k != -1) {
+          const int p = wbase + __popc(occ & ((1u << (tid & 31)) - 1));
+          c_idx[base + p] = k;
+          c_val[base + p] = vals[i];
+        }
+      }
+      __threadfence_block();
+      __syncthreads();
+      int np2 = 1;
+      while (np2 < n) np2 <<= 1;
+      for (int i = tid; i < np2; i += THREADS) {
+        keys[i] = i < n ? c_idx[base + i] : INT_MAX;
+        vals[i] = i < n ? c_val[base + i] : (V)0;
+      }
+      __syncthreads();
+      bitonic_sort_kv<V>(keys, vals, np2, tid, THREADS, [] { __syncthreads(); });
       for (int i = tid; i < n; i += THREADS) { c_idx[base + i] = keys[i]; c_val[base + i] = vals[i]; }
     }
   }
@@ -355,6 +485,10 @@ spgemm_dense_kernel(int64_t count, const int32_t* __restrict__ perm, const P* __
   __shared__ double red[32];
   __shared__ int s_scan[THREADS / 32];
   __shared__ long long s_base;
+  __shared__ int s_excl[THREADS];
+  __shared__ int s_wsum[THREADS / 32];
+  __shared__ long long s_blo[THREADS];
+  __shared__ V s_av[NUMERIC ? THREADS : 1];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   constexpr int NWARPS = THREADS / 32;
   unsigned int* bm0 = reinterpret_cast<unsigned int*>(bitmaps + slot_bytes * blockIdx.x);
@@ -363,18 +497,32 @@ spgemm_dense_kernel(int64_t count, const int32_t* __restrict__ perm, const P* __
   for (int64_t it = blockIdx.x; it < count; it += gridDim.x) {
     const int32_t row = perm[it];
     const int64_t alo = (int64_t)a_ptr[row], ahi = (int64_t)a_ptr[row + 1];
-    for (int64_t ka = alo + wid; ka < ahi; ka += NWARPS) {
-      const int32_t kk = a_idx[ka];
-      const int64_t blo = (int64_t)b_ptr[kk], bhi = (int64_t)b_ptr[kk + 1];
-      V av = (V)0;
-      if (NUMERIC) av = a_val[ka];
-      for (int64_t jb = blo + lane; jb < bhi; jb += 32) {
+    // flattened expansion, THREADS A-entries per round (see spgemm_warp_kernel)
+    for (int64_t base = alo; base < ahi; base += THREADS) {
+      const int64_t ka = base + tid;
+      int len = 0;
+      if (ka < ahi) {
+        const int32_t kk = a_idx[ka];
+        const long long blo = (long long)b_ptr[kk];
+        len = (int)((long long)b_ptr[kk + 1] - blo);
+        s_blo[tid] = blo;
+        if (NUMERIC) s_av[tid] = a_val[ka];
+      }
+      const int total = block_exclusive_scan<THREADS>(len, s_excl, s_wsum);
+      for (int p = tid; p < total; p += THREADS) {
+        int lo = 0, hi = THREADS - 1;
+        while (lo < hi) {
+          const int mid = (lo + hi + 1) >> 1;
+          if (s_excl[mid] <= p) lo = mid; else hi = mid - 1;
+        }
+        const long long jb = s_blo[lo] + (p - s_excl[lo]);
         const int32_t j = b_idx[jb];
         const unsigned int bit = 1u << (j & 31);
         const unsigned int old = atomicOr(&bm0[j >> 5], bit);
         if (old == 0) atomicOr(&bm1[j >> 10], 1u << ((j >> 5) & 31));
-        if (NUMERIC) atomicAdd(&acc[j], av * b_val[jb]);
+        if (NUMERIC) atomicAdd(&acc[j], s_av[lo] * b_val[jb]);
       }
+      __syncthreads();
     }
     __threadfence_block();
     __syncthreads();
@@ -487,34 +635,41 @@ static int run_classes(int sm_count, const unsigned long long counts[8], const C
   if (counts[1]) {
     int64_t want = ((int64_t)counts[1] + 7) / 8, cap = (int64_t)sm_count * 16;
     unsigned grid = (unsigned)(want < cap ? want : cap);
-    spgemm_warp_kernel<V, P, NUMERIC><<<grid, 256, 0, st>>>((int64_t)counts[1], perm + offs.off[1], ap, a_idx, av, bp,
-                                                            b_idx, bv, c_ptr, c_idx, cv);
+    spgemm_warp_kernel<V, P, TBL0, 6, (int)CLS0_MAX, NUMERIC><<<grid, 256, 0, st>>>(
+        (int64_t)counts[1], perm + offs.off[1], ap, a_idx, av, bp, b_idx, bv, c_ptr, c_idx, cv);
     B2S_LAUNCH_CHECK();
   }
   if (counts[2]) {
-    auto kern = spgemm_cta_kernel<V, P, TBL2, 11, 128, NUMERIC>;
-    const size_t smem = sizeof(int32_t) * TBL2 + (NUMERIC ? sizeof(V) * TBL2 : 0);
-    int64_t cap = (int64_t)sm_count * 16;
-    unsigned grid = (unsigned)((int64_t)counts[2] < cap ? (int64_t)counts[2] : cap);
-    kern<<<grid, 128, smem, st>>>((int64_t)counts[2], perm + offs.off[2], ap, a_idx, av, bp, b_idx, bv, c_ptr, c_idx, cv);
+    int64_t want = ((int64_t)counts[2] + 7) / 8, cap = (int64_t)sm_count * 16;
+    unsigned grid = (unsigned)(want < cap ? want : cap);
+    spgemm_warp_kernel<V, P, TBL1, 8, (int)CLS1_MAX, NUMERIC><<<grid, 256, 0, st>>>(
+        (int64_t)counts[2], perm + offs.off[2], ap, a_idx, av, bp, b_idx, bv, c_ptr, c_idx, cv);
     B2S_LAUNCH_CHECK();
   }
   if (counts[3]) {
+    auto kern = spgemm_cta_kernel<V, P, TBL2, 11, 128, NUMERIC>;
+    const size_t smem = sizeof(int32_t) * TBL2 + (NUMERIC ? sizeof(V) * TBL2 : 0);
+    int64_t cap = (int64_t)sm_count * 16;
+    unsigned grid = (unsigned)((int64_t)counts[3] < cap ? (int64_t)counts[3] : cap);
+    kern<<<grid, 128, smem, st>>>((int64_t)counts[3], perm + offs.off[3], ap, a_idx, av, bp, b_idx, bv, c_ptr, c_idx, cv);
+    B2S_LAUNCH_CHECK();
+  }
+  if (counts[4]) {
     auto kern = spgemm_cta_kernel<V, P, TBL3, 14, 256, NUMERIC>;
     const size_t smem = sizeof(int32_t) * TBL3 + (NUMERIC ? sizeof(V) * TBL3 : 0);
     B2S_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int64_t cap = (int64_t)sm_count * (NUMERIC ? 2 : 6);
-    unsigned grid = (unsigned)((int64_t)counts[3] < cap ? (int64_t)counts[3] : cap);
-    kern<<<grid, 256, smem, st>>>((int64_t)counts[3], perm + offs.off[3], ap, a_idx, av, bp, b_idx, bv, c_ptr, c_idx, cv);
+    unsigned grid = (unsigned)((int64_t)counts[4] < cap ? (int64_t)counts[4] : cap);
+    kern<<<grid, 256, smem, st>>>((int64_t)counts[4], perm + offs.off[4], ap, a_idx, av, bp, b_idx, bv, c_ptr, c_idx, cv);
     B2S_LAUNCH_CHECK();
   }
-  if (counts[4]) {
+  if (counts[5]) {
     int64_t slots = L.nslots;
     if (NUMERIC && dense_slots < slots) slots = dense_slots;
-    if ((int64_t)counts[4] < slots) slots = (int64_t)counts[4];
+    if ((int64_t)counts[5] < slots) slots = (int64_t)counts[5];
     if (slots < 1) { set_error("dense accumulator workspace too small"); return B2S_ENOMEM; }
     spgemm_dense_kernel<V, P, 256, NUMERIC><<<(unsigned)slots, 256, 0, st>>>(
-        (int64_t)counts[4], perm + offs.off[4], ap, a_idx, av, bp, b_idx, bv, c_ptr, c_idx, cv, bitmaps,
+        (int64_t)counts[5], perm + offs.off[5], ap, a_idx, av, bp, b_idx, bv, c_ptr, c_idx, cv, bitmaps,
         L.bitmap_slot_bytes, L.bitmap_words0, L.bitmap_words1, (V*)dense, n);
     B2S_LAUNCH_CHECK();
   }
@@ -578,7 +733,7 @@ int b2s_spgemm_csr_symbolic(int pt, int64_t m, int64_t k, int64_t n, const void*
   unsigned long long flops = 0;
   ClsOffsets offs;
   if (int rc = run_binning<false>(m, ub, hdr, perm, true, counts, &flops, &offs, st)) return rc;
-  if (counts[4]) B2S_CUDA(cudaMemsetAsync(bitmaps, 0, (size_t)(L.bitmap_slot_bytes * L.nslots), st));
+  if (counts[5]) B2S_CUDA(cudaMemsetAsync(bitmaps, 0, (size_t)(L.bitmap_slot_bytes * L.nslots), st));
   int rc;
   long long* cp = (long long*)c_indptr;
   if (pt == B2S_I32) rc = run_classes<float, int32_t, false>(pr.sm_count, counts, offs, perm, a_indptr, a_indices, nullptr, b_indptr, b_indices, nullptr, cp, nullptr, nullptr, bitmaps, L, nullptr, 0, n, st);
@@ -594,7 +749,7 @@ int b2s_spgemm_csr_symbolic(int pt, int64_t m, int64_t k, int64_t n, const void*
   B2S_CUDA(cudaStreamSynchronize(st));
   info_host[0] = nnz;
   info_host[1] = (int64_t)flops;
-  info_host[2] = (int64_t)counts2[4];
+  info_host[2] = (int64_t)counts2[5];
   return B2S_OK;
 }
 
@@ -619,7 +774,7 @@ int b2s_spgemm_csr_numeric(int vt, int pt, int64_t m, int64_t k, int64_t n, cons
   ClsOffsets offs;
   if (int rc = run_binning<true>(m, (const long long*)c_indptr, hdr, perm, false, counts, nullptr, &offs, st)) return rc;
   int64_t dense_slots = 0;
-  if (counts[4]) {
+  if (counts[5]) {
     const int64_t per = n * (vt == B2S_F32 ? 4 : 8);
     dense_slots = per > 0 ? dense_ws_bytes / per : 0;
     B2S_CHECK_ARG(dense_ws != nullptr && dense_slots >= 1, "numeric pass needs a dense accumulator workspace of >= %lld bytes", (long long)per);
