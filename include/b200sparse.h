@@ -145,14 +145,29 @@ int         b2s_spgemm_csr_numeric(int vt, int pt, int64_t m, int64_t k, int64_t
                                    const int64_t* c_indptr, int32_t* c_indices, void* c_vals,
                                    void* scratch, void* dense_ws, int64_t dense_ws_bytes, void* stream);
 
-/* ---- multi-GPU plumbing: peer-visible x shards over NVLink (CUDA IPC) ----------------
- * One process per GPU.  A rank exports the allocation holding its x shard, peers map it,
- * and the window-exchange kernel pulls [lo,hi) pieces of remote shards straight over
- * NVLink.  Replaces the implicit Legion/Realm halo copies driven by MinMaxImagePartition
- * (sparse/partition.py:139-208).  Handles are 64 opaque bytes (cudaIpcMemHandle_t). */
+/* ---- multi-GPU: NVLink peer-memory exchange (one process per GPU, CUDA IPC) -------------
+ * Replaces the implicit Legion/Realm halo copies driven by MinMaxImagePartition
+ * (sparse/partition.py:139-208) and the future-map reductions behind r.dot(z)/p.dot(q)
+ * (sparse/linalg.py:540,550).  Each rank owns one buffer from b2s_ipc_alloc: the first
+ * b2s_peer_header_bytes() bytes are flags/mailboxes, the x vector lives after them.  Handles
+ * are 64 opaque bytes (cudaIpcMemHandle_t) exchanged by the caller (e.g. over
+ * torch.distributed); `peers_host` is a host array of nranks device pointers (own buffer at
+ * [rank], IPC-mapped peers elsewhere).  All spins are bounded; b2s_peer_check reports a timeout. */
+int64_t     b2s_peer_header_bytes(void);
+int         b2s_ipc_alloc(int64_t bytes, void** dev_ptr);          /* cudaMalloc + zero fill; syncs */
+int         b2s_ipc_free(void* dev_ptr);
 int         b2s_ipc_export(const void* dev_ptr, void* handle64_host);
 int         b2s_ipc_open(const void* handle64_host, void** dev_ptr_out);
 int         b2s_ipc_close(void* dev_ptr);
+/* one-shot all-reduce (sum) of count <= 4 scalars of type vt, in place, identical result on every rank */
+int         b2s_peer_allreduce(int vt, int rank, int nranks, void* const* peers_host, void* inout_dev,
+                               int count, void* stream);
+/* push slices of the local x into the neighbours' x buffers and wait for the slices they push here.
+ * send_desc_host: nsends x {peer, src_elem_off, dst_elem_off, count}; recv_peers_host: nrecvs source ranks */
+int         b2s_peer_halo_exchange(int vt, int rank, int nranks, void* const* peers_host,
+                                   const void* x_local_dev, int nsends, const int64_t* send_desc_host,
+                                   int nrecvs, const int32_t* recv_peers_host, void* stream);
+int         b2s_peer_check(void* own_buf_dev, void* stream, int64_t* error_out_host);   /* syncs */
 /* dst[i] = src[i] for i in [0,n) elements of type vt where src is a (possibly peer) device
  * pointer; 128-bit loads when both are 16-byte aligned. */
 int         b2s_copy(int vt, int64_t n, void* dst, const void* src, void* stream);

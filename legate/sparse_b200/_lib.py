@@ -43,6 +43,12 @@ SIGNATURES = {
     "b2s_spgemm_csr_symbolic": (c_i32, [c_i32, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "b2s_spgemm_csr_numeric": (c_i32, [c_i32, c_i32, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp,
                                        c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
+    "b2s_peer_header_bytes": (c_i64, []),
+    "b2s_ipc_alloc": (c_i32, [c_i64, ctypes.POINTER(c_vp)]),
+    "b2s_ipc_free": (c_i32, [c_vp]),
+    "b2s_peer_allreduce": (c_i32, [c_i32, c_i32, c_i32, c_vp, c_vp, c_i32, c_vp]),
+    "b2s_peer_halo_exchange": (c_i32, [c_i32, c_i32, c_i32, c_vp, c_vp, c_i32, c_vp, c_i32, c_vp, c_vp]),
+    "b2s_peer_check": (c_i32, [c_vp, c_vp, c_vp]),
     "b2s_ipc_export": (c_i32, [c_vp, c_vp]),
     "b2s_ipc_open": (c_i32, [c_vp, ctypes.POINTER(c_vp)]),
     "b2s_ipc_close": (c_i32, [c_vp]),

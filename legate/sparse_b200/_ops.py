@@ -172,12 +172,50 @@ def spgemm(a_indptr, a_indices, a_data, b_indptr, b_indices, b_data, shape_a, sh
     return c_indptr, c_indices, c_data, {"nnz": nnz, "products": products, "dense_rows": dense_rows}
 
 
-# ---- CUDA IPC ------------------------------------------------------------------------------------------
-def ipc_export(t: torch.Tensor) -> bytes:
-    _chk_dev(t)
+# ---- CUDA IPC / NVLink peer exchange -----------------------------------------------------------------------
+def ipc_alloc(nbytes: int) -> int:
+    out = _lib.c_vp()
+    _lib.check(L.b2s_ipc_alloc(int(nbytes), ctypes.byref(out)), "b2s_ipc_alloc")
+    return int(out.value)
+
+
+def ipc_free(p: int) -> None:
+    _lib.check(L.b2s_ipc_free(p), "b2s_ipc_free")
+
+
+def ipc_export(p) -> bytes:
+    if isinstance(p, torch.Tensor):
+        _chk_dev(p)
+        p = ptr(p)
     buf = ctypes.create_string_buffer(64)
-    _lib.check(L.b2s_ipc_export(ptr(t), buf), "b2s_ipc_export")
+    _lib.check(L.b2s_ipc_export(p, buf), "b2s_ipc_export")
     return buf.raw
+
+
+def peer_allreduce(t: torch.Tensor, rank: int, peers) -> torch.Tensor:
+    _chk_dev(t)
+    n = len(peers)
+    arr = (_lib.c_vp * n)(*peers)
+    _lib.check(L.b2s_peer_allreduce(vt_code(t.dtype), rank, n, arr, ptr(t), t.numel(), _stream()), "b2s_peer_allreduce")
+    return t
+
+
+def peer_halo_exchange(x_local: torch.Tensor, rank: int, peers, sends, recv_peers) -> None:
+    """sends: list of (peer, src_elem_off, dst_elem_off, count)."""
+    _chk_dev(x_local)
+    n = len(peers)
+    arr = (_lib.c_vp * n)(*peers)
+    flat = [int(v) for s in sends for v in s]
+    desc = (_lib.c_i64 * max(len(flat), 1))(*flat)
+    rp = (ctypes.c_int32 * max(len(recv_peers), 1))(*recv_peers)
+    _lib.check(L.b2s_peer_halo_exchange(vt_code(x_local.dtype), rank, n, arr, ptr(x_local), len(sends), desc,
+                                        len(recv_peers), rp, _stream()), "b2s_peer_halo_exchange")
+
+
+def peer_check(own_ptr: int) -> int:
+    out = _lib.c_i64(0)
+    _lib.check(L.b2s_peer_check(own_ptr, _stream(), ctypes.byref(out)), "b2s_peer_check")
+    return int(out.value)
 
 
 def ipc_open(handle: bytes) -> int:

@@ -79,6 +79,73 @@ def _intersect(a_lo, a_hi, b_lo, b_hi):
     return (lo, hi) if hi > lo else None
 
 
+class _RawCudaBuffer:
+    """Zero-copy view of a raw device allocation as a torch tensor (via __cuda_array_interface__)."""
+
+    def __init__(self, ptr: int, nelems: int, np_dtype):
+        self.__cuda_array_interface__ = {
+            "shape": (int(nelems),),
+            "typestr": np.dtype(np_dtype).str,
+            "data": (int(ptr), False),
+            "version": 3,
+            "strides": None,
+        }
+
+
+class PeerComm:
+    """NVLink peer-memory communicator of one box: every rank allocates one IPC-shareable buffer
+    [header | x vector], maps the other ranks' buffers, and then exchanges halos / all-reduces scalars with
+    plain remote stores + epoch flags (csrc/peer.cu) instead of NCCL calls.  Collective constructor."""
+
+    def __init__(self, x_elems: int, np_dtype, rank: int, nranks: int, group=None):
+        from . import _lib
+
+        self.rank, self.nranks = rank, nranks
+        self.dtype = np.dtype(np_dtype)
+        self.header = int(_lib.lib.b2s_peer_header_bytes())
+        self.x_elems = int(x_elems)
+        nbytes = self.header + (self.x_elems + 8) * self.dtype.itemsize
+        self.own = _ops.ipc_alloc(nbytes)
+        handle = _ops.ipc_export(self.own)
+        handles = [None] * nranks
+        dist.all_gather_object(handles, handle, group=group)
+        self.peers = []
+        self._opened = []
+        for q in range(nranks):
+            if q == rank:
+                self.peers.append(self.own)
+            else:
+                p = _ops.ipc_open(handles[q])
+                self._opened.append(p)
+                self.peers.append(p)
+        self._keep = _RawCudaBuffer(self.own + self.header, self.x_elems + 8, self.dtype)
+        self.x_base = torch.as_tensor(self._keep, device=runtime.device)
+        dist.barrier(group=group)
+
+    def allreduce(self, t: torch.Tensor) -> torch.Tensor:
+        return _ops.peer_allreduce(t, self.rank, self.peers)
+
+    def check(self):
+        if _ops.peer_check(self.own):
+            raise RuntimeError("NVLink peer exchange timed out waiting for another rank (PeerHeader.error set)")
+
+    def close(self):
+        for p in self._opened:
+            try:
+                _ops.ipc_close(p)
+            except Exception:
+                pass
+        self._opened = []
+        if self.own:
+            self.x_base = None
+            self._keep = None
+            try:
+                _ops.ipc_free(self.own)
+            except Exception:
+                pass
+            self.own = 0
+
+
 class dist_csr_array:
     """A row shard of a global square-or-rectangular CSR matrix.
 
@@ -161,16 +228,47 @@ class dist_csr_array:
             mode = "p2p" if total_need * 4 < (self.nranks - 1) * self.col_plan.tile else "allgather"
         self.exchange_mode = mode if self.nranks > 1 else "none"
         self.recv_elems = need
+        # NVLink peer-memory path (csrc/peer.cu), for ranks that are CUDA devices of one box:
+        #   B2S_PEER=1 (default)      CG scalars are all-reduced by the one-shot peer kernel (one ~5 us launch
+        #                             instead of an NCCL all-reduce; 2 GPUs, PDE4096: 299 -> 271 us/iteration)
+        #   B2S_PEER_HALO=1 (opt-in)  x halo pieces are pushed by remote stores instead of NCCL send/recv.
+        #                             Measured equal to NCCL (two launches, ~20 us vs ~18 us per exchange at
+        #                             2 GPUs), so it stays off until the wait is fused into the SpMV kernel.
+        self._peer = {}
+        peer_ok = self.nranks > 1 and runtime.has_cuda and self.nranks <= 16
+        self.use_peer = peer_ok and os.environ.get("B2S_PEER", "1") != "0"
+        self.use_peer_halo = self.use_peer and os.environ.get("B2S_PEER_HALO", "0") == "1"
 
     def _comm_device(self):
         return runtime.device
 
     # -- vectors ----------------------------------------------------------------------------------------
+    def _peer_comm(self, np_dtype):
+        key = np.dtype(np_dtype)
+        pc = self._peer.get(key)
+        if pc is None:
+            n = max(self.col_plan.padded, 1)
+            pc = PeerComm(n, key, self.rank, self.nranks, self.group)
+            per16 = 16 // key.itemsize
+            pc.x_off = (-self.my_cols[0]) % per16  # own slice starts 16-byte aligned
+            offs = [None] * self.nranks
+            dist.all_gather_object(offs, pc.x_off, group=self.group)
+            pc.peer_x_off = offs
+            pc.x_full = pc.x_base[pc.x_off : pc.x_off + n]
+            self._peer[key] = pc
+        return pc
+
     def new_full_vector(self, dtype=None) -> torch.Tensor:
         """Full-length x buffer (padded to P*T so the all-gather lands in place).  The buffer is offset
         inside its allocation so that this rank's own slice starts 16-byte aligned (the vector kernels
-        then take their 128-bit path on the shard views)."""
-        dt = torch_dtype(self.dtype if dtype is None else dtype)
+        then take their 128-bit path on the shard views).  With the peer path enabled the buffer lives in
+        this rank's IPC allocation (one per dtype, reused) so neighbours can push their halo pieces into it."""
+        np_dt = numpy_dtype(self.dtype if dtype is None else dtype)
+        if self.use_peer_halo:
+            pc = self._peer_comm(np_dt)
+            pc.x_full.zero_()
+            return pc.x_full
+        dt = torch_dtype(np_dt)
         n = max(self.col_plan.padded, 1)
         base = torch.zeros(n + 4, dtype=dt, device=runtime.device)
         per16 = 16 // base.element_size()
@@ -197,6 +295,11 @@ class dist_csr_array:
             T = self.col_plan.tile
             src = full[self.rank * T : (self.rank + 1) * T]
             dist.all_gather_into_tensor(full, src, group=self.group)
+            return
+        pc = self._peer.get(numpy_dtype(full.dtype)) if self.use_peer_halo else None
+        if pc is not None and full.data_ptr() == pc.x_full.data_ptr():
+            sends = [(q, a, pc.peer_x_off[q] + a, b - a) for q, a, b in self.sends]
+            _ops.peer_halo_exchange(full, self.rank, pc.peers, sends, [q for q, _, _ in self.recvs])
             return
         ops = []
         for q, a, b in self.recvs:
@@ -231,7 +334,20 @@ class dist_csr_array:
         return full, self.local_view(full)
 
     def allreduce(self, t):
+        if self.use_peer and t.is_cuda and t.numel() <= 4:
+            # any of this shard's peer communicators will do: the scalar mailboxes do not depend on the x dtype
+            pc = next(iter(self._peer.values())) if self._peer else self._peer_comm(self.dtype)
+            return pc.allreduce(t)
         return allreduce_scalar(t, self.group)
+
+    def check_peer(self):
+        for pc in self._peer.values():
+            pc.check()
+
+    def close(self):
+        for pc in self._peer.values():
+            pc.close()
+        self._peer = {}
 
     def matvec_global(self, x_global):
         """Convenience for tests: replicated x in, replicated y out (numpy)."""
@@ -273,4 +389,6 @@ def cg(A: dist_csr_array, b_local, x0_local=None, tol=1e-08, maxiter=None, callb
     b = to_device(b_local, dtype=dt).reshape(-1)
     n = b.shape[0]
     x = torch.zeros(n, dtype=b.dtype, device=b.device) if x0_local is None else to_device(x0_local, dtype=dt, copy=True)
-    return _cg_fused_loop(Al, A, b, x, tol, maxiter, callback, conv_test_iters, True)
+    out = _cg_fused_loop(Al, A, b, x, tol, maxiter, callback, conv_test_iters, True)
+    A.check_peer()
+    return out

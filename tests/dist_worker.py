@@ -43,35 +43,48 @@ def main():
         assert np.allclose(Bm.matvec_global(xb), B @ xb, rtol=1e-12, atol=1e-12), mode
     os.environ["B2S_EXCHANGE"] = "auto"
 
-    # 2. shards assembled directly (gallery row_lo/row_hi) equal the slices of the global operator
-    n1, n2 = 300, 200 * world
-    N = n1 * n2
-    plan = bd.RowBlockPlan(N, world)
-    lo, hi = plan.rows(rank)
-    local = gallery.laplacian_5pt(n1, n2, np.float64, row_lo=lo, row_hi=hi)
-    G = gallery.laplacian_5pt(n1, n2, np.float64).to_scipy_sparse_csr()
-    Ls = local.to_scipy_sparse_csr()
-    assert (Ls != G[lo:hi]).nnz == 0
-    Ad = bd.dist_csr_array(local, (N, N))
-    assert Ad.exchange_mode == "p2p" and Ad.recv_elems <= 2 * n1
-    xg = rng.standard_normal(N)
-    assert np.allclose(Ad.matvec_global(xg), G @ xg, rtol=1e-12, atol=1e-6)
+    # 2./3. with the NVLink peer-memory path (csrc/peer.cu) and with plain NCCL
+    for peer, halo in (("1", "1"), ("1", "0"), ("0", "0")):
+        os.environ["B2S_PEER"] = peer
+        os.environ["B2S_PEER_HALO"] = halo
+        # 2. shards assembled directly (gallery row_lo/row_hi) equal the slices of the global operator
+        n1, n2 = 300, 200 * world
+        N = n1 * n2
+        plan = bd.RowBlockPlan(N, world)
+        lo, hi = plan.rows(rank)
+        local = gallery.laplacian_5pt(n1, n2, np.float64, row_lo=lo, row_hi=hi)
+        G = gallery.laplacian_5pt(n1, n2, np.float64).to_scipy_sparse_csr()
+        Ls = local.to_scipy_sparse_csr()
+        assert (Ls != G[lo:hi]).nnz == 0
+        Ad = bd.dist_csr_array(local, (N, N))
+        assert Ad.use_peer == (peer == "1") and Ad.use_peer_halo == (halo == "1")
+        assert Ad.exchange_mode == "p2p" and Ad.recv_elems <= 2 * n1
+        for rep in range(3):  # repeated exchanges exercise the epoch / ack protocol
+            xg = rng.standard_normal(N)
+            assert np.allclose(Ad.matvec_global(xg), G @ xg, rtol=1e-12, atol=1e-6), (peer, rep)
 
-    # 3. sharded CG == oracle CG on the global problem (same iteration count, same solution)
-    b = np.ones(N)
-    xl, iters = bd.cg(Ad, b[lo:hi], tol=1e-8, maxiter=500)
-    xs = bd.gather_vector(xl, Ad.row_plan, rank)
-    xo, io = orc.cg(lambda v: orc.spmv(G.indptr, G.indices, G.data, v), b, tol=1e-8, maxiter=500)
-    assert iters == io, (iters, io)
-    assert np.allclose(xs, xo, rtol=1e-6, atol=1e-12)
-    Ad2, xs2 = sample_spd(400, 0.1, 471014)
-    S2 = sp.csr_array(Ad2)
-    y2 = S2 @ xs2
-    A2 = bd.dist_csr_array.from_global(S2)
-    l2, h2 = A2.row_plan.rows(rank)
-    xl2, it2 = bd.cg(A2, y2[l2:h2], tol=1e-8)
-    xg2 = bd.gather_vector(xl2, A2.row_plan, rank)
-    assert np.allclose(S2 @ xg2, y2)
+        # 3. sharded CG == oracle CG on the global problem (same iteration count, same solution)
+        b = np.ones(N)
+        xl, iters = bd.cg(Ad, b[lo:hi], tol=1e-8, maxiter=500)
+        xs = bd.gather_vector(xl, Ad.row_plan, rank)
+        xo, io = orc.cg(lambda v: orc.spmv(G.indptr, G.indices, G.data, v), b, tol=1e-8, maxiter=500)
+        assert iters == io, (peer, iters, io)
+        assert np.allclose(xs, xo, rtol=1e-6, atol=1e-12)
+        # scalars all-reduced through peer memory are bit-identical on every rank
+        t = torch.tensor([float(rank + 1) * 0.1], dtype=torch.float64, device="cuda")
+        Ad.allreduce(t)
+        ref = sum((r + 1) * 0.1 for r in range(world))
+        assert abs(float(t[0]) - ref) < 1e-12
+        Ad2, xs2 = sample_spd(400, 0.1, 471014)
+        S2 = sp.csr_array(Ad2)
+        y2 = S2 @ xs2
+        A2 = bd.dist_csr_array.from_global(S2)
+        l2, h2 = A2.row_plan.rows(rank)
+        xl2, it2 = bd.cg(A2, y2[l2:h2], tol=1e-8)
+        xg2 = bd.gather_vector(xl2, A2.row_plan, rank)
+        assert np.allclose(S2 @ xg2, y2)
+        Ad.check_peer(); A2.check_peer()
+        Ad.close(); A2.close()
 
     dist.barrier()
     if rank == 0:
