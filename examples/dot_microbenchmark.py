@@ -1,0 +1,43 @@
+#!/usr/bin/env python
+"""SpMV throughput on a banded matrix -- the workload of the reference's examples/dot_microbenchmark.py
+(diags([1]*k, centred offsets, shape (n, n), csr), x = ones, one warm-up then `-i` timed products; prints
+"Iterations / sec").  The Summit logs in the reference were produced with `-nnz-per-row 11 -n 10000000 -i 100`.
+
+    python examples/dot_microbenchmark.py -n 10000000 -i 100 [--package scipy]
+"""
+import argparse
+
+import numpy as np
+
+from common import select_package
+
+ap = argparse.ArgumentParser()
+ap.add_argument("-n", type=int, default=10_000_000)
+ap.add_argument("-i", type=int, default=100, dest="iters")
+ap.add_argument("-nnz-per-row", type=int, default=11, dest="k")
+ap.add_argument("--package", default="b200")
+args = ap.parse_args()
+
+name, timer, xp, sparse, _, on_device = select_package()
+offsets = [d - args.k // 2 for d in range(args.k)]
+A = sparse.diags([1] * args.k, offsets, shape=(args.n, args.n), format="csr", dtype=np.float64)
+x = xp.ones(args.n)
+y = xp.zeros(args.n)
+
+
+def product():
+    global y
+    if on_device:
+        A.dot(x, out=y)
+    else:
+        y = A.dot(x)
+
+
+product()  # warm-up (plan creation / page faults)
+timer.start()
+for _ in range(args.iters):
+    product()
+ms = timer.stop()
+nnz = A.nnz
+print(f"Iterations / sec: {args.iters / (ms / 1e3):.3f}")
+print(f"[{name}] n={args.n} nnz={nnz} {2 * nnz * args.iters / (ms * 1e-3) / 1e9:.1f} GFLOP/s")

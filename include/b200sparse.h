@@ -116,6 +116,11 @@ int         b2s_cg_update_xr(int vt, int64_t n, void* x, void* r, const void* p,
                              const void* rho_dev, const void* pq_dev, void* rr_out_dev,
                              void* ws, void* stream);
 
+/* diag_out[i] = A[i,i] (0 if absent). Replaces CSR_DIAGONAL / compute_diag_kernel
+ * (src/sparse/array/csr/get_diagonal.cu:25-39), used by the GMG example's Jacobi smoother. */
+int         b2s_csr_diagonal(int vt, int it, int pt, int64_t nrows, const void* indptr,
+                             const void* indices, const void* vals, void* diag_out, void* stream);
+
 /* ---- CSR x CSR -> CSR SpGEMM  (replaces SpGEMMCSRxCSRxCSRGPU::gpu_variant ->
  *      cusparseSpGEMM_{workEstimation,compute,copy}, src/sparse/array/csr/
  *      spgemm_csr_csr_csr.cu:33-272, and the NNZ/fill pair of the CPU branch,

@@ -135,6 +135,14 @@ def cg_update_xr(x, r, p, q, rho, pq, rr_out):
     return rr_out
 
 
+def csr_diagonal(indptr, indices, data, nrows: int):
+    _chk_dev(indptr, indices, data)
+    out = torch.empty(nrows, dtype=data.dtype, device=data.device)
+    _lib.check(L.b2s_csr_diagonal(vt_code(data.dtype), idx_code(indices.dtype), idx_code(indptr.dtype), nrows,
+                                  ptr(indptr), ptr(indices), ptr(data), ptr(out), _stream()), "b2s_csr_diagonal")
+    return out
+
+
 def copy(dst, src_ptr: int, n: int):
     """dst[:n] = *(src_ptr) -- src may be a peer-mapped (IPC) pointer."""
     _chk_dev(dst)

@@ -234,15 +234,31 @@ class csr_array:
     toarray = todense
 
     def transpose(self, copy=False):
-        # host-side (construction path only; reference does CSR.T via CSC aliasing, csc.py:317-324)
-        t = self.to_scipy_sparse_csr().T.tocsr()
-        return csr_array(t)
+        """CSR of the transpose (construction path: the reference reaches it through CSC aliasing,
+        csc.py:317-324).  Counting sort by column with plain tensor ops on the device."""
+        nrows, ncols = self.shape
+        dev = self.device
+        counts = (self._indptr[1:] - self._indptr[:-1]).to(torch.int64)
+        rows = torch.repeat_interleave(torch.arange(nrows, dtype=torch.int64, device=dev), counts)
+        cols = self._indices.to(torch.int64)
+        order = torch.argsort(cols * max(nrows, 1) + rows)
+        t_counts = torch.bincount(cols, minlength=ncols)
+        t_indptr = torch.zeros(ncols + 1, dtype=torch.int64, device=dev)
+        torch.cumsum(t_counts, 0, out=t_indptr[1:])
+        idx_dt = torch.int64 if (_force_wide() or nrows > _INT32_MAX) else torch.int32
+        ptr_dt = torch.int64 if (_force_wide() or self.nnz > _INT32_MAX) else torch.int32
+        return csr_array._from_parts(t_indptr.to(ptr_dt), rows[order].to(idx_dt), self._data[order], (ncols, nrows))
 
     T = property(transpose)
 
     def diagonal(self, k=0):
+        """Main diagonal as a device vector (reference csr.py:629-649; only k = 0 there too)."""
         if k != 0:
             raise NotImplementedError
+        rows, cols = self.shape
+        if self._data.is_cuda:
+            d = _ops.csr_diagonal(self._indptr, self._indices, self._data, rows)
+            return d[: min(rows, cols)]
         return to_device(self.to_scipy_sparse_csr().diagonal())
 
     # -- the hot path -----------------------------------------------------------------------------------

@@ -170,6 +170,29 @@ copy1_kernel(int64_t nbytes, unsigned char* __restrict__ dst, const unsigned cha
   for (int64_t i = tid; i < nbytes; i += nth) dst[i] = src[i];
 }
 
+// ---- diagonal of a CSR matrix (GMG's weighted-Jacobi smoother) --------------------------------------
+// diag[i] = value stored at (i, i), 0 if absent; with duplicate entries the last one wins, as in the
+// reference's compute_diag_kernel (src/sparse/array/csr/get_diagonal.cu:25-39).  One thread per row.
+template <typename V, typename I, typename P>
+__global__ void __launch_bounds__(VTHREADS)
+csr_diagonal_kernel(int64_t nrows, const P* __restrict__ indptr, const I* __restrict__ indices,
+                    const V* __restrict__ vals, V* __restrict__ diag) {
+  const int64_t i = (int64_t)blockIdx.x * VTHREADS + threadIdx.x;
+  if (i >= nrows) return;
+  V d = (V)0;
+  for (int64_t k = (int64_t)indptr[i]; k < (int64_t)indptr[i + 1]; k++)
+    if ((int64_t)indices[k] == i) d = vals[k];
+  diag[i] = d;
+}
+
+template <typename V, typename I, typename P>
+static void launch_diag(int64_t nrows, const void* indptr, const void* indices, const void* vals, void* diag,
+                        cudaStream_t st) {
+  const unsigned grid = (unsigned)((nrows + VTHREADS - 1) / VTHREADS);
+  csr_diagonal_kernel<V, I, P><<<grid, VTHREADS, 0, st>>>(nrows, (const P*)indptr, (const I*)indices,
+                                                         (const V*)vals, (V*)diag);
+}
+
 static bool vec_aligned(const void* a, const void* b = nullptr, const void* c = nullptr, const void* d = nullptr) {
   return aligned16(a) && aligned16(b) && aligned16(c) && aligned16(d);
 }
@@ -240,6 +263,27 @@ int b2s_cg_update_xr(int vt, int64_t n, void* x, void* r, const void* p, const v
   const int vec_ok = vec_aligned(x, r, p, q);
   if (vt == B2S_F32) cg_update_xr_kernel<float><<<grid, VTHREADS, 0, st>>>(n, (float*)x, (float*)r, (const float*)p, (const float*)q, (const float*)rho_dev, (const float*)pq_dev, (float*)rr_out_dev, ws, vec_ok);
   else               cg_update_xr_kernel<double><<<grid, VTHREADS, 0, st>>>(n, (double*)x, (double*)r, (const double*)p, (const double*)q, (const double*)rho_dev, (const double*)pq_dev, (double*)rr_out_dev, ws, vec_ok);
+  B2S_LAUNCH_CHECK();
+  return B2S_OK;
+}
+
+int b2s_csr_diagonal(int vt, int it, int pt, int64_t nrows, const void* indptr, const void* indices,
+                     const void* vals, void* diag_out, void* stream) {
+  B2S_CHECK_ARG(vt == B2S_F32 || vt == B2S_F64, "bad value type code %d", vt);
+  B2S_CHECK_ARG((it == B2S_I32 || it == B2S_I64) && (pt == B2S_I32 || pt == B2S_I64), "bad index type codes");
+  B2S_CHECK_ARG(nrows >= 0, "negative dimension");
+  if (nrows == 0) return B2S_OK;
+  B2S_CHECK_ARG(indptr && diag_out, "NULL pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+#define B2S_DIAG(V)                                                                                   \
+  do {                                                                                                \
+    if (it == B2S_I32 && pt == B2S_I32) launch_diag<V, int32_t, int32_t>(nrows, indptr, indices, vals, diag_out, st); \
+    else if (it == B2S_I32) launch_diag<V, int32_t, int64_t>(nrows, indptr, indices, vals, diag_out, st);             \
+    else if (pt == B2S_I32) launch_diag<V, int64_t, int32_t>(nrows, indptr, indices, vals, diag_out, st);             \
+    else launch_diag<V, int64_t, int64_t>(nrows, indptr, indices, vals, diag_out, st);                                \
+  } while (0)
+  if (vt == B2S_F32) B2S_DIAG(float); else B2S_DIAG(double);
+#undef B2S_DIAG
   B2S_LAUNCH_CHECK();
   return B2S_OK;
 }

@@ -367,8 +367,15 @@ def _try_capture(fn):
             runtime.workspace()  # allocate the reduction workspace of the capture stream before capturing
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g, stream=side):
-            fn()
+        # capture_begin/end directly: the torch.cuda.graph() context manager also runs gc.collect() and
+        # torch.cuda.empty_cache(), which costs seconds when gigabytes of assembly temporaries are cached
+        with torch.cuda.stream(side):
+            g.capture_begin()
+            try:
+                fn()
+            finally:
+                g.capture_end()
+        cur.wait_stream(side)
         torch.cuda.synchronize()
         return _GraphOnCurrent(g)
     except Exception as exc:  # pragma: no cover - depends on driver / NCCL capture support
