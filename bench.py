@@ -369,9 +369,55 @@ def run_gpu(args):
         "clocks": clocks,
         "gpu_launches": args.steps * world,
     }
+    if world == 1 and not args.no_extras:
+        line["extras"] = other_rows_of_the_path(torch, gallery, peak)
     line.update(extra)
     print(json.dumps(line), flush=True)
     return 0
+
+
+def other_rows_of_the_path(torch, gallery, peak):
+    """The other hot-path rows of SURVEY 8 at N=1, so one bench line records them all (bounded: ~5 s).
+    CG: examples/pde.py -nx 4096 -ny 4096 -throughput -max_iter 300 (BASELINE config 3).
+    SpGEMM: examples/spgemm_microbenchmark.py shape (banded, 11 nnz/row) at n = 1M."""
+    from legate.sparse_b200 import linalg
+
+    out = {}
+    try:
+        A = gallery.laplacian_5pt(4094, 4094, np.float64)
+        b = torch.ones(A.shape[0], dtype=torch.float64, device="cuda")
+        linalg.cg(A, b, tol=1e-10, maxiter=30)
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        x, iters = linalg.cg(A, b, tol=1e-10, maxiter=300)
+        e.record()
+        torch.cuda.synchronize()
+        ms = s.elapsed_time(e)
+        N, nnz = A.shape[0], A.nnz
+        fused_bytes = nnz * 12 + N * 20 + 9 * 8 * N
+        out["cg_pde4096"] = {"iters": iters, "it_per_s": iters / (ms * 1e-3), "us_per_iter": ms / iters * 1e3,
+                             "model_bytes_per_iter": fused_bytes,
+                             "frac_of_hbm_peak": fused_bytes * iters / (ms * 1e-3) / 1e9 / peak}
+        del A, b, x
+    except Exception as exc:  # pragma: no cover
+        out["cg_error"] = str(exc)
+    try:
+        B = gallery.banded(1_000_000, 11, np.float64)
+        C = B @ B
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            C = B @ B
+            torch.cuda.synchronize()
+            ts.append(time.perf_counter() - t0)
+        info = C.spgemm_info
+        out["spgemm_banded1m"] = {"ms": min(ts) * 1e3, "products": info["products"], "nnz_c": info["nnz"],
+                                  "gflops": 2 * info["products"] / min(ts) / 1e9}
+    except Exception as exc:  # pragma: no cover
+        out["spgemm_error"] = str(exc)
+    return out
 
 
 def main():
@@ -382,6 +428,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU-baseline sampling (rank 0, N=1)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the CG / SpGEMM side measurements at N=1")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -54,24 +54,49 @@ def world():
 
 
 class RowBlockPlan:
-    """Static 1-D row-block partition of N rows over P ranks (reference csr.py:238-246)."""
+    """Static 1-D row-block partition of N rows over P ranks.
 
-    def __init__(self, nrows: int, nranks: int):
+    Default: equal row tiles, T = ceil(N/P) (reference sparse/csr.py:238-246).  `balanced()` instead cuts the
+    rows so every rank holds about nnz/P nonzeros -- the reference's `csr_array.balance()` (sparse/base.py:198-282:
+    equal nnz tiles, preimage to rows, made disjoint), which matters for power-law matrices."""
+
+    def __init__(self, nrows: int, nranks: int, bounds=None):
         self.nrows = int(nrows)
         self.nranks = int(nranks)
-        self.tile = (self.nrows + self.nranks - 1) // self.nranks if self.nranks > 0 else 0
+        if bounds is None:
+            t = (self.nrows + self.nranks - 1) // self.nranks if self.nranks > 0 else 0
+            bounds = [min(r * t, self.nrows) for r in range(self.nranks + 1)]
+            self.uniform = True
+            self.tile = t
+        else:
+            bounds = [int(b) for b in bounds]
+            assert len(bounds) == self.nranks + 1 and bounds[0] == 0 and bounds[-1] == self.nrows
+            assert all(b1 >= b0 for b0, b1 in zip(bounds, bounds[1:]))
+            self.uniform = False
+            self.tile = max([b1 - b0 for b0, b1 in zip(bounds, bounds[1:])] + [0])
+        self.bounds = bounds
+
+    @classmethod
+    def balanced(cls, indptr, nranks: int):
+        """Row cuts at the first row whose starting nonzero reaches k*nnz/P."""
+        ip = np.asarray(to_host(indptr)).astype(np.int64)
+        nrows, nnz = ip.shape[0] - 1, int(ip[-1])
+        targets = [(k * nnz) // nranks for k in range(1, nranks)]
+        cuts = [int(np.searchsorted(ip, t, side="left")) for t in targets]
+        bounds = [0] + [min(max(c, 0), nrows) for c in cuts] + [nrows]
+        for k in range(1, len(bounds)):
+            bounds[k] = max(bounds[k], bounds[k - 1])
+        return cls(nrows, nranks, bounds)
 
     def rows(self, rank: int):
-        lo = min(rank * self.tile, self.nrows)
-        hi = min(lo + self.tile, self.nrows)
-        return lo, hi
+        return self.bounds[rank], self.bounds[rank + 1]
 
     def owner(self, row: int) -> int:
-        return min(row // self.tile, self.nranks - 1) if self.tile else 0
+        return max(0, min(int(np.searchsorted(self.bounds, row, side="right")) - 1, self.nranks - 1))
 
     @property
     def padded(self) -> int:
-        return self.tile * self.nranks
+        return max(self.tile * self.nranks, self.nrows)
 
 
 def _intersect(a_lo, a_hi, b_lo, b_hi):
@@ -153,7 +178,7 @@ class dist_csr_array:
     (ncols is partitioned by the same plan as nrows for the square matrices of the hot path; for
     rectangular ones x is partitioned by its own RowBlockPlan over ncols)."""
 
-    def __init__(self, local: csr_array, global_shape, rank=None, nranks=None, group=None):
+    def __init__(self, local: csr_array, global_shape, rank=None, nranks=None, group=None, row_plan=None):
         r, w = world()
         self.rank = r if rank is None else rank
         self.nranks = w if nranks is None else nranks
@@ -161,8 +186,9 @@ class dist_csr_array:
         self.local = local
         self.shape = tuple(int(s) for s in global_shape)
         self.dtype = local.dtype
-        self.row_plan = RowBlockPlan(self.shape[0], self.nranks)
-        self.col_plan = RowBlockPlan(self.shape[1], self.nranks)
+        self.row_plan = RowBlockPlan(self.shape[0], self.nranks) if row_plan is None else row_plan
+        # vectors are sharded like the rows when the matrix is square (CG); otherwise by equal tiles of ncols
+        self.col_plan = self.row_plan if self.shape[0] == self.shape[1] else RowBlockPlan(self.shape[1], self.nranks)
         self.row_lo, self.row_hi = self.row_plan.rows(self.rank)
         assert local.shape == (self.row_hi - self.row_lo, self.shape[1]), (local.shape, self.shape)
         self._xbuf = {}
@@ -170,7 +196,7 @@ class dist_csr_array:
 
     # -- construction -------------------------------------------------------------------------------
     @classmethod
-    def from_global(cls, A, rank=None, nranks=None):
+    def from_global(cls, A, rank=None, nranks=None, balanced=False):
         """Slice this rank's shard out of a replicated global matrix (scipy CSR or csr_array). Used by
         tests and small problems; large runs assemble shards directly (gallery.*(row_lo=, row_hi=))."""
         import scipy.sparse as sp
@@ -179,12 +205,12 @@ class dist_csr_array:
         rank = r if rank is None else rank
         nranks = w if nranks is None else nranks
         S = A.to_scipy_sparse_csr() if isinstance(A, csr_array) else sp.csr_array(A)
-        plan = RowBlockPlan(S.shape[0], nranks)
+        plan = RowBlockPlan.balanced(S.indptr, nranks) if balanced else RowBlockPlan(S.shape[0], nranks)
         lo, hi = plan.rows(rank)
         klo, khi = int(S.indptr[lo]), int(S.indptr[hi])
         local = csr_array((S.data[klo:khi], S.indices[klo:khi], S.indptr[lo : hi + 1] - klo),
                           shape=(hi - lo, S.shape[1]))
-        return cls(local, S.shape, rank=rank, nranks=nranks)
+        return cls(local, S.shape, rank=rank, nranks=nranks, row_plan=plan)
 
     # -- exchange plan --------------------------------------------------------------------------------
     def _build_exchange(self):
@@ -226,6 +252,8 @@ class dist_csr_array:
         if mode == "auto":
             # all-gather moves (P-1)*T elements into every rank; use p2p windows when they are much smaller
             mode = "p2p" if total_need * 4 < (self.nranks - 1) * self.col_plan.tile else "allgather"
+        if not self.col_plan.uniform and mode == "allgather":
+            mode = "p2p"  # the in-place all-gather needs equal shards; uneven (balanced) plans exchange windows
         self.exchange_mode = mode if self.nranks > 1 else "none"
         self.recv_elems = need
         # NVLink peer-memory path (csrc/peer.cu), for ranks that are CUDA devices of one box:
@@ -291,7 +319,7 @@ class dist_csr_array:
         if self.exchange_mode == "none":
             return
         if self.exchange_mode == "allgather":
-            lo, hi = self.my_cols
+            assert self.col_plan.uniform
             T = self.col_plan.tile
             src = full[self.rank * T : (self.rank + 1) * T]
             dist.all_gather_into_tensor(full, src, group=self.group)
@@ -356,6 +384,55 @@ class dist_csr_array:
         return gather_vector(y, self.row_plan, self.rank, self.group)
 
 
+def _allgather_varlen(t: torch.Tensor, group=None):
+    """All-gather 1-D tensors of different lengths; returns the list of per-rank tensors."""
+    world = dist.get_world_size(group)
+    sizes = [None] * world
+    dist.all_gather_object(sizes, int(t.shape[0]), group=group)
+    m = max(max(sizes), 1)
+    pad = torch.zeros(m, dtype=t.dtype, device=t.device)
+    pad[: t.shape[0]] = t
+    out = torch.empty(m * world, dtype=t.dtype, device=t.device)
+    dist.all_gather_into_tensor(out, pad, group=group)
+    return [out[q * m : q * m + sizes[q]] for q in range(world)]
+
+
+def gather_matrix(A: "dist_csr_array") -> csr_array:
+    """Replicate a row-sharded matrix on every rank (all-gather of indptr / indices / data shards)."""
+    if A.nranks == 1:
+        return A.local
+    loc = A.local
+    counts = (loc.indptr[1:] - loc.indptr[:-1]).to(torch.int64)
+    all_counts = torch.cat(_allgather_varlen(counts, A.group))
+    indptr = torch.zeros(all_counts.shape[0] + 1, dtype=torch.int64, device=all_counts.device)
+    torch.cumsum(all_counts, 0, out=indptr[1:])
+    indices = torch.cat(_allgather_varlen(loc.indices, A.group))
+    data = torch.cat(_allgather_varlen(loc.data, A.group))
+    ptr_dt = torch.int32 if int(indptr[-1]) < 2**31 - 1 else torch.int64
+    return csr_array._from_parts(indptr.to(ptr_dt), indices, data, A.shape)
+
+
+def spgemm(A: "dist_csr_array", B: "dist_csr_array") -> "dist_csr_array":
+    """C = A @ B for row-sharded operands: B is replicated (all-gather once), every rank multiplies its
+    rows of A, and C comes back row-sharded with the same row plan as A -- the partitioning of the
+    reference's GPU branch (sparse/csr.py:1322-1389: rows of the left operand tiled, the right operand
+    gathered by image, per-GPU local CSR).  `C.nnz_offset` is this shard's position in the global nnz
+    order (exclusive scan of the per-rank nnz; the reference does that scan on the host,
+    scan_local_results_and_scale_pos csr.py:827-859)."""
+    assert A.shape[1] == B.shape[0]
+    Bfull = gather_matrix(B)
+    Cl = A.local @ Bfull
+    C = dist_csr_array(Cl, (A.shape[0], B.shape[1]), rank=A.rank, nranks=A.nranks, group=A.group)
+    nnzs = [None] * A.nranks
+    if A.nranks > 1:
+        dist.all_gather_object(nnzs, Cl.nnz, group=A.group)
+    else:
+        nnzs[0] = Cl.nnz
+    C.nnz_offset = int(sum(nnzs[: A.rank]))
+    C.global_nnz = int(sum(nnzs))
+    return C
+
+
 def allreduce_scalar(t: torch.Tensor, group=None) -> torch.Tensor:
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
@@ -366,12 +443,14 @@ def gather_vector(v_local: torch.Tensor, plan: RowBlockPlan, rank: int, group=No
     """All ranks receive the concatenated global vector (host numpy)."""
     if plan.nranks == 1:
         return to_host(v_local)
-    T = plan.tile
+    T = max(plan.tile, 1)
     pad = torch.zeros(T, dtype=v_local.dtype, device=v_local.device)
     pad[: v_local.shape[0]] = v_local
     full = torch.empty(T * plan.nranks, dtype=v_local.dtype, device=v_local.device)
     dist.all_gather_into_tensor(full, pad, group=group)
-    return to_host(full[: plan.nrows])
+    if plan.uniform:
+        return to_host(full[: plan.nrows])
+    return to_host(torch.cat([full[q * T : q * T + (plan.bounds[q + 1] - plan.bounds[q])] for q in range(plan.nranks)]))
 
 
 def cg(A: dist_csr_array, b_local, x0_local=None, tol=1e-08, maxiter=None, callback=None, conv_test_iters=25):

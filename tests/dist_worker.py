@@ -86,6 +86,19 @@ def main():
         Ad.check_peer(); A2.check_peer()
         Ad.close(); A2.close()
 
+    # 4. row-sharded SpGEMM: B all-gathered, C row-sharded with exact structure
+    os.environ["B2S_PEER"] = "1"
+    os.environ["B2S_PEER_HALO"] = "0"
+    SA = sp.random(900, 700, density=0.01, random_state=rng, format="csr", dtype=np.float64)
+    SB = sp.random(700, 800, density=0.012, random_state=rng, format="csr", dtype=np.float64)
+    Ca = bd.spgemm(bd.dist_csr_array.from_global(SA), bd.dist_csr_array.from_global(SB))
+    ref = (SA @ SB).tocsr()
+    ref.sort_indices()
+    Gc = bd.gather_matrix(Ca).to_scipy_sparse_csr()
+    assert np.array_equal(Gc.indptr, ref.indptr) and np.array_equal(Gc.indices, ref.indices)
+    assert np.allclose(Gc.data, ref.data, rtol=1e-12)
+    assert Ca.global_nnz == ref.nnz
+
     dist.barrier()
     if rank == 0:
         print(f"DIST_WORKER_OK world={world}")

@@ -57,8 +57,16 @@ def _patch_ops_with_oracle():
         rr_out[:] = torch.from_numpy(orc.dot(r.numpy(), r.numpy()))
         return rr_out
 
+    def spgemm(a_ptr, a_idx, a_val, b_ptr, b_idx, b_val, shape_a, shape_b):
+        cp, ci, cv = orc.spgemm((a_ptr.numpy(), a_idx.numpy(), a_val.numpy()), (b_ptr.numpy(), b_idx.numpy(), b_val.numpy()),
+                                shape_a, shape_b, sort_rows=True)
+        return (torch.from_numpy(cp), torch.from_numpy(ci.astype(np.int32)), torch.from_numpy(cv),
+                {"nnz": int(cp[-1]), "products": 0, "dense_rows": 0})
+
     _ops.spmv, _ops.spmv_dot, _ops.axpby, _ops.dot, _ops.cg_update_xr = spmv, spmv_dot, axpby, dot, cg_update_xr
+    _ops.spgemm = spgemm
     csr_mod.csr_array._get_plan = lambda self: None
+    csr_mod.runtime.require_cuda = lambda what: None
 
 
 def _worker(rank, world, port, case, q):
@@ -101,6 +109,37 @@ def _worker(rank, world, port, case, q):
             A = bd.dist_csr_array.from_global(S)
             assert A.exchange_mode == "allgather"
             assert np.allclose(A.matvec_global(x[:300]), S @ x[:300], rtol=1e-12)
+            # nnz-balanced row cuts (reference csr_array.balance(), tests/integration/test_csr_misc.py:26-37)
+            rng = np.random.default_rng(12)
+            lens = np.minimum((rng.pareto(1.1, 600) * 3).astype(np.int64), 400)
+            rows = np.repeat(np.arange(600), lens)
+            cols = rng.integers(0, 600, rows.shape[0])
+            S = sp.coo_array((rng.standard_normal(rows.shape[0]), (rows, cols)), shape=(600, 600)).tocsr()
+            S.sum_duplicates()
+            A = bd.dist_csr_array.from_global(S, balanced=True)
+            nnzs = [None] * world
+            dist.all_gather_object(nnzs, A.local.nnz)
+            assert sum(nnzs) == S.nnz and max(nnzs) <= S.nnz / world + lens.max() + 1
+            assert not A.row_plan.uniform or world == 1
+            xs = rng.standard_normal(600)
+            assert np.allclose(A.matvec_global(xs), S @ xs, rtol=1e-12, atol=1e-12)
+            out["ok"] = True
+        elif case == "spgemm":
+            rng = np.random.default_rng(5)
+            SA = sp.random(130, 90, density=0.05, random_state=rng, format="csr", dtype=np.float64)
+            SB = sp.random(90, 110, density=0.06, random_state=rng, format="csr", dtype=np.float64)
+            A, B = bd.dist_csr_array.from_global(SA), bd.dist_csr_array.from_global(SB)
+            C = bd.spgemm(A, B)
+            ref = (SA @ SB).tocsr()
+            ref.sort_indices()
+            lo, hi = C.row_plan.rows(rank)
+            loc = C.local.to_scipy_sparse_csr()
+            assert np.array_equal(loc.indptr, ref.indptr[lo : hi + 1] - ref.indptr[lo])
+            assert np.array_equal(loc.indices, ref.indices[ref.indptr[lo] : ref.indptr[hi]])
+            assert np.allclose(loc.data, ref.data[ref.indptr[lo] : ref.indptr[hi]], rtol=1e-12)
+            assert C.nnz_offset == ref.indptr[lo] and C.global_nnz == ref.nnz
+            G = bd.gather_matrix(C).to_scipy_sparse_csr()
+            assert (G != ref).nnz == 0
             out["ok"] = True
         elif case == "cg":
             from oracle import oracle as orc
@@ -150,6 +189,10 @@ def test_sharded_spmv_gloo(world):
 
 def test_sharded_cg_gloo():
     _run(2, "cg")
+
+
+def test_sharded_spgemm_gloo():
+    _run(3, "spgemm")
 
 
 def test_row_block_plan_matches_oracle(oracle, golden):

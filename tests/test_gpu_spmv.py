@@ -108,6 +108,10 @@ def _random_csr(rng, nrows, ncols, row_lens, dtype):
 STRUCTURES = {
     "uniform5": lambda rng, n: np.full(n, 5),
     "uniform32": lambda rng, n: np.full(n, 32),
+    "uniform8": lambda rng, n: np.full(n, 8),
+    "uniform6": lambda rng, n: np.full(n, 6),
+    "uniform64": lambda rng, n: np.full(n, 64),
+    "uniform200": lambda rng, n: np.full(n, 200),
     "ragged": lambda rng, n: rng.integers(0, 40, n),
     "mostly_empty": lambda rng, n: (rng.random(n) < 0.05) * rng.integers(1, 9, n),
     "all_empty": lambda rng, n: np.zeros(n, dtype=np.int64),
@@ -279,3 +283,25 @@ def test_plan_rejects_mismatched_matrix():
     y = torch.empty(2000, dtype=torch.float64, device="cuda")
     with pytest.raises(_lib.B200SparseError, match="different matrix"):
         _ops.spmv(B.indptr, B.indices, B.data, x, y, B.shape, plan=A._get_plan())
+
+
+@pytest.mark.parametrize("filename", MTX_FILES)
+def test_balance_row_partitions(filename):
+    """reference tests/integration/test_csr_misc.py:26-37: SpMV still equals scipy after arr.balance()."""
+    arr = sparse.io.mmread(mtx_path(filename)).tocsr()
+    arr.balance()
+    s = sio.mmread(mtx_path(filename), spmatrix=False).tocsr()
+    vec = np.random.default_rng(2).random(arr.shape[0])
+    assert np.allclose(arr @ vec, s @ vec)
+    assert np.allclose(arr.dot(vec), s.dot(vec))
+    vec = np.random.default_rng(3).random((arr.shape[0], 1))
+    assert np.allclose(arr @ vec, s @ vec)
+
+
+@pytest.mark.parametrize("filename", MTX_FILES)
+def test_csr_transpose_and_diagonal(filename):
+    """reference test_csr_misc.py:40-44 (transpose) + the diagonal kernel used by GMG."""
+    arr = sparse.io.mmread(mtx_path(filename)).tocsr()
+    s = sio.mmread(mtx_path(filename), spmatrix=False).tocsr()
+    assert np.array_equal(arr.T.todense(), np.ascontiguousarray(s.T.toarray()))
+    assert np.array_equal(arr.diagonal().cpu().numpy(), s.diagonal())

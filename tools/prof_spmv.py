@@ -18,6 +18,10 @@ elif wl == "banded":
     A = gallery.banded(10_000_000, 11, np.float64)
 elif wl == "r32":
     A = gallery.random_fixed(10_000_000, 10_000_000, 32, np.float32)
+elif wl == "b32f32":
+    A = gallery.banded(10_000_000, 32, np.float32)
+elif wl == "l5f32":
+    A = gallery.laplacian_5pt(3162, 3162, np.float32)
 else:
     raise SystemExit("unknown workload")
 _lib.check(_lib.lib.b2s_spmv_set_config(cfg, waves))  # cfg < 0: automatic
