@@ -49,15 +49,9 @@ struct __align__(16) PlanEntry {
   X(4, 1, 4, 6, 2, 4)       \
   X(5, 1, 4, 8, 2, 3)       \
   X(6, 1, 4, 3, 2, 8)       \
-  X(7, 1, 4, 2, 2, 10)      \
-  X(8, 1, 2, 4, 2, 12)      \
-  X(9, 1, 2, 8, 2, 8)       \
-  X(10, 1, 3, 4, 2, 8)      \
-  X(11, 1, 4, 4, 2, 7)      \
-  X(12, 1, 8, 2, 2, 4)      \
-  X(13, 1, 6, 4, 2, 4)      \
-  X(14, 1, 4, 4, 3, 4)      \
-  X(15, 1, 2, 6, 2, 10)
+  X(7, 1, 3, 4, 2, 8)       \
+  X(8, 1, 6, 4, 2, 4)       \
+  X(9, 1, 4, 4, 3, 4)
 struct TileCfgRt { int kind, a, b, c, d; };
 static const TileCfgRt kCfgs[] = {
 #define X(ID, K, A, B, C, D) {K, A, B, C, D},
@@ -109,7 +103,8 @@ __global__ void spmv_plan_kernel(int64_t nrows, const P* __restrict__ indptr, in
 // fixed-degree graphs, interior rows of banded matrices), else 0.  Such tiles can be reduced straight from
 // registers (see the uniform fast path of spmv_tma_kernel).
 template <typename P>
-__global__ void spmv_plan_uniform_kernel(const P* __restrict__ indptr, int64_t ntiles, PlanEntry* __restrict__ plan) {
+__global__ void spmv_plan_uniform_kernel(const P* __restrict__ indptr, int64_t ntiles, PlanEntry* __restrict__ plan,
+                                         int ept, unsigned long long* __restrict__ qualifying) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= ntiles) return;
   const int r0 = plan[t].row, r1 = plan[t + 1].row;
@@ -121,6 +116,10 @@ __global__ void spmv_plan_uniform_kernel(const P* __restrict__ indptr, int64_t n
     L = same ? (int)len0 : 0;
   }
   plan[t].pad = L;
+  // tiles the register fast path can take: L = ept * 2^s (s <= 5) and a 16-byte aligned first nonzero
+  const int lpr = L / ept;
+  if (L > 0 && lpr * ept == L && lpr <= 32 && (lpr & (lpr - 1)) == 0 && (plan[t].k & 3) == 0)
+    atomicAdd(qualifying, 1ull);
 }
 
 __device__ __forceinline__ PlanEntry ld_plan(const PlanEntry* p) {
@@ -405,7 +404,7 @@ struct TmaLayout {
   static constexpr int TOTAL = BAR_OFF + 2 * STAGES * 8;
 };
 
-template <typename V, typename I, typename P, int NC, int G, int STAGES, int MINB, bool DOT>
+template <typename V, typename I, typename P, int NC, int G, int STAGES, int MINB, bool UNI, bool DOT>
 __global__ void __launch_bounds__((NC + 1) * 32, MINB)
 spmv_tma_kernel(int64_t ntiles, int64_t nrows, int64_t nnz, const P* __restrict__ indptr,
                 const I* __restrict__ indices, const V* __restrict__ vals, const V* __restrict__ x,
@@ -528,7 +527,7 @@ spmv_tma_kernel(int64_t ntiles, int64_t nrows, int64_t nnz, const P* __restrict_
       // no row-pointer reads, ~4x fewer instructions per nonzero than the generic reduce below.
       const int UL = m.pad;
       const int lpr = UL / EPT;
-      if (UL > 0 && off == 0 && !has_tail && lpr * EPT == UL && lpr <= 32 && (lpr & (lpr - 1)) == 0) {
+      if (UNI && UL > 0 && off == 0 && !has_tail && lpr * EPT == UL && lpr <= 32 && (lpr & (lpr - 1)) == 0) {
         const int lshift = 31 - __clz(lpr);
         I c[G][EPT];
         V a[G][EPT];
@@ -619,7 +618,8 @@ spmv_tma_kernel(int64_t ntiles, int64_t nrows, int64_t nnz, const P* __restrict_
 
       // ---- reduce ----------------------------------------------------------------------------------------
       const int gshift = lanes_per_row_shift(k1 - k0, nr);
-      const bool skew = gshift > 0 || ((((k1 - k0) + nr - 1) / nr) & 1) == 0;  // even / long rows: rotate the walk
+      // even / long rows: rotate the walk (only compiled into the variant the plan selects for such matrices)
+      const bool skew = UNI && (gshift > 0 || ((((k1 - k0) + nr - 1) / nr) & 1) == 0);
       const int g = 1 << gshift;
       const int lig = ctid & (g - 1);
       const int grp = ctid >> gshift;
@@ -694,6 +694,7 @@ struct SpmvArgs {
   void* y;
   const PlanEntry* plan;
   int vec_ok;
+  int uniform;  // plan found >= 25% ELL-like tiles: use the kernel variant with the register fast path
   const void* w;
   void* dot_out;
   void* ws;
@@ -731,11 +732,11 @@ static int launch_ldg(const SpmvArgs& a) {
   return B2S_OK;
 }
 
-template <typename V, typename I, typename P, int NC, int G, int STAGES, int MINB, bool DOT>
-static int launch_tma(const SpmvArgs& a) {
+template <typename V, typename I, typename P, int NC, int G, int STAGES, int MINB, bool UNI, bool DOT>
+static int launch_tma_u(const SpmvArgs& a) {
   using LY = TmaLayout<V, I, P, NC, G, STAGES>;
   constexpr int THREADS = (NC + 1) * 32;
-  auto kern = spmv_tma_kernel<V, I, P, NC, G, STAGES, MINB, DOT>;
+  auto kern = spmv_tma_kernel<V, I, P, NC, G, STAGES, MINB, UNI, DOT>;
   const size_t smem = LY::TOTAL;
   static bool attr_done = false;
   static int occ = 0;
@@ -758,6 +759,14 @@ static int launch_tma(const SpmvArgs& a) {
                                                 (V*)a.dot_out, a.ws);
   B2S_LAUNCH_CHECK();
   return B2S_OK;
+}
+
+template <typename V, typename I, typename P, int NC, int G, int STAGES, int MINB, bool DOT>
+static int launch_tma(const SpmvArgs& a) {
+  // the register fast path is compiled in only for matrices where the plan found enough uniform tiles, so
+  // the kernel of irregular matrices keeps its smaller code and register footprint
+  if (a.uniform) return launch_tma_u<V, I, P, NC, G, STAGES, MINB, true, DOT>(a);
+  return launch_tma_u<V, I, P, NC, G, STAGES, MINB, false, DOT>(a);
 }
 
 template <typename V, typename I, typename P, int KIND, int A, int B, int C, int D, bool DOT>
@@ -870,6 +879,7 @@ struct PlanHandle {
   int vt, it, pt;
   int cfg;          // tile configuration the device plan was built for
   int use_rowgroup; // 1: matrix judged scattered -> plan-free row-group kernel
+  int use_uniform;  // 1: >= 25% of the tiles are ELL-like -> kernel variant with the register fast path
   int64_t nrows, ncols, nnz, ntiles;
   double lines_per_warp;
   const PlanEntry* dev;
@@ -916,37 +926,46 @@ int b2s_spmv_plan_create(int vt, int it, int pt, int64_t nrows, int64_t ncols, i
   PlanEntry* dev = (PlanEntry*)plan_buf;
   unsigned long long* stat = (unsigned long long*)(dev + ntiles + 1);
   double lines = 0.0;
+  int64_t uniform_tiles = 0;
   if (ntiles > 0) {
     const int64_t T = cfg_T(cfg, vt);
     const unsigned grid = (unsigned)((ntiles + 1 + 255) / 256);
     if (pt == B2S_I32) spmv_plan_kernel<int32_t><<<grid, 256, 0, st>>>(nrows, (const int32_t*)indptr, T, ntiles, dev);
     else               spmv_plan_kernel<int64_t><<<grid, 256, 0, st>>>(nrows, (const int64_t*)indptr, T, ntiles, dev);
     B2S_LAUNCH_CHECK();
+    B2S_CUDA(cudaMemsetAsync(stat, 0, 16, st));
     {
       const unsigned gu = (unsigned)((ntiles + 255) / 256);
-      if (pt == B2S_I32) spmv_plan_uniform_kernel<int32_t><<<gu, 256, 0, st>>>((const int32_t*)indptr, ntiles, dev);
-      else               spmv_plan_uniform_kernel<int64_t><<<gu, 256, 0, st>>>((const int64_t*)indptr, ntiles, dev);
+      const int ept = vt == B2S_F32 ? 4 : 2;
+      if (pt == B2S_I32) spmv_plan_uniform_kernel<int32_t><<<gu, 256, 0, st>>>((const int32_t*)indptr, ntiles, dev, ept, stat + 1);
+      else               spmv_plan_uniform_kernel<int64_t><<<gu, 256, 0, st>>>((const int64_t*)indptr, ntiles, dev, ept, stat + 1);
       B2S_LAUNCH_CHECK();
     }
+    int64_t ns = 0;
     if (nnz >= 64) {
-      int64_t ns = nnz / 32;
+      ns = nnz / 32;
       if (ns > 4096) ns = 4096;
-      B2S_CUDA(cudaMemsetAsync(stat, 0, 16, st));
       const unsigned g2 = (unsigned)((ns * 32 + 255) / 256);
       const int shift = vt == B2S_F32 ? 2 : 3;
       if (it == B2S_I32) spmv_locality_kernel<int32_t><<<g2, 256, 0, st>>>(nnz, (const int32_t*)indices, shift, ns, stat);
       else               spmv_locality_kernel<int64_t><<<g2, 256, 0, st>>>(nnz, (const int64_t*)indices, shift, ns, stat);
       B2S_LAUNCH_CHECK();
-      unsigned long long total = 0;
-      B2S_CUDA(cudaMemcpyAsync(&total, stat, sizeof(total), cudaMemcpyDeviceToHost, st));
-      B2S_CUDA(cudaStreamSynchronize(st));
-      lines = (double)total / (double)ns;
     }
+    unsigned long long totals[2] = {0, 0};
+    B2S_CUDA(cudaMemcpyAsync(totals, stat, sizeof(totals), cudaMemcpyDeviceToHost, st));
+    B2S_CUDA(cudaStreamSynchronize(st));
+    if (ns > 0) lines = (double)totals[0] / (double)ns;
+    uniform_tiles = (int64_t)totals[1];
   }
   PlanHandle* h = new PlanHandle();
   h->magic = kPlanMagic;
   h->vt = vt; h->it = it; h->pt = pt; h->cfg = cfg;
   h->use_rowgroup = lines > 16.0 ? 1 : 0;
+  // kernel flavour: the variant with the register fast path and the conflict-avoiding skewed reduce is used
+  // when >= 25% of the tiles are ELL-like, or rows are long (>= 12) or of even mean length; short odd rows
+  // (e.g. 5-point stencils) keep the lean sequential-reduce variant
+  const int64_t meanL = nrows > 0 ? (nnz + nrows / 2) / nrows : 0;
+  h->use_uniform = (ntiles > 0 && (uniform_tiles * 4 >= ntiles || meanL >= 12 || (meanL > 0 && (meanL & 1) == 0))) ? 1 : 0;
   h->nrows = nrows; h->ncols = ncols; h->nnz = nnz; h->ntiles = ntiles;
   h->lines_per_warp = lines;
   h->dev = dev;
@@ -968,7 +987,7 @@ int b2s_spmv_plan_destroy(void* plan) {
 int b2s_spmv_plan_info(const void* plan, int64_t* out4_host) {
   const PlanHandle* h = (const PlanHandle*)plan;
   B2S_CHECK_ARG(h && h->magic == kPlanMagic && out4_host, "bad plan handle / out pointer");
-  out4_host[0] = h->cfg; out4_host[1] = h->use_rowgroup; out4_host[2] = h->ntiles;
+  out4_host[0] = h->cfg; out4_host[1] = h->use_rowgroup + 2 * h->use_uniform; out4_host[2] = h->ntiles;
   out4_host[3] = (int64_t)(h->lines_per_warp * 1000.0);
   return B2S_OK;
 }
@@ -1015,6 +1034,7 @@ static int spmv_impl(int vt, int it, int pt, int64_t nrows, int64_t ncols, int64
   a.indptr = indptr; a.indices = indices; a.vals = vals; a.x = x; a.y = y;
   a.plan = h->dev;
   a.vec_ok = aligned ? 1 : 0;
+  a.uniform = h->use_uniform;
   a.w = dot ? w : nullptr; a.dot_out = dot ? dot_out : nullptr; a.ws = dot ? ws : nullptr;
   a.st = st;
   if (vt == B2S_F32) {
