@@ -67,11 +67,11 @@ int64_t     b2s_ws_bytes(void);
  * src/sparse/partition/fast_image_range.cu:27-54, bounds_from_partitioned_coordinates.cu).
  *   b2s_spmv_plan_bytes : size of the DEVICE buffer the caller provides (16-byte aligned);
  *   b2s_spmv_plan_create: fills it, samples the column locality of the matrix (mean number
- *       of distinct 128-byte x lines per 32 consecutive nonzeros) to choose between the
- *       TMA-staged tile kernel and the row-group kernel, and returns a small HOST handle.
+ *       of distinct 128-byte x lines per 32 consecutive nonzeros) to choose the tile shape
+ *       (streaming vs deep-gather) and kernel flavour, and returns a small HOST handle.
  *       syncs the stream once (the reference's partition tasks also block, fast_image_range.cu:27-54).
  *   b2s_spmv_plan_destroy: frees the host handle (never the device buffer).
- *   b2s_spmv_plan_info  : out[0]=tile config id, out[1]=bit0 row-group kernel, bit1 uniform-row fast path, out[2]=tiles,
+ *   b2s_spmv_plan_info  : out[0]=tile config id, out[1]=bit0 row-group kernel, bit1 uniform-row fast path, bit2 scattered, out[2]=tiles,
  *                         out[3]=1000*lines-per-warp statistic. */
 int64_t     b2s_spmv_plan_tiles(int vt, int64_t nrows, int64_t nnz);
 int64_t     b2s_spmv_plan_bytes(int vt, int64_t nrows, int64_t nnz);

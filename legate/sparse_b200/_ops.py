@@ -37,7 +37,7 @@ class SpmvPlan:
         self.buf = buf
         out = (_lib.c_i64 * 4)()
         _lib.check(L.b2s_spmv_plan_info(handle, out), "b2s_spmv_plan_info")
-        self.config, self.rowgroup, self.uniform = int(out[0]), bool(out[1] & 1), bool(out[1] & 2)
+        self.config, self.rowgroup, self.uniform, self.scattered = int(out[0]), bool(out[1] & 1), bool(out[1] & 2), bool(out[1] & 4)
         self.tiles, self.lines_per_warp = int(out[2]), out[3] / 1000.0
 
     def set_kernel(self, rowgroup: bool):

@@ -51,7 +51,11 @@ struct __align__(16) PlanEntry {
   X(6, 1, 4, 3, 2, 8)       \
   X(7, 1, 3, 4, 2, 8)       \
   X(8, 1, 6, 4, 2, 4)       \
-  X(9, 1, 4, 4, 3, 4)
+  X(9, 1, 4, 4, 3, 4)       \
+  X(10, 1, 4, 12, 2, 2)     \
+  X(11, 1, 4, 16, 2, 1)     \
+  X(12, 1, 8, 8, 2, 1)      \
+  X(13, 1, 8, 4, 2, 2)
 struct TileCfgRt { int kind, a, b, c, d; };
 static const TileCfgRt kCfgs[] = {
 #define X(ID, K, A, B, C, D) {K, A, B, C, D},
@@ -64,7 +68,14 @@ static int g_waves = 0;  // LDG kind: 0 = one tile per CTA; >0 = grid-stride wit
                          // TMA kind: CTAs per SM cap (0 = occupancy)
 static constexpr int kDefaultCfgF64 = 0;   // 4 consumer warps x 4 groups, 2 stages, 6 CTAs/SM (CAP 1024)
 static constexpr int kDefaultCfgF32 = 6;   // 4 consumer warps x 3 groups, 2 stages, 8 CTAs/SM (CAP 1536)
-static inline int resolve_cfg(int vt) { return g_cfg >= 0 ? g_cfg : (vt == B2S_F32 ? kDefaultCfgF32 : kDefaultCfgF64); }
+// scattered matrices (plan statistic > 16 distinct x lines per warp gather) want many gathers in flight per thread:
+static constexpr int kScatterCfgF64 = 3;   // LDG tiles, 128 threads x 8 nnz, scalar mapping (R32 fp64: 2.01 ms vs 2.09 row-group)
+static constexpr int kScatterCfgF32 = 5;   // TMA tiles, 4 warps x 8 groups = 32 gathers/thread (R32 fp32: 1.33 ms vs 1.78)
+static inline int resolve_cfg(int vt, bool scattered = false) {
+  if (g_cfg >= 0) return g_cfg;
+  if (scattered) return vt == B2S_F32 ? kScatterCfgF32 : kScatterCfgF64;
+  return vt == B2S_F32 ? kDefaultCfgF32 : kDefaultCfgF64;
+}
 
 static inline int cfg_cap(int c, int vt) {
   const TileCfgRt& k = kCfgs[c];
@@ -784,7 +795,8 @@ template <typename V, typename I, typename P, bool DOT>
 static int dispatch_cfg(int cfg, const SpmvArgs& a) {
 #define B2S_CFG_CASE(ID, K, A, B, C, D)                                  \
   case ID:                                                               \
-    if constexpr (ID == kDefaultCfgF64 || ID == kDefaultCfgF32 || (sizeof(I) == 4 && sizeof(P) == 4)) \
+    if constexpr (ID == kDefaultCfgF64 || ID == kDefaultCfgF32 || ID == kScatterCfgF64 || ID == kScatterCfgF32 || \
+                  (sizeof(I) == 4 && sizeof(P) == 4))                                             \
       return launch_cfg<V, I, P, K, A, B, C, D, DOT>(a);                 \
     else                                                                 \
       break;
@@ -880,6 +892,7 @@ struct PlanHandle {
   int cfg;          // tile configuration the device plan was built for
   int use_rowgroup; // 1: matrix judged scattered -> plan-free row-group kernel
   int use_uniform;  // 1: >= 25% of the tiles are ELL-like -> kernel variant with the register fast path
+  int scattered;    // 1: > 16 distinct x lines per warp-wide gather
   int64_t nrows, ncols, nnz, ntiles;
   double lines_per_warp;
   const PlanEntry* dev;
@@ -903,14 +916,21 @@ int b2s_spmv_set_config(int cfg, int waves) {
 int b2s_spmv_get_config(void) { return g_cfg; }
 int b2s_spmv_num_configs(void) { return kNumCfgs; }
 
-int64_t b2s_spmv_plan_tiles(int vt, int64_t nrows, int64_t nnz) {
+static int64_t tiles_for(int cfg, int vt, int64_t nrows, int64_t nnz) {
   if (nrows <= 0 || nnz < 0) return 0;
-  const int64_t T = cfg_T(resolve_cfg(vt), vt);
+  const int64_t T = cfg_T(cfg, vt);
   return (nrows + nnz + T - 1) / T;
 }
 
+int64_t b2s_spmv_plan_tiles(int vt, int64_t nrows, int64_t nnz) {
+  // upper bound over the configurations plan_create may pick (it decides after sampling the matrix)
+  const int64_t a = tiles_for(resolve_cfg(vt, false), vt, nrows, nnz);
+  const int64_t b = tiles_for(resolve_cfg(vt, true), vt, nrows, nnz);
+  return a > b ? a : b;
+}
+
 int64_t b2s_spmv_plan_bytes(int vt, int64_t nrows, int64_t nnz) {
-  // (ntiles + 1) entries + one 16-byte slot for the locality statistic
+  // (ntiles + 1) entries + one 16-byte slot for the plan statistics
   return (b2s_spmv_plan_tiles(vt, nrows, nnz) + 2) * (int64_t)sizeof(PlanEntry);
 }
 
@@ -921,12 +941,30 @@ int b2s_spmv_plan_create(int vt, int it, int pt, int64_t nrows, int64_t ncols, i
   if (int rc = check_common(vt, it, pt, nrows, ncols, nnz, indptr, indices, indices, plan_out, plan_out)) return rc;
   B2S_CHECK_ARG(plan_buf != nullptr && aligned16(plan_buf), "plan buffer must be non-NULL and 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
-  const int cfg = resolve_cfg(vt);
-  const int64_t ntiles = b2s_spmv_plan_tiles(vt, nrows, nnz);
   PlanEntry* dev = (PlanEntry*)plan_buf;
-  unsigned long long* stat = (unsigned long long*)(dev + ntiles + 1);
+  // the statistics slot sits after the largest plan this buffer may hold
+  unsigned long long* stat = (unsigned long long*)(dev + b2s_spmv_plan_tiles(vt, nrows, nnz) + 1);
   double lines = 0.0;
   int64_t uniform_tiles = 0;
+  // 1. column locality (decides the kernel family / tile shape)
+  if (nrows > 0 && nnz >= 64) {
+    int64_t ns = nnz / 32;
+    if (ns > 4096) ns = 4096;
+    B2S_CUDA(cudaMemsetAsync(stat, 0, 16, st));
+    const unsigned g2 = (unsigned)((ns * 32 + 255) / 256);
+    const int shift = vt == B2S_F32 ? 2 : 3;
+    if (it == B2S_I32) spmv_locality_kernel<int32_t><<<g2, 256, 0, st>>>(nnz, (const int32_t*)indices, shift, ns, stat);
+    else               spmv_locality_kernel<int64_t><<<g2, 256, 0, st>>>(nnz, (const int64_t*)indices, shift, ns, stat);
+    B2S_LAUNCH_CHECK();
+    unsigned long long total = 0;
+    B2S_CUDA(cudaMemcpyAsync(&total, stat, sizeof(total), cudaMemcpyDeviceToHost, st));
+    B2S_CUDA(cudaStreamSynchronize(st));
+    lines = (double)total / (double)ns;
+  }
+  const bool scattered = lines > 16.0;
+  const int cfg = resolve_cfg(vt, scattered);
+  const int64_t ntiles = tiles_for(cfg, vt, nrows, nnz);
+  // 2. tile boundaries + uniform-row annotation for the chosen tile shape
   if (ntiles > 0) {
     const int64_t T = cfg_T(cfg, vt);
     const unsigned grid = (unsigned)((ntiles + 1 + 255) / 256);
@@ -934,33 +972,21 @@ int b2s_spmv_plan_create(int vt, int it, int pt, int64_t nrows, int64_t ncols, i
     else               spmv_plan_kernel<int64_t><<<grid, 256, 0, st>>>(nrows, (const int64_t*)indptr, T, ntiles, dev);
     B2S_LAUNCH_CHECK();
     B2S_CUDA(cudaMemsetAsync(stat, 0, 16, st));
-    {
-      const unsigned gu = (unsigned)((ntiles + 255) / 256);
-      const int ept = vt == B2S_F32 ? 4 : 2;
-      if (pt == B2S_I32) spmv_plan_uniform_kernel<int32_t><<<gu, 256, 0, st>>>((const int32_t*)indptr, ntiles, dev, ept, stat + 1);
-      else               spmv_plan_uniform_kernel<int64_t><<<gu, 256, 0, st>>>((const int64_t*)indptr, ntiles, dev, ept, stat + 1);
-      B2S_LAUNCH_CHECK();
-    }
-    int64_t ns = 0;
-    if (nnz >= 64) {
-      ns = nnz / 32;
-      if (ns > 4096) ns = 4096;
-      const unsigned g2 = (unsigned)((ns * 32 + 255) / 256);
-      const int shift = vt == B2S_F32 ? 2 : 3;
-      if (it == B2S_I32) spmv_locality_kernel<int32_t><<<g2, 256, 0, st>>>(nnz, (const int32_t*)indices, shift, ns, stat);
-      else               spmv_locality_kernel<int64_t><<<g2, 256, 0, st>>>(nnz, (const int64_t*)indices, shift, ns, stat);
-      B2S_LAUNCH_CHECK();
-    }
-    unsigned long long totals[2] = {0, 0};
-    B2S_CUDA(cudaMemcpyAsync(totals, stat, sizeof(totals), cudaMemcpyDeviceToHost, st));
+    const unsigned gu = (unsigned)((ntiles + 255) / 256);
+    const int ept = vt == B2S_F32 ? 4 : 2;
+    if (pt == B2S_I32) spmv_plan_uniform_kernel<int32_t><<<gu, 256, 0, st>>>((const int32_t*)indptr, ntiles, dev, ept, stat + 1);
+    else               spmv_plan_uniform_kernel<int64_t><<<gu, 256, 0, st>>>((const int64_t*)indptr, ntiles, dev, ept, stat + 1);
+    B2S_LAUNCH_CHECK();
+    unsigned long long ut = 0;
+    B2S_CUDA(cudaMemcpyAsync(&ut, stat + 1, sizeof(ut), cudaMemcpyDeviceToHost, st));
     B2S_CUDA(cudaStreamSynchronize(st));
-    if (ns > 0) lines = (double)totals[0] / (double)ns;
-    uniform_tiles = (int64_t)totals[1];
+    uniform_tiles = (int64_t)ut;
   }
   PlanHandle* h = new PlanHandle();
   h->magic = kPlanMagic;
   h->vt = vt; h->it = it; h->pt = pt; h->cfg = cfg;
-  h->use_rowgroup = lines > 16.0 ? 1 : 0;
+  h->use_rowgroup = 0;  // scattered matrices now get a deep-MLP tile shape instead (see kScatterCfg*)
+  h->scattered = scattered ? 1 : 0;
   // kernel flavour: the variant with the register fast path and the conflict-avoiding skewed reduce is used
   // when >= 25% of the tiles are ELL-like, or rows are long (>= 12) or of even mean length; short odd rows
   // (e.g. 5-point stencils) keep the lean sequential-reduce variant
@@ -987,7 +1013,7 @@ int b2s_spmv_plan_destroy(void* plan) {
 int b2s_spmv_plan_info(const void* plan, int64_t* out4_host) {
   const PlanHandle* h = (const PlanHandle*)plan;
   B2S_CHECK_ARG(h && h->magic == kPlanMagic && out4_host, "bad plan handle / out pointer");
-  out4_host[0] = h->cfg; out4_host[1] = h->use_rowgroup + 2 * h->use_uniform; out4_host[2] = h->ntiles;
+  out4_host[0] = h->cfg; out4_host[1] = h->use_rowgroup + 2 * h->use_uniform + 4 * h->scattered; out4_host[2] = h->ntiles;
   out4_host[3] = (int64_t)(h->lines_per_warp * 1000.0);
   return B2S_OK;
 }

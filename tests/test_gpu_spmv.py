@@ -181,7 +181,7 @@ def test_unaligned_base_pointers(oracle):
     assert np.allclose(y.cpu().numpy(), oracle.spmv(indptr, indices, data, x), rtol=1e-12, atol=1e-12)
 
 
-@pytest.mark.parametrize("cfg", range(10))
+@pytest.mark.parametrize("cfg", range(14))
 @pytest.mark.parametrize("dtype", TYPES)
 def test_all_tile_configs(oracle, cfg, dtype):
     rng = np.random.default_rng(100 + cfg)
@@ -189,7 +189,7 @@ def test_all_tile_configs(oracle, cfg, dtype):
     lens = np.where(np.arange(nrows) % 501 == 0, 9000, rng.integers(0, 12, nrows))
     indptr, indices, data = _random_csr(rng, nrows, ncols, lens, dtype)
     x = rng.standard_normal(ncols).astype(dtype)
-    assert _lib.lib.b2s_spmv_num_configs() == 10
+    assert _lib.lib.b2s_spmv_num_configs() == 14
     try:
         _lib.check(_lib.lib.b2s_spmv_set_config(cfg, cfg % 3))
         A = sparse.csr_array((data, indices, indptr), shape=(nrows, ncols))
@@ -263,15 +263,15 @@ def test_plan_kernel_choice_by_column_locality():
     B = gallery.banded(100000, 11, np.float64)
     R = gallery.random_fixed(100000, 100000, 32, np.float32)
     pl, pb, pr = L5._get_plan(), B._get_plan(), R._get_plan()
-    assert not pl.rowgroup and pl.lines_per_warp < 12
-    assert not pb.rowgroup and pb.lines_per_warp < 6
+    assert not pl.scattered and pl.lines_per_warp < 12
+    assert not pb.scattered and pb.lines_per_warp < 6
     assert not pl.uniform and not pb.uniform      # short odd rows keep the lean variant
     assert gallery.banded(100000, 32, np.float32)._get_plan().uniform
-    assert pr.rowgroup and pr.lines_per_warp > 28
+    assert pr.scattered and pr.lines_per_warp > 28 and pr.config == 5   # deep-MLP tile shape for scattered fp32
     # both kernel families give the same answer on the same plan
     x = torch.rand(100000, dtype=torch.float32, device="cuda")
     y1 = R @ x
-    pr.set_kernel(False)
+    pr.set_kernel(True)   # plan-free row-group kernel on the same matrix
     y2 = R @ x
     assert torch.allclose(y1, y2, rtol=1e-4, atol=1e-4)
 

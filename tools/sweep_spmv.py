@@ -89,6 +89,8 @@ if __name__ == "__main__":
     os.makedirs("gpurun_out", exist_ok=True)
     which = sys.argv[1:] or ["l5", "banded", "r32", "r32w", "r32f64"]
     cfgs = list(range(int(_lib.lib.b2s_spmv_num_configs())))
+    if os.environ.get("SWEEP_CFGS"):
+        cfgs = [int(c) for c in os.environ["SWEEP_CFGS"].split(",")]
     waves = [0, 2, 4]
     with open("gpurun_out/sweep_spmv.txt", "a") as out:
         out.write(f"# {time.ctime()} {torch.cuda.get_device_name(0)} {sparse.runtime.device_info()}\n")
