@@ -91,6 +91,26 @@ int         b2s_spmv_csr(int vt, int it, int pt, int64_t nrows, int64_t ncols, i
                          const void* indptr, const void* indices, const void* vals,
                          const void* x, void* y, const void* plan, void* stream);
 
+/* Row chunks for pipelined host<->device products.  A plan is cut into up to 16 chunks of tiles;
+ * chunk c owns rows [row_lo,row_hi) and reads x only inside its column window [col_lo,col_hi)
+ * (the reference's MinMaxImagePartition, sparse/partition.py:139-208, applied to row chunks of
+ * one GPU).  b2s_spmv_plan_chunks: out = nchunks x {tile_lo,tile_hi,row_lo,row_hi,col_lo,col_hi}.
+ * b2s_spmv_csr_tiles runs the tiles of one chunk, so x can still be arriving (H2D) for later
+ * chunks while y of earlier chunks is already leaving (D2H). */
+int         b2s_spmv_plan_chunks(const void* plan, int64_t* out_host, int max_chunks, int* nchunks_host);
+int         b2s_spmv_csr_tiles(int vt, int it, int pt, int64_t nrows, int64_t ncols, int64_t nnz,
+                               const void* indptr, const void* indices, const void* vals,
+                               const void* x, void* y, const void* plan,
+                               int64_t tile_lo, int64_t tile_hi, void* stream);
+
+/* y_host = A x_host for HOST vectors (the matrix stays resident): pipelined H2D / tiles / D2H over the plan's
+ * chunks on internal copy streams; x_dev / y_dev are caller-owned device scratch (ncols / nrows elements).
+ * Pinned host memory gives true overlap.  syncs: y_host is complete on return. */
+int         b2s_spmv_csr_host(int vt, int it, int pt, int64_t nrows, int64_t ncols, int64_t nnz,
+                              const void* indptr, const void* indices, const void* vals,
+                              const void* x_host, void* y_host, void* x_dev, void* y_dev,
+                              const void* plan, void* stream);
+
 /* y = A x and *dot_out = sum_i w[i] * y[i] in one pass (CG: q = A p, pq = p.q;
  * sparse/linalg.py:549-550 fused).  w has nrows entries (for a row shard it is the
  * shard's slice of p).  dot_out: one value of type vt on the device. */

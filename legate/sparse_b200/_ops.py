@@ -40,6 +40,17 @@ class SpmvPlan:
         self.config, self.rowgroup, self.uniform, self.scattered = int(out[0]), bool(out[1] & 1), bool(out[1] & 2), bool(out[1] & 4)
         self.tiles, self.lines_per_warp = int(out[2]), out[3] / 1000.0
 
+    @property
+    def chunks(self):
+        """Row chunks for pipelined host<->device products: list of (tile_lo, tile_hi, row_lo, row_hi, col_lo, col_hi);
+        empty when the plan is too small or not a TMA tile plan."""
+        if getattr(self, "_chunks", None) is None:
+            out = (_lib.c_i64 * (6 * 16))()
+            n = ctypes.c_int(0)
+            _lib.check(L.b2s_spmv_plan_chunks(self.handle, out, 16, ctypes.byref(n)), "b2s_spmv_plan_chunks")
+            self._chunks = [tuple(int(out[6 * c + k]) for k in range(6)) for c in range(n.value)]
+        return self._chunks
+
     def set_kernel(self, rowgroup: bool):
         _lib.check(L.b2s_spmv_plan_set_kernel(self.handle, int(bool(rowgroup))), "b2s_spmv_plan_set_kernel")
         self.rowgroup = bool(rowgroup)
@@ -82,6 +93,25 @@ def spmv(indptr, indices, data, x, y, shape, plan=None):
                               nnz, ptr(indptr), ptr(indices), ptr(data), ptr(x), ptr(y), _plan_handle(plan), _stream()),
                "b2s_spmv_csr")
     return y
+
+
+def spmv_tiles(indptr, indices, data, x, y, shape, plan, tile_lo: int, tile_hi: int):
+    """Rows of tiles [tile_lo, tile_hi) of y = A @ x (x must be valid on that chunk's column window)."""
+    _chk_dev(indptr, indices, data, x, y)
+    nrows, ncols = shape
+    _lib.check(L.b2s_spmv_csr_tiles(vt_code(data.dtype), idx_code(indices.dtype), idx_code(indptr.dtype), nrows, ncols,
+                                    data.shape[0], ptr(indptr), ptr(indices), ptr(data), ptr(x), ptr(y),
+                                    _plan_handle(plan), tile_lo, tile_hi, _stream()), "b2s_spmv_csr_tiles")
+    return y
+
+
+def spmv_host(indptr, indices, data, x_host_ptr: int, y_host_ptr: int, x_dev, y_dev, shape, plan):
+    """y_host = A @ x_host through the pipelined C entry point (returns when y_host is complete)."""
+    _chk_dev(indptr, indices, data, x_dev, y_dev)
+    nrows, ncols = shape
+    _lib.check(L.b2s_spmv_csr_host(vt_code(data.dtype), idx_code(indices.dtype), idx_code(indptr.dtype), nrows, ncols,
+                                   data.shape[0], ptr(indptr), ptr(indices), ptr(data), x_host_ptr, y_host_ptr,
+                                   ptr(x_dev), ptr(y_dev), _plan_handle(plan), _stream()), "b2s_spmv_csr_host")
 
 
 def spmv_dot(indptr, indices, data, x, y, w, out, shape, plan):

@@ -285,6 +285,27 @@ class csr_array:
             cache[common] = (self._data.data_ptr(), self.astype(common, copy=False))
         return cache[common][1]
 
+    def _dot_host_pipelined(self, x: np.ndarray, out, plan):
+        """y = A @ x for HOST vectors, software-pipelined over the plan's row chunks.
+
+        Chunk c only reads x inside its column window (plan.chunks; the reference's MinMaxImagePartition idea
+        applied to row chunks of one GPU), so its tiles can run as soon as x[:col_hi_c] has arrived, while the
+        rest of x is still crossing PCIe and while y of earlier chunks is already on its way back.  For a
+        banded matrix the product then costs about max(H2D, D2H) instead of H2D + kernel + D2H.  Pinned host
+        arrays give true overlap; pageable ones still work (the copies just serialise)."""
+        dev = self.device
+        tdt = torch_dtype(self.dtype)
+        st = self.__dict__.setdefault("_pipe", {})
+        if st.get("key") != (self.shape, self.dtype):
+            st.clear()
+            st.update(key=(self.shape, self.dtype), xd=torch.empty(self.shape[1], dtype=tdt, device=dev),
+                      yd=torch.empty(self.shape[0], dtype=tdt, device=dev))
+        if out is None:
+            out = np.empty(self.shape[0], dtype=self.dtype)
+        _ops.spmv_host(self._indptr, self._indices, self._data, x.ctypes.data, out.ctypes.data, st["xd"], st["yd"],
+                       self.shape, plan)
+        return out
+
     def dot(self, other, out=None, spmv_domain_part=False):
         """`A.dot(x)` / `A @ B`; see reference sparse/csr.py:442-582.
 
@@ -326,7 +347,6 @@ class csr_array:
                     f"SpMV for resolved dtype {common} is not implemented (float32/float64 kernels only)"
                 )
             A = self._promoted(common)
-            xd = to_device(x, dtype=common)
             if out is not None:
                 odt = numpy_dtype(out.dtype)
                 if odt != common:
@@ -336,9 +356,20 @@ class csr_array:
                     assert not spmv_domain_part
                 else:
                     assert tuple(out.shape) == (self.shape[0],)
+            plan = A._get_plan()
+            if (not on_device and isinstance(x, np.ndarray) and xdt == common and x.flags.c_contiguous
+                    and (out is None or (isinstance(out, np.ndarray) and out.flags.c_contiguous))
+                    and plan.chunks and os.environ.get("B2S_PIPELINE", "1") != "0"):
+                # host vectors: stream x in / y out chunk by chunk, overlapping both PCIe directions with the kernel
+                res = A._dot_host_pipelined(x, None if out is None else out.reshape(-1), plan)
+                result = out if out is not None else (res.reshape(-1, 1) if other_originally_2d else res)
+                if other_originally_sparse:
+                    return csr_array(np.asarray(result).reshape(self.shape[0], -1))
+                return result
+            xd = to_device(x, dtype=common)
             direct = isinstance(out, torch.Tensor) and out.is_cuda and out.is_contiguous()
             y = out.reshape(-1) if direct else torch.empty(self.shape[0], dtype=torch_dtype(common), device=A.device)
-            _ops.spmv(A._indptr, A._indices, A._data, xd, y, A.shape, plan=A._get_plan())
+            _ops.spmv(A._indptr, A._indices, A._data, xd, y, A.shape, plan=plan)
             if out is None:
                 result = y if on_device else to_host(y)
                 if other_originally_2d:

@@ -23,6 +23,7 @@
 // HBM-bound by construction: algorithmic bytes per launch are
 //   nnz*(sizeof V + sizeof I) + (nrows+1)*sizeof P + ncols*sizeof V + nrows*sizeof V.
 #include "common.cuh"
+#include <limits.h>
 
 namespace b2s {
 
@@ -417,7 +418,7 @@ struct TmaLayout {
 
 template <typename V, typename I, typename P, int NC, int G, int STAGES, int MINB, bool UNI, bool DOT>
 __global__ void __launch_bounds__((NC + 1) * 32, MINB)
-spmv_tma_kernel(int64_t ntiles, int64_t nrows, int64_t nnz, const P* __restrict__ indptr,
+spmv_tma_kernel(int64_t tile_lo, int64_t tile_hi, int64_t nrows, int64_t nnz, const P* __restrict__ indptr,
                 const I* __restrict__ indices, const V* __restrict__ vals, const V* __restrict__ x,
                 V* __restrict__ y, const PlanEntry* __restrict__ plan, const V* __restrict__ w, V* dot_out, void* ws) {
   using LY = TmaLayout<V, I, P, NC, G, STAGES>;
@@ -453,7 +454,7 @@ spmv_tma_kernel(int64_t ntiles, int64_t nrows, int64_t nnz, const P* __restrict_
     const int64_t np1 = nrows + 1;
     const int64_t rp4 = np1 & ~(int64_t)3;
     int it = 0;
-    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    for (int64_t t = tile_lo + blockIdx.x; t < tile_hi; t += gridDim.x) {
       const PlanEntry e0 = ld_plan(plan + t), e1 = ld_plan(plan + t + 1);
       const int nr = e1.row - e0.row;
       if (nr <= 0) continue;  // warp-uniform
@@ -701,6 +702,7 @@ spmv_rowgroup_kernel(int64_t nrows, const P* __restrict__ indptr, const I* __res
 // ---------------------------------------------------------------------------------------------
 struct SpmvArgs {
   int64_t ntiles, nrows, nnz;
+  int64_t tile_lo, tile_hi;  // tile sub-range to run (TMA kernels); [0, ntiles) for a whole SpMV
   const void *indptr, *indices, *vals, *x;
   void* y;
   const PlanEntry* plan;
@@ -762,10 +764,10 @@ static int launch_tma_u(const SpmvArgs& a) {
   int per_sm = occ;
   if (g_waves > 0 && g_waves < occ) per_sm = g_waves;
   int64_t grid = (int64_t)pr.sm_count * per_sm;
-  if (grid > a.ntiles) grid = a.ntiles;
+  if (grid > a.tile_hi - a.tile_lo) grid = a.tile_hi - a.tile_lo;
   if (DOT && grid > WS_MAX_PARTIALS) grid = WS_MAX_PARTIALS;
   if (grid < 1) grid = 1;
-  kern<<<(unsigned)grid, THREADS, smem, a.st>>>(a.ntiles, a.nrows, a.nnz, (const P*)a.indptr, (const I*)a.indices,
+  kern<<<(unsigned)grid, THREADS, smem, a.st>>>(a.tile_lo, a.tile_hi, a.nrows, a.nnz, (const P*)a.indptr, (const I*)a.indices,
                                                 (const V*)a.vals, (const V*)a.x, (V*)a.y, a.plan, (const V*)a.w,
                                                 (V*)a.dot_out, a.ws);
   B2S_LAUNCH_CHECK();
@@ -886,6 +888,35 @@ spmv_locality_kernel(int64_t nnz, const I* __restrict__ indices, int elem_shift,
   if (lane == 0) atomicAdd(out, (unsigned long long)__popc(leaders));
 }
 
+// [min col, max col] of the nonzeros [k_lo, k_hi) -- the x window a chunk of rows reads (reference:
+// MinMaxImagePartition, sparse/partition.py:139-208 / bounds_from_partitioned_coordinates.cu:35-62).
+template <typename I>
+__global__ void __launch_bounds__(256)
+spmv_col_window_kernel(const I* __restrict__ indices, const long long* __restrict__ kbounds, int nchunks,
+                       int blocks_per_chunk, long long* __restrict__ out_minmax) {
+  const int c = blockIdx.x / blocks_per_chunk, b = blockIdx.x % blocks_per_chunk;
+  if (c >= nchunks) return;
+  const long long lo = kbounds[c], hi = kbounds[c + 1];
+  long long mn = LLONG_MAX, mx = -1;
+  for (long long k = lo + (long long)b * 256 + threadIdx.x; k < hi; k += 256LL * blocks_per_chunk) {
+    const long long v = (long long)indices[k];
+    mn = v < mn ? v : mn;
+    mx = v > mx ? v : mx;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const long long a = __shfl_xor_sync(0xffffffffu, mn, o), bb = __shfl_xor_sync(0xffffffffu, mx, o);
+    mn = a < mn ? a : mn;
+    mx = bb > mx ? bb : mx;
+  }
+  if ((threadIdx.x & 31) == 0 && mx >= 0) {
+    atomicMin(reinterpret_cast<long long*>(&out_minmax[2 * c]), mn);
+    atomicMax(reinterpret_cast<long long*>(&out_minmax[2 * c + 1]), mx);
+  }
+}
+
+constexpr int kPlanChunks = 16;
+
 struct PlanHandle {
   uint32_t magic;
   int vt, it, pt;
@@ -896,6 +927,10 @@ struct PlanHandle {
   int64_t nrows, ncols, nnz, ntiles;
   double lines_per_warp;
   const PlanEntry* dev;
+  // row chunks for pipelined host<->device SpMV: chunk c = tiles [ctile[c], ctile[c+1]), rows [crow[c], crow[c+1]),
+  // reading x only inside [ccol_lo[c], ccol_hi[c])
+  int nchunks;
+  int64_t ctile[kPlanChunks + 1], crow[kPlanChunks + 1], ccol_lo[kPlanChunks], ccol_hi[kPlanChunks];
 };
 static constexpr uint32_t kPlanMagic = 0xB2005A17u;
 
@@ -995,7 +1030,53 @@ int b2s_spmv_plan_create(int vt, int it, int pt, int64_t nrows, int64_t ncols, i
   h->nrows = nrows; h->ncols = ncols; h->nnz = nnz; h->ntiles = ntiles;
   h->lines_per_warp = lines;
   h->dev = dev;
+  h->nchunks = 0;
+  if (ntiles >= 4 * kPlanChunks && nnz > 0) {
+    // chunk boundaries (tiles), their rows / nnz ranges (read back from the device plan) and column windows
+    const int K = kPlanChunks;
+    PlanEntry ends[kPlanChunks + 1];
+    for (int c = 0; c <= K; c++) {
+      h->ctile[c] = ntiles * c / K;
+      B2S_CUDA(cudaMemcpyAsync(&ends[c], dev + h->ctile[c], sizeof(PlanEntry), cudaMemcpyDeviceToHost, st));
+    }
+    B2S_CUDA(cudaStreamSynchronize(st));
+    long long kb_host[kPlanChunks + 1], mm_host[2 * kPlanChunks];
+    for (int c = 0; c <= K; c++) { h->crow[c] = ends[c].row; kb_host[c] = ends[c].k; }
+    for (int c = 0; c < K; c++) { mm_host[2 * c] = LLONG_MAX; mm_host[2 * c + 1] = -1; }
+    // scratch: the tail of the plan buffer is free to borrow here?  No -- use a small temporary allocation.
+    long long* dtmp = nullptr;
+    B2S_CUDA(cudaMallocAsync((void**)&dtmp, sizeof(long long) * (3 * K + 1), st));
+    B2S_CUDA(cudaMemcpyAsync(dtmp, kb_host, sizeof(long long) * (K + 1), cudaMemcpyHostToDevice, st));
+    B2S_CUDA(cudaMemcpyAsync(dtmp + K + 1, mm_host, sizeof(long long) * 2 * K, cudaMemcpyHostToDevice, st));
+    const int bpc = 64;
+    if (it == B2S_I32) spmv_col_window_kernel<int32_t><<<K * bpc, 256, 0, st>>>((const int32_t*)indices, dtmp, K, bpc, dtmp + K + 1);
+    else               spmv_col_window_kernel<int64_t><<<K * bpc, 256, 0, st>>>((const int64_t*)indices, dtmp, K, bpc, dtmp + K + 1);
+    B2S_LAUNCH_CHECK();
+    B2S_CUDA(cudaMemcpyAsync(mm_host, dtmp + K + 1, sizeof(long long) * 2 * K, cudaMemcpyDeviceToHost, st));
+    B2S_CUDA(cudaStreamSynchronize(st));
+    B2S_CUDA(cudaFreeAsync(dtmp, st));
+    for (int c = 0; c < K; c++) {
+      if (mm_host[2 * c + 1] < 0) { h->ccol_lo[c] = 0; h->ccol_hi[c] = 0; }
+      else { h->ccol_lo[c] = mm_host[2 * c]; h->ccol_hi[c] = mm_host[2 * c + 1] + 1; }
+    }
+    h->nchunks = K;
+  }
   *plan_out = h;
+  return B2S_OK;
+}
+
+/* Row chunks of a plan for pipelined host<->device products: out = nchunks x {tile_lo, tile_hi, row_lo, row_hi,
+ * col_lo, col_hi}; returns the number of chunks through *nchunks_host (0: plan too small / not chunked). */
+int b2s_spmv_plan_chunks(const void* plan, int64_t* out_host, int max_chunks, int* nchunks_host) {
+  const PlanHandle* h = (const PlanHandle*)plan;
+  B2S_CHECK_ARG(h && h->magic == kPlanMagic && out_host && nchunks_host, "bad plan handle / out pointer");
+  const int n = h->nchunks < max_chunks ? h->nchunks : max_chunks;
+  for (int c = 0; c < n; c++) {
+    out_host[6 * c + 0] = h->ctile[c]; out_host[6 * c + 1] = h->ctile[c + 1];
+    out_host[6 * c + 2] = h->crow[c];  out_host[6 * c + 3] = h->crow[c + 1];
+    out_host[6 * c + 4] = h->ccol_lo[c]; out_host[6 * c + 5] = h->ccol_hi[c];
+  }
+  *nchunks_host = (kCfgs[h->cfg].kind == 1 && !h->use_rowgroup) ? n : 0;
   return B2S_OK;
 }
 
@@ -1028,7 +1109,7 @@ int b2s_spmv_plan_set_kernel(void* plan, int use_rowgroup) {
 
 static int spmv_impl(int vt, int it, int pt, int64_t nrows, int64_t ncols, int64_t nnz, const void* indptr,
                      const void* indices, const void* vals, const void* x, void* y, const void* w, void* dot_out,
-                     const void* plan, void* ws, void* stream, bool dot) {
+                     const void* plan, void* ws, void* stream, bool dot, int64_t tile_lo = 0, int64_t tile_hi = -1) {
   if (int rc = check_common(vt, it, pt, nrows, ncols, nnz, indptr, indices, vals, x, y)) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   if (dot) {
@@ -1056,6 +1137,12 @@ static int spmv_impl(int vt, int it, int pt, int64_t nrows, int64_t ncols, int64
   }
   SpmvArgs a;
   a.ntiles = h->ntiles;
+  a.tile_lo = tile_lo;
+  a.tile_hi = tile_hi < 0 ? h->ntiles : tile_hi;
+  B2S_CHECK_ARG(a.tile_lo >= 0 && a.tile_lo <= a.tile_hi && a.tile_hi <= h->ntiles, "tile range out of bounds");
+  B2S_CHECK_ARG((a.tile_lo == 0 && a.tile_hi == h->ntiles) || kCfgs[h->cfg].kind == 1,
+                "tile sub-ranges need a TMA tile plan");
+  if (a.tile_lo == a.tile_hi) return B2S_OK;
   a.nrows = nrows; a.nnz = nnz;
   a.indptr = indptr; a.indices = indices; a.vals = vals; a.x = x; a.y = y;
   a.plan = h->dev;
@@ -1075,6 +1162,81 @@ int b2s_spmv_csr(int vt, int it, int pt, int64_t nrows, int64_t ncols, int64_t n
                  const void* indices, const void* vals, const void* x, void* y, const void* plan, void* stream) {
   return spmv_impl(vt, it, pt, nrows, ncols, nnz, indptr, indices, vals, x, y, nullptr, nullptr, plan, nullptr,
                    stream, false);
+}
+
+/* y[rows of tiles [tile_lo, tile_hi)] = (A x) restricted to those rows; needs x valid on the chunk's column window */
+int b2s_spmv_csr_tiles(int vt, int it, int pt, int64_t nrows, int64_t ncols, int64_t nnz, const void* indptr,
+                       const void* indices, const void* vals, const void* x, void* y, const void* plan,
+                       int64_t tile_lo, int64_t tile_hi, void* stream) {
+  B2S_CHECK_ARG(plan != nullptr, "b2s_spmv_csr_tiles needs a plan");
+  return spmv_impl(vt, it, pt, nrows, ncols, nnz, indptr, indices, vals, x, y, nullptr, nullptr, plan, nullptr,
+                   stream, false, tile_lo, tile_hi);
+}
+
+/* y_host = A x_host with HOST vectors (matrix resident on the device): x is streamed in and y streamed out chunk
+ * by chunk on two internal copy streams while the tiles of each chunk run on `stream`, so both PCIe directions
+ * and the kernel overlap (see b2s_spmv_plan_chunks).  x_dev / y_dev are caller-owned device scratch vectors of
+ * ncols / nrows elements.  Pinned host memory gives true overlap.  Returns after y_host is complete (syncs). */
+int b2s_spmv_csr_host(int vt, int it, int pt, int64_t nrows, int64_t ncols, int64_t nnz, const void* indptr,
+                      const void* indices, const void* vals, const void* x_host, void* y_host, void* x_dev,
+                      void* y_dev, const void* plan, void* stream) {
+  B2S_CHECK_ARG(vt == B2S_F32 || vt == B2S_F64, "bad value type code %d", vt);
+  B2S_CHECK_ARG((ncols == 0 || (x_host && x_dev)) && (nrows == 0 || (y_host && y_dev)), "NULL vector pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t sv = vt == B2S_F32 ? 4 : 8;
+  const PlanHandle* h = (const PlanHandle*)plan;
+  const bool chunked = h && h->magic == kPlanMagic && h->nchunks > 0 && kCfgs[h->cfg].kind == 1 && !h->use_rowgroup;
+  if (!chunked) {
+    B2S_CUDA(cudaMemcpyAsync(x_dev, x_host, sv * (size_t)ncols, cudaMemcpyHostToDevice, st));
+    if (int rc = b2s_spmv_csr(vt, it, pt, nrows, ncols, nnz, indptr, indices, vals, x_dev, y_dev, plan, stream)) return rc;
+    B2S_CUDA(cudaMemcpyAsync(y_host, y_dev, sv * (size_t)nrows, cudaMemcpyDeviceToHost, st));
+    B2S_CUDA(cudaStreamSynchronize(st));
+    return B2S_OK;
+  }
+  // per-device copy streams and events, created once
+  struct Pipe { cudaStream_t s_in = nullptr, s_out = nullptr; cudaEvent_t ev_in[kPlanChunks], ev_k[kPlanChunks], ev0; bool ok = false; };
+  static Pipe pipes[64];
+  int dev = 0;
+  B2S_CUDA(cudaGetDevice(&dev));
+  B2S_CHECK_ARG(dev >= 0 && dev < 64, "device ordinal out of range");
+  Pipe& P = pipes[dev];
+  if (!P.ok) {
+    B2S_CUDA(cudaStreamCreateWithFlags(&P.s_in, cudaStreamNonBlocking));
+    B2S_CUDA(cudaStreamCreateWithFlags(&P.s_out, cudaStreamNonBlocking));
+    for (int c = 0; c < kPlanChunks; c++) {
+      B2S_CUDA(cudaEventCreateWithFlags(&P.ev_in[c], cudaEventDisableTiming));
+      B2S_CUDA(cudaEventCreateWithFlags(&P.ev_k[c], cudaEventDisableTiming));
+    }
+    B2S_CUDA(cudaEventCreateWithFlags(&P.ev0, cudaEventDisableTiming));
+    P.ok = true;
+  }
+  // the copy streams start after everything already queued on the compute stream
+  B2S_CUDA(cudaEventRecord(P.ev0, st));
+  B2S_CUDA(cudaStreamWaitEvent(P.s_in, P.ev0, 0));
+  B2S_CUDA(cudaStreamWaitEvent(P.s_out, P.ev0, 0));
+  int64_t copied = 0;
+  for (int c = 0; c < h->nchunks; c++) {
+    const int64_t need = h->ccol_hi[c];
+    if (need > copied) {
+      B2S_CUDA(cudaMemcpyAsync((char*)x_dev + sv * copied, (const char*)x_host + sv * copied, sv * (size_t)(need - copied),
+                               cudaMemcpyHostToDevice, P.s_in));
+      copied = need;
+      B2S_CUDA(cudaEventRecord(P.ev_in[c], P.s_in));
+      B2S_CUDA(cudaStreamWaitEvent(st, P.ev_in[c], 0));
+    }
+    if (int rc = b2s_spmv_csr_tiles(vt, it, pt, nrows, ncols, nnz, indptr, indices, vals, x_dev, y_dev, plan,
+                                    h->ctile[c], h->ctile[c + 1], stream)) return rc;
+    const int64_t r0 = h->crow[c], r1 = h->crow[c + 1];
+    if (r1 > r0) {
+      B2S_CUDA(cudaEventRecord(P.ev_k[c], st));
+      B2S_CUDA(cudaStreamWaitEvent(P.s_out, P.ev_k[c], 0));
+      B2S_CUDA(cudaMemcpyAsync((char*)y_host + sv * r0, (const char*)y_dev + sv * r0, sv * (size_t)(r1 - r0),
+                               cudaMemcpyDeviceToHost, P.s_out));
+    }
+  }
+  B2S_CUDA(cudaStreamSynchronize(P.s_out));
+  B2S_CUDA(cudaStreamSynchronize(st));
+  return B2S_OK;
 }
 
 int b2s_spmv_csr_dot(int vt, int it, int pt, int64_t nrows, int64_t ncols, int64_t nnz, const void* indptr,
