@@ -339,13 +339,80 @@ class dist_csr_array:
                 req.wait()
 
     # -- SpMV ---------------------------------------------------------------------------------------------
+    def _overlap_schedule(self):
+        """Split the local SpMV plan into runs of tiles that only read locally owned x (can run while the halo
+        is still in flight) and runs that touch remote columns (must wait for the exchange).  Uses the plan's
+        row chunks and their column windows; None when the plan is not chunked."""
+        if getattr(self, "_sched", None) is None:
+            plan = self.local._get_plan()
+            lo, hi = self.my_cols
+            interior, boundary = [], []
+            for tile_lo, tile_hi, _, _, col_lo, col_hi in plan.chunks:
+                if tile_hi <= tile_lo:
+                    continue
+                inside = col_hi <= col_lo or (col_lo >= lo and col_hi <= hi)
+                runs = interior if inside else boundary
+                if runs and runs[-1][1] == tile_lo:
+                    runs[-1][1] = tile_hi
+                else:
+                    runs.append([tile_lo, tile_hi])
+            self._sched = (interior, boundary) if plan.chunks and interior else ()
+        return self._sched or None
+
     def dot(self, x_full: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
-        """y_local = A_local @ x.  `x_full` is a full-length buffer whose my_cols slice is current."""
-        self.exchange(x_full)
+        """y_local = A_local @ x.  `x_full` is a full-length buffer whose my_cols slice is current.
+
+        With a chunked plan and a point-to-point halo the exchange runs on a side stream while the tiles that
+        read only local columns are already being multiplied; the few boundary tiles follow once the halo has
+        landed (B2S_OVERLAP=0 serialises exchange and SpMV)."""
         A = self.local
         if out is None:
             out = torch.empty(A.shape[0], dtype=x_full.dtype, device=x_full.device)
-        _ops.spmv(A.indptr, A.indices, A.data, x_full[: A.shape[1]], out, A.shape, plan=A._get_plan())
+        xin = x_full[: A.shape[1]]
+        plan = A._get_plan()
+        sched = None
+        if (self.exchange_mode == "p2p" and x_full.is_cuda and A.dtype == numpy_dtype(x_full.dtype)
+                and os.environ.get("B2S_OVERLAP", "1") != "0"):
+            sched = self._overlap_schedule()
+        if sched is None:
+            self.exchange(x_full)
+            _ops.spmv(A.indptr, A.indices, A.data, xin, out, A.shape, plan=plan)
+            return out
+        interior, boundary = sched
+        cur = torch.cuda.current_stream()
+        if getattr(self, "_comm_stream", None) is None:
+            self._comm_stream = torch.cuda.Stream()
+        cs = self._comm_stream
+        cs.wait_stream(cur)
+        with torch.cuda.stream(cs):
+            self.exchange(x_full)
+            done = cs.record_event()
+        for tile_lo, tile_hi in interior:
+            _ops.spmv_tiles(A.indptr, A.indices, A.data, xin, out, A.shape, plan, tile_lo, tile_hi)
+        cur.wait_event(done)
+        for tile_lo, tile_hi in boundary:
+            _ops.spmv_tiles(A.indptr, A.indices, A.data, xin, out, A.shape, plan, tile_lo, tile_hi)
+        return out
+
+    def dot_graphed(self, x_full: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+        """`dot` replayed from a CUDA graph (captured on first use for this (x_full, out) pair): the exchange
+        (NCCL send/recv or peer kernels), the stream fork/join of the overlap schedule and the tile launches
+        cost one graph launch on the host instead of ~150 us of Python/NCCL call overhead per product, which
+        is what bounds a 140 us SpMV step otherwise."""
+        from .linalg import _try_capture
+
+        key = (x_full.data_ptr(), out.data_ptr(), os.environ.get("B2S_OVERLAP", "1"))
+        cache = self.__dict__.setdefault("_dot_graphs", {})
+        g = cache.get(key)
+        if g is None:
+            self.dot(x_full, out=out)  # eager warm-up: plans, schedules, communicators, kernel attributes
+            torch.cuda.synchronize()
+            g = _try_capture(lambda: self.dot(x_full, out=out)) or False
+            cache[key] = g
+        if g:
+            g.replay()
+        else:
+            self.dot(x_full, out=out)
         return out
 
     def dot_fused(self, x_full, out, w, dot_out):

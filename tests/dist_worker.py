@@ -48,7 +48,7 @@ def main():
         os.environ["B2S_PEER"] = peer
         os.environ["B2S_PEER_HALO"] = halo
         # 2. shards assembled directly (gallery row_lo/row_hi) equal the slices of the global operator
-        n1, n2 = 300, 200 * world
+        n1, n2 = 300, 400 * world   # >= 64 tiles per shard so the plan is chunked
         N = n1 * n2
         plan = bd.RowBlockPlan(N, world)
         lo, hi = plan.rows(rank)
@@ -62,6 +62,15 @@ def main():
         for rep in range(3):  # repeated exchanges exercise the epoch / ack protocol
             xg = rng.standard_normal(N)
             assert np.allclose(Ad.matvec_global(xg), G @ xg, rtol=1e-12, atol=1e-6), (peer, rep)
+        # overlapped (halo exchange || interior tiles) and serialised schedules give identical results
+        sched = Ad._overlap_schedule()
+        assert sched and len(sched[0]) >= 1 and len(sched[1]) >= 1, sched
+        xf = Ad.scatter_vector(xg)
+        y1 = Ad.dot(xf).clone()
+        os.environ["B2S_OVERLAP"] = "0"
+        y2 = Ad.dot(xf)
+        os.environ["B2S_OVERLAP"] = "1"
+        assert torch.equal(y1, y2)
 
         # 3. sharded CG == oracle CG on the global problem (same iteration count, same solution)
         b = np.ones(N)

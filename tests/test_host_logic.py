@@ -32,6 +32,28 @@ def test_abi_exports_every_declared_symbol():
         assert n in _lib.SIGNATURES, f"{n} has no ctypes signature in _lib.py"
 
 
+def test_abi_signature_arity_matches_header():
+    """Every prototype in include/b200sparse.h has as many parameters as its ctypes signature in _lib.py."""
+    text = open(os.path.join(ROOT, "include", "b200sparse.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    protos = re.findall(r"\b(b2s_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", text, flags=re.S)
+    assert len(protos) >= 30
+    for name, params in protos:
+        params = params.strip()
+        n = 0 if params in ("", "void") else params.count(",") + 1
+        assert len(_lib.SIGNATURES[name][1]) == n, f"{name}: header has {n} parameters, ctypes {len(_lib.SIGNATURES[name][1])}"
+
+
+def test_reference_package_alias():
+    """`import sparse` (the reference's package name) resolves to this implementation."""
+    import sparse as ref_name
+    import sparse.io
+    import sparse.linalg
+
+    assert ref_name.csr_array is sparse.csr_array and ref_name.linalg.cg is sparse.linalg.cg
+    assert ref_name.io.mmread is sparse.io.mmread
+
+
 def test_abi_version_and_sizes():
     assert _lib.lib.b2s_version() == 1
     assert _lib.lib.b2s_ws_bytes() >= 16 + 8 * 1024
