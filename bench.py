@@ -371,7 +371,7 @@ def run_gpu(args):
         "config": {"workload": WORKLOAD, "global_rows": Nglob, "global_nnz": nnz_glob, "rows_per_gpu": hi - lo,
                    "index_bytes": 4, "indptr_bytes": 4, "partition": f"1-D row blocks x{world}",
                    "x_exchange": A.exchange_mode, "halo_elems_per_rank": A.recv_elems,
-                   "exchange_overlapped_with_interior_tiles": bool(world > 1 and A._overlap_schedule()),
+                   "exchange_overlapped_with_interior_tiles": bool(world > 1 and os.environ.get("B2S_OVERLAP", "0") == "1"),
                    "step_replayed_from_cuda_graph": bool(graphed),
                    "l2": "inputs larger than L2 (matrix stream 600 MB + x/y 160 MB per step vs 126 MB L2); no flush",
                    "tile_config": int(spmv_plan.config), "kernel_family": "rowgroup" if spmv_plan.rowgroup else "tma-tiles",

@@ -362,9 +362,11 @@ class dist_csr_array:
     def dot(self, x_full: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
         """y_local = A_local @ x.  `x_full` is a full-length buffer whose my_cols slice is current.
 
-        With a chunked plan and a point-to-point halo the exchange runs on a side stream while the tiles that
-        read only local columns are already being multiplied; the few boundary tiles follow once the halo has
-        landed (B2S_OVERLAP=0 serialises exchange and SpMV)."""
+        With B2S_OVERLAP=1, a chunked plan and a point-to-point halo, the exchange runs on a side stream while
+        the tiles that read only local columns are already being multiplied; the few boundary tiles follow once
+        the halo has landed.  Off by default: measured on 2 and 4 B200s the split into three tile launches costs
+        what the overlap gains (156 vs 157 us/step at 2 GPUs, 164 vs 159 at 4), so exchange and SpMV are simply
+        serialised; the remaining ~16 us is the NCCL send/recv kernel itself."""
         A = self.local
         if out is None:
             out = torch.empty(A.shape[0], dtype=x_full.dtype, device=x_full.device)
@@ -372,7 +374,7 @@ class dist_csr_array:
         plan = A._get_plan()
         sched = None
         if (self.exchange_mode == "p2p" and x_full.is_cuda and A.dtype == numpy_dtype(x_full.dtype)
-                and os.environ.get("B2S_OVERLAP", "1") != "0"):
+                and os.environ.get("B2S_OVERLAP", "0") == "1"):
             sched = self._overlap_schedule()
         if sched is None:
             self.exchange(x_full)
@@ -401,7 +403,7 @@ class dist_csr_array:
         is what bounds a 140 us SpMV step otherwise."""
         from .linalg import _try_capture
 
-        key = (x_full.data_ptr(), out.data_ptr(), os.environ.get("B2S_OVERLAP", "1"))
+        key = (x_full.data_ptr(), out.data_ptr(), os.environ.get("B2S_OVERLAP", "0"))
         cache = self.__dict__.setdefault("_dot_graphs", {})
         g = cache.get(key)
         if g is None:

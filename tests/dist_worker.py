@@ -66,11 +66,13 @@ def main():
         sched = Ad._overlap_schedule()
         assert sched and len(sched[0]) >= 1 and len(sched[1]) >= 1, sched
         xf = Ad.scatter_vector(xg)
+        os.environ["B2S_OVERLAP"] = "1"
         y1 = Ad.dot(xf).clone()
         os.environ["B2S_OVERLAP"] = "0"
-        y2 = Ad.dot(xf)
-        os.environ["B2S_OVERLAP"] = "1"
-        assert torch.equal(y1, y2)
+        y2 = Ad.dot(xf).clone()
+        y3 = Ad.dot_graphed(xf, torch.empty_like(y2))
+        y3 = Ad.dot_graphed(xf, y3)   # second call replays the captured graph
+        assert torch.equal(y1, y2) and torch.equal(y2, y3)
 
         # 3. sharded CG == oracle CG on the global problem (same iteration count, same solution)
         b = np.ones(N)
