@@ -267,6 +267,23 @@ __device__ __forceinline__ void bitonic_sort_kv(int32_t* keys, V* vals, int n, i
   }
 }
 
+// 32-element bitonic sort held one (key,val) per lane, exchanged with shuffles (no shared memory, no barriers)
+template <typename V>
+__device__ __forceinline__ void warp_bitonic32(int32_t& k, V& v, int lane) {
+#pragma unroll
+  for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      const int32_t ok = __shfl_xor_sync(0xffffffffu, k, stride);
+      const V ov = __shfl_xor_sync(0xffffffffu, v, stride);
+      const bool up = (lane & size) == 0;
+      const bool lower = (lane & stride) == 0;
+      const bool take = (up == lower) ? (ok < k) : (ok > k);
+      if (take) { k = ok; v = ov; }
+    }
+  }
+}
+
 // ---- class 1: warp per row ---------------------------------------------------------------------------------
 // NUMERIC=false: count distinct columns -> row_nnz[row]; NUMERIC=true: accumulate, sort, write.
 template <typename V, typename P, int TBL, int BITS, int CMAX, bool NUMERIC>
@@ -373,13 +390,21 @@ spgemm_warp_kernel(int64_t count, const int32_t* __restrict__ perm, const P* __r
       }
       __syncwarp();
       const int n = s_n[wid];
-      int np2 = 1;
-      while (np2 < n) np2 <<= 1;
-      for (int i = n + lane; i < np2; i += 32) { s_ck[wid][i] = INT_MAX; s_cv[wid][i] = (V)0; }
-      __syncwarp();
-      bitonic_sort_kv<V>(s_ck[wid], s_cv[wid], np2, lane, 32, [] { __syncwarp(); });
       const long long base = c_ptr[row];
-      for (int i = lane; i < n; i += 32) { c_idx[base + i] = s_ck[wid][i]; c_val[base + i] = s_cv[wid][i]; }
+      if (n <= 32) {
+        // register sort: one entry per lane
+        int32_t k = lane < n ? s_ck[wid][lane] : INT_MAX;
+        V v = lane < n ? s_cv[wid][lane] : (V)0;
+        warp_bitonic32<V>(k, v, lane);
+        if (lane < n) { c_idx[base + lane] = k; c_val[base + lane] = v; }
+      } else {
+        int np2 = 1;
+        while (np2 < n) np2 <<= 1;
+        for (int i = n + lane; i < np2; i += 32) { s_ck[wid][i] = INT_MAX; s_cv[wid][i] = (V)0; }
+        __syncwarp();
+        bitonic_sort_kv<V>(s_ck[wid], s_cv[wid], np2, lane, 32, [] { __syncwarp(); });
+        for (int i = lane; i < n; i += 32) { c_idx[base + i] = s_ck[wid][i]; c_val[base + i] = s_cv[wid][i]; }
+      }
       __syncwarp();
     }
   }
