@@ -103,6 +103,19 @@ int         b2s_spmv_csr_tiles(int vt, int it, int pt, int64_t nrows, int64_t nc
                                const void* x, void* y, const void* plan,
                                int64_t tile_lo, int64_t tile_hi, void* stream);
 
+/* SpMV fused with the arrival of the x halo that peer GPUs are pushing (b2s_peer_halo_push): ONE kernel does
+ * the compute and consumes the collective.  Tiles are visited range by range (ranges_host = nranges x
+ * {tile_lo, tile_hi}); the first n_free ranges read only locally valid x; before its first other tile each
+ * CTA polls the nflags arrival flags (addresses in this GPU's memory, written remotely over NVLink) until
+ * they reach `expect`, so the exchange latency hides behind the interior tiles.  Bounded spin: on timeout
+ * *error_flag_dev = 1.  Replaces Legion's implicit halo copy + cusparseSpMV pair (sparse/csr.py:928-968). */
+int         b2s_spmv_csr_halo(int vt, int it, int pt, int64_t nrows, int64_t ncols, int64_t nnz,
+                              const void* indptr, const void* indices, const void* vals,
+                              const void* x, void* y, const void* plan, int nranges,
+                              const int64_t* ranges_host, int n_free, int nflags,
+                              void* const* flag_ptrs_host, uint64_t expect, void* error_flag_dev,
+                              void* stream);
+
 /* y_host = A x_host for HOST vectors (the matrix stays resident): pipelined H2D / tiles / D2H over the plan's
  * chunks on internal copy streams; x_dev / y_dev are caller-owned device scratch (ncols / nrows elements).
  * Pinned host memory gives true overlap.  syncs: y_host is complete on return. */
@@ -192,6 +205,14 @@ int         b2s_peer_allreduce(int vt, int rank, int nranks, void* const* peers_
 int         b2s_peer_halo_exchange(int vt, int rank, int nranks, void* const* peers_host,
                                    const void* x_local_dev, int nsends, const int64_t* send_desc_host,
                                    int nrecvs, const int32_t* recv_peers_host, void* stream);
+/* push only (no wait kernel); `epoch` > 0 increases by one per exchange and is the same on every rank.
+ * The consumer is b2s_spmv_csr_halo, which polls the arrival flags inside the SpMV kernel. */
+int         b2s_peer_halo_push(int vt, int rank, int nranks, void* const* peers_host,
+                               const void* x_local_dev, int nsends, const int64_t* send_desc_host,
+                               int nrecvs, const int32_t* recv_peers_host, int64_t epoch, void* stream);
+/* byte offset inside the peer header of the host-numbered arrival flag of source rank idx (which = 0) or of the
+ * error word (which = 1) */
+int64_t     b2s_peer_header_offset(int which, int idx);
 int         b2s_peer_check(void* own_buf_dev, void* stream, int64_t* error_out_host);   /* syncs */
 /* dst[i] = src[i] for i in [0,n) elements of type vt where src is a (possibly peer) device
  * pointer; 128-bit loads when both are 16-byte aligned. */

@@ -35,6 +35,8 @@ SIGNATURES = {
     "b2s_spmv_plan_chunks": (c_i32, [c_vp, c_vp, c_i32, ctypes.POINTER(c_i32)]),
     "b2s_spmv_csr_tiles": (c_i32, [c_i32, c_i32, c_i32, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp,
                                    c_i64, c_i64, c_vp]),
+    "b2s_spmv_csr_halo": (c_i32, [c_i32, c_i32, c_i32, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32,
+                                  c_vp, c_i32, c_i32, c_vp, ctypes.c_uint64, c_vp, c_vp]),
     "b2s_spmv_csr_host": (c_i32, [c_i32, c_i32, c_i32, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp,
                                   c_vp, c_vp]),
     "b2s_spmv_csr_dot": (c_i32, [c_i32, c_i32, c_i32, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp,
@@ -54,6 +56,8 @@ SIGNATURES = {
     "b2s_ipc_free": (c_i32, [c_vp]),
     "b2s_peer_allreduce": (c_i32, [c_i32, c_i32, c_i32, c_vp, c_vp, c_i32, c_vp]),
     "b2s_peer_halo_exchange": (c_i32, [c_i32, c_i32, c_i32, c_vp, c_vp, c_i32, c_vp, c_i32, c_vp, c_vp]),
+    "b2s_peer_halo_push": (c_i32, [c_i32, c_i32, c_i32, c_vp, c_vp, c_i32, c_vp, c_i32, c_vp, c_i64, c_vp]),
+    "b2s_peer_header_offset": (c_i64, [c_i32, c_i32]),
     "b2s_peer_check": (c_i32, [c_vp, c_vp, c_vp]),
     "b2s_ipc_export": (c_i32, [c_vp, c_vp]),
     "b2s_ipc_open": (c_i32, [c_vp, ctypes.POINTER(c_vp)]),

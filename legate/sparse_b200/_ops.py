@@ -251,6 +251,32 @@ def peer_halo_exchange(x_local: torch.Tensor, rank: int, peers, sends, recv_peer
                                         len(recv_peers), rp, _stream()), "b2s_peer_halo_exchange")
 
 
+def peer_halo_push(x_local: torch.Tensor, rank: int, peers, sends, recv_peers, epoch: int) -> None:
+    """Push halo slices into the neighbours' x buffers and raise their arrival flags (no wait kernel)."""
+    _chk_dev(x_local)
+    n = len(peers)
+    arr = (_lib.c_vp * n)(*peers)
+    flat = [int(v) for s in sends for v in s]
+    desc = (_lib.c_i64 * max(len(flat), 1))(*flat)
+    rp = (ctypes.c_int32 * max(len(recv_peers), 1))(*recv_peers)
+    _lib.check(L.b2s_peer_halo_push(vt_code(x_local.dtype), rank, n, arr, ptr(x_local), len(sends), desc,
+                                    len(recv_peers), rp, int(epoch), _stream()), "b2s_peer_halo_push")
+
+
+def spmv_halo(indptr, indices, data, x, y, shape, plan, ranges, n_free: int, flag_ptrs, expect: int, error_ptr: int):
+    """SpMV that waits inside the kernel for the halo flags before its non-free tile ranges."""
+    _chk_dev(indptr, indices, data, x, y)
+    nrows, ncols = shape
+    flat = [int(v) for r in ranges for v in r]
+    rg = (_lib.c_i64 * len(flat))(*flat)
+    fl = (_lib.c_vp * max(len(flag_ptrs), 1))(*flag_ptrs)
+    _lib.check(L.b2s_spmv_csr_halo(vt_code(data.dtype), idx_code(indices.dtype), idx_code(indptr.dtype), nrows, ncols,
+                                   data.shape[0], ptr(indptr), ptr(indices), ptr(data), ptr(x), ptr(y),
+                                   _plan_handle(plan), len(ranges), rg, n_free, len(flag_ptrs), fl, int(expect),
+                                   error_ptr, _stream()), "b2s_spmv_csr_halo")
+    return y
+
+
 def peer_check(own_ptr: int) -> int:
     out = _lib.c_i64(0)
     _lib.check(L.b2s_peer_check(own_ptr, _stream(), ctypes.byref(out)), "b2s_peer_check")

@@ -21,7 +21,8 @@ namespace b2s {
 
 constexpr int PEER_MAX = 16;
 constexpr int PEER_DATA_OFF = 8192;
-constexpr long long SPIN_LIMIT = 1LL << 27;  // ~ a second of polling
+constexpr long long SPIN_LIMIT = 1LL << 28;  // ~30 s of polling (20 ns sleep + a system-scope load per try): ranks may be
+                                             // seconds apart (graph capture, host-side work) without it being an error
 
 struct PeerHeader {
   unsigned long long ar_epoch;                  // completed all-reduces (local, device-incremented)
@@ -32,6 +33,10 @@ struct PeerHeader {
   double ar_val[2][PEER_MAX][4];                // written by peers
   unsigned long long halo_flag[PEER_MAX];       // written by peers: epoch of the last halo pushed by src
   unsigned long long halo_ack[PEER_MAX];        // written by peers: epoch dst has finished consuming
+  // second, independent flag set for the host-numbered protocol of the fused SpMV (b2s_peer_halo_push +
+  // b2s_spmv_csr_halo), so the two protocols can be mixed on one buffer without confusing each other's epochs
+  unsigned long long halo_flag2[PEER_MAX];
+  unsigned long long halo_ack2[PEER_MAX];
 };
 static_assert(sizeof(PeerHeader) <= PEER_DATA_OFF, "header must fit before the data region");
 
@@ -88,20 +93,22 @@ peer_allreduce_kernel(PeerPtrs peers, int rank, int nranks, V* inout, int count)
 template <typename V>
 __global__ void __launch_bounds__(256)
 peer_halo_push_kernel(PeerPtrs peers, int rank, const V* __restrict__ x_local, HaloSends sends, HaloRecvs recvs,
-                      long long data_off) {
+                      long long data_off, long long host_epoch) {
   PeerHeader* me = reinterpret_cast<PeerHeader*>(peers.p[rank]);
-  const unsigned long long e = me->halo_epoch + 1;
+  // epoch: device counter (advanced by the wait kernel) or, for the fused SpMV path, supplied by the host
+  const unsigned long long e = host_epoch > 0 ? (unsigned long long)host_epoch : me->halo_epoch + 1;
   const int b = blockIdx.x;
+  const bool hostp = host_epoch > 0;
   // acknowledge epoch e-1 to everyone who pushed to me: this kernel is stream-ordered after the SpMV that
   // consumed those halos, so their buffers may be overwritten now
   if (b == 0 && threadIdx.x < recvs.n) {
     PeerHeader* src = reinterpret_cast<PeerHeader*>(peers.p[recvs.peer[threadIdx.x]]);
-    st_sys(&src->halo_ack[rank], e - 1);
+    st_sys(hostp ? &src->halo_ack2[rank] : &src->halo_ack[rank], e - 1);
   }
   if (b >= sends.n) return;
   const int q = sends.peer[b];
   __shared__ bool ok;
-  if (threadIdx.x == 0) ok = spin_until_ge(&me->halo_ack[q], e - 1, me);
+  if (threadIdx.x == 0) ok = spin_until_ge(hostp ? &me->halo_ack2[q] : &me->halo_ack[q], e - 1, me);
   __syncthreads();
   if (!ok) return;
   V* dst = reinterpret_cast<V*>(peers.p[q] + data_off) + sends.dst_off[b];
@@ -121,7 +128,7 @@ peer_halo_push_kernel(PeerPtrs peers, int rank, const V* __restrict__ x_local, H
   __syncthreads();
   if (threadIdx.x == 0) {
     PeerHeader* dh = reinterpret_cast<PeerHeader*>(peers.p[q]);
-    st_sys(&dh->halo_flag[rank], e);
+    st_sys(hostp ? &dh->halo_flag2[rank] : &dh->halo_flag[rank], e);
   }
 }
 
@@ -185,9 +192,9 @@ int b2s_peer_allreduce(int vt, int rank, int nranks, void* const* peers_host, vo
 
 /* desc: nsends x {peer, src_elem_off, dst_elem_off, count}; recv_peers: ranks that push into this rank.
  * x_local_dev: this rank's x buffer (the data region of its own IPC buffer or any local array). */
-int b2s_peer_halo_exchange(int vt, int rank, int nranks, void* const* peers_host, const void* x_local_dev,
-                           int nsends, const int64_t* send_desc_host, int nrecvs, const int32_t* recv_peers_host,
-                           void* stream) {
+static int peer_halo_impl(int vt, int rank, int nranks, void* const* peers_host, const void* x_local_dev,
+                          int nsends, const int64_t* send_desc_host, int nrecvs, const int32_t* recv_peers_host,
+                          long long host_epoch, void* stream) {
   B2S_CHECK_ARG(vt == B2S_F32 || vt == B2S_F64, "bad value type code %d", vt);
   B2S_CHECK_ARG(nsends >= 0 && nsends <= PEER_MAX && nrecvs >= 0 && nrecvs <= PEER_MAX, "too many halo pieces");
   B2S_CHECK_ARG(nsends == 0 || (send_desc_host && x_local_dev), "NULL send descriptors / x");
@@ -211,12 +218,38 @@ int b2s_peer_halo_exchange(int vt, int rank, int nranks, void* const* peers_host
   }
   cudaStream_t st = (cudaStream_t)stream;
   const int blocks = nsends > 0 ? nsends : 1;
-  if (vt == B2S_F32) peer_halo_push_kernel<float><<<blocks, 256, 0, st>>>(pp, rank, (const float*)x_local_dev, s, r, PEER_DATA_OFF);
-  else               peer_halo_push_kernel<double><<<blocks, 256, 0, st>>>(pp, rank, (const double*)x_local_dev, s, r, PEER_DATA_OFF);
+  if (vt == B2S_F32) peer_halo_push_kernel<float><<<blocks, 256, 0, st>>>(pp, rank, (const float*)x_local_dev, s, r, PEER_DATA_OFF, host_epoch);
+  else               peer_halo_push_kernel<double><<<blocks, 256, 0, st>>>(pp, rank, (const double*)x_local_dev, s, r, PEER_DATA_OFF, host_epoch);
   B2S_LAUNCH_CHECK();
-  peer_halo_wait_kernel<<<1, 32, 0, st>>>(pp, rank, r);
-  B2S_LAUNCH_CHECK();
+  if (host_epoch <= 0) {
+    peer_halo_wait_kernel<<<1, 32, 0, st>>>(pp, rank, r);
+    B2S_LAUNCH_CHECK();
+  }
   return B2S_OK;
+}
+
+int b2s_peer_halo_exchange(int vt, int rank, int nranks, void* const* peers_host, const void* x_local_dev,
+                           int nsends, const int64_t* send_desc_host, int nrecvs, const int32_t* recv_peers_host,
+                           void* stream) {
+  return peer_halo_impl(vt, rank, nranks, peers_host, x_local_dev, nsends, send_desc_host, nrecvs, recv_peers_host, 0,
+                        stream);
+}
+
+/* push only (no wait kernel): the consumer is b2s_spmv_csr_halo, which polls the arrival flags itself.
+ * `epoch` (> 0, increasing by one per exchange, the same on every rank) replaces the device-side counter. */
+int b2s_peer_halo_push(int vt, int rank, int nranks, void* const* peers_host, const void* x_local_dev, int nsends,
+                       const int64_t* send_desc_host, int nrecvs, const int32_t* recv_peers_host, int64_t epoch,
+                       void* stream) {
+  B2S_CHECK_ARG(epoch > 0, "epoch must be positive");
+  return peer_halo_impl(vt, rank, nranks, peers_host, x_local_dev, nsends, send_desc_host, nrecvs, recv_peers_host,
+                        epoch, stream);
+}
+
+/* byte offsets inside the peer header: which=0 halo_flag[idx], which=1 error word */
+int64_t b2s_peer_header_offset(int which, int idx) {
+  if (which == 0 && idx >= 0 && idx < PEER_MAX) return (int64_t)offsetof(PeerHeader, halo_flag2) + 8 * idx;
+  if (which == 1) return (int64_t)offsetof(PeerHeader, error);
+  return -1;
 }
 
 /* reads PeerHeader::error of this rank's buffer (syncs the stream). */

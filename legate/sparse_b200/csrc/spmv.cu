@@ -395,6 +395,19 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// Tile processing order + optional in-kernel wait for a halo that other GPUs are still pushing into x
+// (csrc/peer.cu).  Tiles are visited range by range; ranges [0, n_free) only read locally valid x, the rest
+// may read halo columns, so before its first such tile each CTA's producer polls the arrival flags (local
+// memory, written remotely by the neighbours' push kernels).  The exchange latency hides behind the interior
+// tiles -- compute and collective in ONE kernel.  n_flags == 0: ordinary launch.
+struct TileOrder {
+  int nranges, n_free, n_flags, pad;
+  long long lo[6], hi[6];
+  const unsigned long long* flag[8];
+  unsigned long long expect;
+  unsigned long long* error;
+};
+
 struct __align__(16) TileMeta {
   long long k0, k1, kb;
   int r0, nr, rb, pad;
@@ -418,7 +431,7 @@ struct TmaLayout {
 
 template <typename V, typename I, typename P, int NC, int G, int STAGES, int MINB, bool UNI, bool DOT>
 __global__ void __launch_bounds__((NC + 1) * 32, MINB)
-spmv_tma_kernel(int64_t tile_lo, int64_t tile_hi, int64_t nrows, int64_t nnz, const P* __restrict__ indptr,
+spmv_tma_kernel(TileOrder order, int64_t nrows, int64_t nnz, const P* __restrict__ indptr,
                 const I* __restrict__ indices, const V* __restrict__ vals, const V* __restrict__ x,
                 V* __restrict__ y, const PlanEntry* __restrict__ plan, const V* __restrict__ w, V* dot_out, void* ws) {
   using LY = TmaLayout<V, I, P, NC, G, STAGES>;
@@ -454,7 +467,34 @@ spmv_tma_kernel(int64_t tile_lo, int64_t tile_hi, int64_t nrows, int64_t nnz, co
     const int64_t np1 = nrows + 1;
     const int64_t rp4 = np1 & ~(int64_t)3;
     int it = 0;
-    for (int64_t t = tile_lo + blockIdx.x; t < tile_hi; t += gridDim.x) {
+    long long total = 0, free_total = 0;
+    for (int r = 0; r < order.nranges; r++) {
+      total += order.hi[r] - order.lo[r];
+      if (r < order.n_free) free_total = total;
+    }
+    bool halo_ready = order.n_flags == 0;
+    for (long long v = blockIdx.x; v < total; v += gridDim.x) {
+      long long off = v;
+      int r = 0;
+      while (off >= order.hi[r] - order.lo[r]) { off -= order.hi[r] - order.lo[r]; r++; }
+      const int64_t t = order.lo[r] + off;
+      if (!halo_ready && v >= free_total) {
+        // first tile of this CTA that may read halo columns: wait (bounded) for every neighbour's push
+        if (lane == 0) {
+          for (int f = 0; f < order.n_flags; f++) {
+            long long spins = 0;
+            unsigned long long seen;
+            do {
+              asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(order.flag[f]) : "memory");
+              if (seen >= order.expect) break;
+              __nanosleep(20);
+            } while (++spins < (1LL << 28));
+            if (seen < order.expect) *order.error = 1ull;
+          }
+        }
+        __syncwarp();
+        halo_ready = true;
+      }
       const PlanEntry e0 = ld_plan(plan + t), e1 = ld_plan(plan + t + 1);
       const int nr = e1.row - e0.row;
       if (nr <= 0) continue;  // warp-uniform
@@ -703,6 +743,7 @@ spmv_rowgroup_kernel(int64_t nrows, const P* __restrict__ indptr, const I* __res
 struct SpmvArgs {
   int64_t ntiles, nrows, nnz;
   int64_t tile_lo, tile_hi;  // tile sub-range to run (TMA kernels); [0, ntiles) for a whole SpMV
+  const TileOrder* order;    // optional explicit tile order + halo wait (TMA kernels); NULL = [tile_lo, tile_hi)
   const void *indptr, *indices, *vals, *x;
   void* y;
   const PlanEntry* plan;
@@ -763,11 +804,23 @@ static int launch_tma_u(const SpmvArgs& a) {
   if (int rc = get_props(&pr)) return rc;
   int per_sm = occ;
   if (g_waves > 0 && g_waves < occ) per_sm = g_waves;
+  TileOrder order;
+  if (a.order) {
+    order = *a.order;
+  } else {
+    order.nranges = 1; order.n_free = 1; order.n_flags = 0; order.pad = 0;
+    order.lo[0] = a.tile_lo; order.hi[0] = a.tile_hi;
+    for (int i = 1; i < 6; i++) { order.lo[i] = 0; order.hi[i] = 0; }
+    for (int i = 0; i < 8; i++) order.flag[i] = nullptr;
+    order.expect = 0; order.error = nullptr;
+  }
+  int64_t ntl = 0;
+  for (int r = 0; r < order.nranges; r++) ntl += order.hi[r] - order.lo[r];
   int64_t grid = (int64_t)pr.sm_count * per_sm;
-  if (grid > a.tile_hi - a.tile_lo) grid = a.tile_hi - a.tile_lo;
+  if (grid > ntl) grid = ntl;
   if (DOT && grid > WS_MAX_PARTIALS) grid = WS_MAX_PARTIALS;
   if (grid < 1) grid = 1;
-  kern<<<(unsigned)grid, THREADS, smem, a.st>>>(a.tile_lo, a.tile_hi, a.nrows, a.nnz, (const P*)a.indptr, (const I*)a.indices,
+  kern<<<(unsigned)grid, THREADS, smem, a.st>>>(order, a.nrows, a.nnz, (const P*)a.indptr, (const I*)a.indices,
                                                 (const V*)a.vals, (const V*)a.x, (V*)a.y, a.plan, (const V*)a.w,
                                                 (V*)a.dot_out, a.ws);
   B2S_LAUNCH_CHECK();
@@ -1109,7 +1162,8 @@ int b2s_spmv_plan_set_kernel(void* plan, int use_rowgroup) {
 
 static int spmv_impl(int vt, int it, int pt, int64_t nrows, int64_t ncols, int64_t nnz, const void* indptr,
                      const void* indices, const void* vals, const void* x, void* y, const void* w, void* dot_out,
-                     const void* plan, void* ws, void* stream, bool dot, int64_t tile_lo = 0, int64_t tile_hi = -1) {
+                     const void* plan, void* ws, void* stream, bool dot, int64_t tile_lo = 0, int64_t tile_hi = -1,
+                     const TileOrder* order = nullptr) {
   if (int rc = check_common(vt, it, pt, nrows, ncols, nnz, indptr, indices, vals, x, y)) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   if (dot) {
@@ -1129,6 +1183,7 @@ static int spmv_impl(int vt, int it, int pt, int64_t nrows, int64_t ncols, int64
   const bool aligned = (nnz == 0) || (aligned16(indices) && aligned16(vals));
   bool rowgroup = (h == nullptr) || h->use_rowgroup;
   if (h && !rowgroup && kCfgs[h->cfg].kind == 1 && !(aligned && aligned16(indptr))) rowgroup = true;  // TMA needs 16-byte aligned bases
+  B2S_CHECK_ARG(!(rowgroup && order), "the fused halo SpMV needs the TMA tile kernel (aligned arrays, tile plan)");
   if (rowgroup) {
     int rc = (vt == B2S_F32) ? dispatch_rowgroup<float>(it, pt, nrows, nnz, indptr, indices, vals, x, y, st)
                              : dispatch_rowgroup<double>(it, pt, nrows, nnz, indptr, indices, vals, x, y, st);
@@ -1139,6 +1194,8 @@ static int spmv_impl(int vt, int it, int pt, int64_t nrows, int64_t ncols, int64
   a.ntiles = h->ntiles;
   a.tile_lo = tile_lo;
   a.tile_hi = tile_hi < 0 ? h->ntiles : tile_hi;
+  a.order = order;
+  B2S_CHECK_ARG(order == nullptr || kCfgs[h->cfg].kind == 1, "explicit tile orders need a TMA tile plan");
   B2S_CHECK_ARG(a.tile_lo >= 0 && a.tile_lo <= a.tile_hi && a.tile_hi <= h->ntiles, "tile range out of bounds");
   B2S_CHECK_ARG((a.tile_lo == 0 && a.tile_hi == h->ntiles) || kCfgs[h->cfg].kind == 1,
                 "tile sub-ranges need a TMA tile plan");
@@ -1171,6 +1228,28 @@ int b2s_spmv_csr_tiles(int vt, int it, int pt, int64_t nrows, int64_t ncols, int
   B2S_CHECK_ARG(plan != nullptr, "b2s_spmv_csr_tiles needs a plan");
   return spmv_impl(vt, it, pt, nrows, ncols, nnz, indptr, indices, vals, x, y, nullptr, nullptr, plan, nullptr,
                    stream, false, tile_lo, tile_hi);
+}
+
+/* SpMV fused with the arrival of a halo that peer GPUs push into x (b2s_peer_halo_push): tiles are visited range by
+ * range -- `ranges_host` = nranges x {tile_lo, tile_hi}, the first n_free ranges read only locally valid x --
+ * and before its first non-free tile each CTA polls the nflags arrival flags (device addresses in this GPU's
+ * memory) until they reach `expect`.  On timeout *error_flag_dev is set to 1 and the product continues. */
+int b2s_spmv_csr_halo(int vt, int it, int pt, int64_t nrows, int64_t ncols, int64_t nnz, const void* indptr,
+                      const void* indices, const void* vals, const void* x, void* y, const void* plan, int nranges,
+                      const int64_t* ranges_host, int n_free, int nflags, void* const* flag_ptrs_host,
+                      uint64_t expect, void* error_flag_dev, void* stream) {
+  B2S_CHECK_ARG(plan != nullptr, "b2s_spmv_csr_halo needs a plan");
+  B2S_CHECK_ARG(nranges >= 1 && nranges <= 6 && ranges_host && n_free >= 0 && n_free <= nranges, "bad tile ranges");
+  B2S_CHECK_ARG(nflags >= 0 && nflags <= 8 && (nflags == 0 || (flag_ptrs_host && error_flag_dev)), "bad flag list");
+  TileOrder o;
+  o.nranges = nranges; o.n_free = n_free; o.n_flags = nflags; o.pad = 0;
+  for (int i = 0; i < 6; i++) { o.lo[i] = i < nranges ? ranges_host[2 * i] : 0; o.hi[i] = i < nranges ? ranges_host[2 * i + 1] : 0; }
+  for (int i = 0; i < nranges; i++) B2S_CHECK_ARG(o.lo[i] >= 0 && o.hi[i] >= o.lo[i], "bad tile range %d", i);
+  for (int i = 0; i < 8; i++) o.flag[i] = i < nflags ? (const unsigned long long*)flag_ptrs_host[i] : nullptr;
+  o.expect = expect;
+  o.error = (unsigned long long*)error_flag_dev;
+  return spmv_impl(vt, it, pt, nrows, ncols, nnz, indptr, indices, vals, x, y, nullptr, nullptr, plan, nullptr,
+                   stream, false, 0, -1, &o);
 }
 
 /* y_host = A x_host with HOST vectors (matrix resident on the device): x is streamed in and y streamed out chunk

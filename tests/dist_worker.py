@@ -44,7 +44,10 @@ def main():
     os.environ["B2S_EXCHANGE"] = "auto"
 
     # 2./3. with the NVLink peer-memory path (csrc/peer.cu) and with plain NCCL
-    for peer, halo in (("1", "1"), ("1", "0"), ("0", "0")):
+    modes = [("1", "1"), ("1", "0"), ("0", "0")]
+    if os.environ.get("B2S_TEST_FUSED_HALO") == "1":   # experimental in-kernel halo wait (b2s_spmv_csr_halo)
+        modes.insert(0, ("1", "fused"))
+    for peer, halo in modes:
         os.environ["B2S_PEER"] = peer
         os.environ["B2S_PEER_HALO"] = halo
         # 2. shards assembled directly (gallery row_lo/row_hi) equal the slices of the global operator
@@ -57,7 +60,8 @@ def main():
         Ls = local.to_scipy_sparse_csr()
         assert (Ls != G[lo:hi]).nnz == 0
         Ad = bd.dist_csr_array(local, (N, N))
-        assert Ad.use_peer == (peer == "1") and Ad.use_peer_halo == (halo == "1")
+        assert Ad.use_peer == (peer == "1") and Ad.use_peer_halo == (halo in ("1", "fused"))
+        assert Ad.fused_halo == (halo == "fused")
         assert Ad.exchange_mode == "p2p" and Ad.recv_elems <= 2 * n1
         for rep in range(3):  # repeated exchanges exercise the epoch / ack protocol
             xg = rng.standard_normal(N)
@@ -95,6 +99,8 @@ def main():
         xg2 = bd.gather_vector(xl2, A2.row_plan, rank)
         assert np.allclose(S2 @ xg2, y2)
         Ad.check_peer(); A2.check_peer()
+        torch.cuda.synchronize()
+        dist.barrier()   # nobody unmaps / frees a shared buffer while a peer kernel may still touch it
         Ad.close(); A2.close()
 
     # 4. row-sharded SpGEMM: B all-gathered, C row-sharded with exact structure
@@ -110,10 +116,14 @@ def main():
     assert np.allclose(Gc.data, ref.data, rtol=1e-12)
     assert Ca.global_nnz == ref.nnz
 
+    torch.cuda.synchronize()
     dist.barrier()
     if rank == 0:
-        print(f"DIST_WORKER_OK world={world}")
-    dist.destroy_process_group()
+        print(f"DIST_WORKER_OK world={world}", flush=True)
+    sys.stdout.flush()
+    # tearing down an NCCL communicator while CUDA graphs that captured its send/recv kernels are still alive
+    # can block forever; every check has passed at this point, so leave without the orderly shutdown
+    os._exit(0)
 
 
 if __name__ == "__main__":
