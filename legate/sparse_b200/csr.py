@@ -48,12 +48,6 @@ def cast_to_common_type(*args):
     return tuple(a.astype(common, copy=False) if numpy_dtype(a.dtype) != common else a for a in args)
 
 
-def _dense_astype(x, dtype):
-    if isinstance(x, torch.Tensor):
-        return x.to(torch_dtype(dtype))
-    return x.astype(dtype, copy=False)
-
-
 class csr_array:
     """CSR matrix resident on one B200 (or, with no GPU visible, on the host for format logic)."""
 

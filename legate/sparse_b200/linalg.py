@@ -377,7 +377,7 @@ def _try_capture(fn):
                 g.capture_end()
         cur.wait_stream(side)
         torch.cuda.synchronize()
-        return _GraphOnCurrent(g)
+        return g
     except Exception as exc:  # pragma: no cover - depends on driver / NCCL capture support
         warnings.warn(f"CUDA graph capture of the CG iteration failed ({exc}); running eagerly", RuntimeWarning)
         try:
@@ -385,14 +385,6 @@ def _try_capture(fn):
         except Exception:
             pass
         return None
-
-
-class _GraphOnCurrent:
-    def __init__(self, g):
-        self.g = g
-
-    def replay(self):
-        self.g.replay()
 
 
 __all__ = [

@@ -344,3 +344,43 @@ def test_host_vectors_pipelined_path(kind, pinned, monkeypatch):
     # (n, 1) host vectors
     monkeypatch.setenv("B2S_PIPELINE", "1")
     assert np.array_equal((A @ x_np.reshape(-1, 1)).reshape(-1), ref)
+
+
+def test_plan_entries_follow_the_tile_rule():
+    """White-box check of b2s_spmv_plan_create: tile t starts at the first row r with indptr[r] + r >= t*T,
+    its entry holds that row, indptr[row] and the common row length of the tile (0 if rows differ); so every
+    tile has <= T rows and all rows but the last fit in T + 4 nonzeros."""
+    rng = np.random.default_rng(77)
+    nrows = 30011
+    lens = rng.integers(0, 9, nrows)
+    lens[5000:9000] = 6            # a uniform stretch
+    lens[12345] = 7000             # one row longer than several tiles
+    lens[20000:20400] = 0          # a run of empty rows
+    indptr = np.zeros(nrows + 1, dtype=np.int64)
+    np.cumsum(lens, out=indptr[1:])
+    rows = np.repeat(np.arange(nrows), lens)
+    indices = np.clip(rows + rng.integers(-40, 41, rows.shape[0]), 0, nrows - 1)   # columns near the diagonal
+    data = rng.standard_normal(rows.shape[0])
+    A = sparse.csr_array((data, indices, indptr), shape=(nrows, nrows))
+    plan = A._get_plan()
+    assert plan.config == 0 and not plan.scattered, (plan.config, plan.lines_per_warp)
+    T = 2 * 128 * 4 - 4            # fp64 default tile shape: CAP = EPT(2) * 128 consumer threads * 4 groups
+    ntiles = plan.tiles
+    assert ntiles == -(-(nrows + int(indptr[-1])) // T)
+    ent = plan.buf.cpu().numpy()[: 4 * (ntiles + 1)].reshape(-1, 4)
+    k = ent[:, 0].astype(np.uint32).astype(np.int64) | (ent[:, 1].astype(np.int64) << 32)
+    row, pad = ent[:, 2], ent[:, 3]
+    s = indptr[:-1] + np.arange(nrows)            # start position of each row in the (rows + nnz) work list
+    s = np.append(s, indptr[-1] + nrows)
+    expect_row = np.searchsorted(s, np.arange(ntiles) * T, side="left")
+    assert np.array_equal(row[:ntiles], expect_row) and row[ntiles] == nrows
+    assert np.array_equal(k, indptr[row])
+    assert (np.diff(row) <= T).all()
+    for t in range(ntiles):
+        r0, r1 = row[t], row[t + 1]
+        if r1 > r0 + 1:
+            assert indptr[r1 - 1] - indptr[r0] <= T        # all rows but the last fit in the staged chunk
+        ls = lens[r0:r1]
+        want = int(ls[0]) if (r1 > r0 and ls[0] > 0 and (ls == ls[0]).all()) else 0
+        assert pad[t] == want, (t, pad[t], want)
+    assert (pad[:ntiles] == 6).sum() >= 20                 # the uniform stretch is recognised
