@@ -11,10 +11,13 @@ Replaces the reference's partitioning layer (sparse/partition.py, sparse/csr.py:
            buffer: either by an all-gather of the T-padded shards (dense/random matrices) or by point-to-
            point pieces of exactly the window (stencil/banded matrices: two halo messages).
 * scalars: CG dot products are all-reduced (sum) as 1-element device tensors; they never visit the host
-           between convergence checks (linalg.py:539-555 keeps them in futures).
+           between convergence checks (linalg.py:539-555 keeps them in futures).  On GPUs of one box the
+           reduction is the one-shot NVLink peer-memory kernel of csrc/peer.cu (PeerComm), NCCL otherwise.
+* SpGEMM : B all-gathered once, C row-sharded (`spgemm`); rows can also be cut nnz-balanced
+           (`RowBlockPlan.balanced`, the reference's `balance()`).
 
-Collectives go through `torch.distributed` (NCCL on GPUs; gloo on CPU for the host-logic tests).  The
-local compute is always the C-ABI kernels via `_ops`.
+Plumbing goes through `torch.distributed` (NCCL on GPUs; gloo on CPU for the host-logic tests) and CUDA IPC for
+the peer buffers.  The local compute is always the C-ABI kernels via `_ops`.
 """
 from __future__ import annotations
 
