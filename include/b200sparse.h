@@ -132,6 +132,14 @@ int         b2s_spmv_csr_dot(int vt, int it, int pt, int64_t nrows, int64_t ncol
                              const void* x, void* y, const void* w, void* dot_out,
                              const void* plan, void* ws, void* stream);
 
+/* ---- SpMM: Y[nrows,k] = A @ X[ncols,k], dense operands row-major --------------------------
+ * Replaces SpMMCSR::gpu_variant (src/sparse/array/csr/spmm.cu:25-110, cusparseSpMM ALG2 with
+ * CUSPARSE_ORDER_ROW, alpha=1 beta=0) and the builder sparse/csr.py:1151-1205; CPU body spmm.cc:37-50.
+ * ldx / ldy are the row strides of X / Y in elements (>= k).  Y is overwritten. */
+int         b2s_spmm_csr(int vt, int it, int pt, int64_t nrows, int64_t ncols, int64_t nnz, int64_t k,
+                         const void* indptr, const void* indices, const void* vals,
+                         const void* X, int64_t ldx, void* Y, int64_t ldy, void* stream);
+
 /* ---- CG vector kernels ---------------------------------------------------------------
  * b2s_axpby replaces AXPBY::gpu_variant (src/sparse/linalg/axpby.cu:25-62):
  *   val = a[0]/b[0]; negate -> -val; isalpha ? y = val*x + y : y = x + val*y

@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_NAME = "libb200sparse.so"
 LIB_PATH = os.path.join(HERE, LIB_NAME)
-SOURCES = ["capi.cu", "spmv.cu", "vecops.cu", "spgemm.cu", "peer.cu"]
+SOURCES = ["capi.cu", "spmv.cu", "spmm.cu", "vecops.cu", "spgemm.cu", "peer.cu"]
 HEADERS = ["common.cuh", os.path.join("..", "..", "..", "include", "b200sparse.h")]
 
 NVCC_FLAGS = [

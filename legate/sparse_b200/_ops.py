@@ -95,6 +95,23 @@ def spmv(indptr, indices, data, x, y, shape, plan=None):
     return y
 
 
+def spmm(indptr, indices, data, X, Y, shape):
+    """Y = A @ X for row-major dense X (ncols, k), Y (nrows, k) (replaces task SPMM_CSR_DENSE, sparse/csr.py:1151-1205).
+    Rows of X / Y may be strided (leading dimension = stride(0)); the k entries of a row must be contiguous."""
+    _chk_dev(indptr, indices, data, X, Y)
+    nrows, ncols = shape
+    assert X.dtype == data.dtype == Y.dtype and X.ndim == 2 and Y.ndim == 2
+    k = X.shape[1]
+    assert X.shape[0] == ncols and tuple(Y.shape) == (nrows, k)
+    assert k <= 1 or (X.stride(1) == 1 and Y.stride(1) == 1)
+    ldx = X.stride(0) if X.shape[0] > 1 else max(k, 1)
+    ldy = Y.stride(0) if Y.shape[0] > 1 else max(k, 1)
+    _lib.check(L.b2s_spmm_csr(vt_code(data.dtype), idx_code(indices.dtype), idx_code(indptr.dtype), nrows, ncols,
+                              data.shape[0], k, ptr(indptr), ptr(indices), ptr(data), ptr(X), ldx, ptr(Y), ldy,
+                              _stream()), "b2s_spmm_csr")
+    return Y
+
+
 def spmv_tiles(indptr, indices, data, x, y, shape, plan, tile_lo: int, tile_hi: int):
     """Rows of tiles [tile_lo, tile_hi) of y = A @ x (x must be valid on that chunk's column window)."""
     _chk_dev(indptr, indices, data, x, y)

@@ -53,6 +53,7 @@ class csr_array:
 
     ndim = 2
     format = "csr"
+    __array_priority__ = 10.1  # like scipy.sparse: `ndarray @ A` defers to A.__rmatmul__
 
     def __init__(self, arg, shape=None, dtype=None, copy=False):
         from .module import is_sparse_matrix
@@ -304,6 +305,7 @@ class csr_array:
         """`A.dot(x)` / `A @ B`; see reference sparse/csr.py:442-582.
 
         * x 1-D or (n,1), numpy or torch CUDA tensor -> SpMV; result has x's array kind.
+        * other dense 2-D (n,k) -> SpMM, dense (m,k) result of the same array kind.
         * other a csr_array -> SpGEMM (CSR x CSR -> CSR).
         `spmv_domain_part` (column-split SpMV, csr.py:869-927) is accepted for signature
         compatibility; a single GPU has no column split and the row-split kernel is used.
@@ -382,7 +384,42 @@ class csr_array:
             if other_originally_sparse:
                 return csr_array(np.asarray(to_host(result)).reshape(self.shape[0], -1))
             return result
-        raise NotImplementedError("csr_array.dot: only vector (SpMV) and csr_array (SpGEMM) operands are implemented")
+        if other.ndim == 2:
+            # SpMM, reference csr.py:552-579: C = A @ B with a dense row-major B; `out` must have the resolved dtype.
+            runtime.require_cuda("csr_array.dot")
+            assert self.shape[1] == other.shape[0]
+            on_device = is_device_array(other) and other.is_cuda
+            common = np.result_type(self.dtype, numpy_dtype(other.dtype))
+            if common not in SUPPORTED_VALUE_DTYPES:
+                raise NotImplementedError(
+                    f"SpMM for resolved dtype {common} is not implemented (float32/float64 kernels only)"
+                )
+            A = self._promoted(common)
+            k = other.shape[1]
+            if out is not None:
+                odt = numpy_dtype(out.dtype)
+                if odt != common:
+                    raise ValueError(f"Output type {odt} is not consistent with resolved dtype {common}")
+                assert tuple(out.shape) == (self.shape[0], k)
+            B = to_device(other, dtype=common)
+            if k > 1 and B.stride(1) != 1:
+                B = B.contiguous()  # transposed / column-strided operand: the kernel needs contiguous rows (csr.py:572-577)
+            direct = isinstance(out, torch.Tensor) and out.is_cuda and (k <= 1 or out.stride(1) == 1)
+            C = out if direct else torch.empty((self.shape[0], k), dtype=torch_dtype(common), device=A.device)
+            _ops.spmm(A._indptr, A._indices, A._data, B, C, A.shape)
+            if out is None:
+                result = C if on_device else to_host(C)
+            else:
+                if not direct:
+                    if isinstance(out, torch.Tensor):
+                        out.copy_(C)
+                    else:
+                        out[...] = to_host(C)
+                result = out
+            if other_originally_sparse:
+                return csr_array(np.asarray(to_host(result)))
+            return result
+        raise NotImplementedError("csr_array.dot: operand must be a vector, a dense 2-D array or a csr_array")
 
     def matvec(self, other):
         return self @ other
@@ -391,7 +428,20 @@ class csr_array:
         return self.dot(other)
 
     def __rmatmul__(self, other):
-        raise NotImplementedError
+        """dense (i, m) @ A (m, n) -> dense (i, n)  (reference csr.py:801-822, rspmm csr.py:1208-1262).
+        Computed as (A^T @ other^T)^T with the row-major SpMM kernel; A^T is built once and cached."""
+        if not isinstance(other, (np.ndarray, torch.Tensor)):
+            other = np.asarray(other)
+        if other.ndim != 2:
+            raise NotImplementedError
+        assert other.shape[1] == self.shape[0]
+        key = (self._indptr.data_ptr(), self._indices.data_ptr(), self._data.data_ptr(), self.nnz)
+        if getattr(self, "_transposed", None) is None or self._transposed[0] != key:
+            self._transposed = (key, self.transpose())
+        At = self._transposed[1]
+        if isinstance(other, torch.Tensor):
+            return At.dot(other.t().contiguous()).t().contiguous()
+        return np.ascontiguousarray(At.dot(np.ascontiguousarray(other.T)).T)
 
     def __mul__(self, other):
         if np.isscalar(other):

@@ -1,0 +1,184 @@
+// spmm.cu -- CSR x dense (row-major) -> dense:  Y[nrows,k] = A[nrows,ncols] @ X[ncols,k].
+//
+// Replaces SpMMCSR::gpu_variant (reference src/sparse/array/csr/spmm.cu:25-110, cusparseSpMM with
+// CUSPARSE_SPMM_CSR_ALG2 on a row-major dense operand, alpha=1 beta=0) and its Python builder
+// (sparse/csr.py:1151-1205).  The CPU body it restates is spmm.cc:37-50.
+//
+// HBM/L2-bound gather.  A group of `lpr` lanes owns one row of A; lane s of the group owns the
+// output columns [s*VEC, (s+1)*VEC) (+ ch*lpr*VEC for CH column chunks).  Every nonzero turns into
+// one coalesced read of a row of X (lpr lanes x 16 bytes when VEC > 1) and one FMA per owned
+// column, accumulated left to right in registers exactly like the reference loop; Y is written once
+// with 16-byte stores.  The (index,value) pair of a nonzero is a group-uniform address, i.e. a
+// broadcast load -- no shuffles, so groups of a warp may run different trip counts.  The nonzero
+// loop is unrolled by 4 so that 4 independent X-row gathers are in flight per group.
+//
+// Algorithmic bytes: nnz*(sv+si) + (nrows+1)*sp + ncols*k*sv (X once) + nrows*k*sv (Y once); the
+// X-row gathers (nnz*k*sv) are served by L1/L2 when neighbouring rows share columns.
+#include "common.cuh"
+
+namespace b2s {
+
+constexpr int SPMM_THREADS = 256;
+
+template <typename V, int VEC> struct Pack;
+template <typename V> struct Pack<V, 1> {
+  V v[1];
+  __device__ __forceinline__ void load(const V* p) { v[0] = __ldg(p); }
+  __device__ __forceinline__ void store(V* p) const { p[0] = v[0]; }
+};
+template <> struct Pack<float, 4> {
+  float v[4];
+  __device__ __forceinline__ void load(const float* p) {
+    float4 t = __ldg(reinterpret_cast<const float4*>(p));
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  }
+  __device__ __forceinline__ void store(float* p) const { *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]); }
+};
+template <> struct Pack<double, 2> {
+  double v[2];
+  __device__ __forceinline__ void load(const double* p) {
+    double2 t = __ldg(reinterpret_cast<const double2*>(p));
+    v[0] = t.x; v[1] = t.y;
+  }
+  __device__ __forceinline__ void store(double* p) const { *reinterpret_cast<double2*>(p) = make_double2(v[0], v[1]); }
+};
+
+template <typename V, typename I, typename P, int VEC, int CH>
+__global__ void __launch_bounds__(SPMM_THREADS)
+spmm_row_kernel(int64_t nrows, int64_t k, const P* __restrict__ indptr, const I* __restrict__ indices,
+                const V* __restrict__ vals, const V* __restrict__ X, int64_t ldx, V* __restrict__ Y, int64_t ldy,
+                int lpr_shift) {
+  const int lpr = 1 << lpr_shift;
+  const int64_t row = ((int64_t)blockIdx.x * SPMM_THREADS + threadIdx.x) >> lpr_shift;
+  if (row >= nrows) return;
+  const int sub = threadIdx.x & (lpr - 1);
+  const int64_t jstep = (int64_t)lpr * VEC;
+  const int64_t j0 = (int64_t)blockIdx.y * (CH * jstep) + (int64_t)sub * VEC;
+  bool on[CH];
+  Pack<V, VEC> acc[CH];
+#pragma unroll
+  for (int c = 0; c < CH; c++) {
+    on[c] = (j0 + c * jstep) < k;  // VEC divides k on the vector path, so an owned pack is never ragged
+#pragma unroll
+    for (int e = 0; e < VEC; e++) acc[c].v[e] = (V)0;
+  }
+  int64_t p = (int64_t)indptr[row];
+  const int64_t pe = (int64_t)indptr[row + 1];
+  for (; p + 4 <= pe; p += 4) {
+    int64_t col[4];
+    V a[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      col[u] = (int64_t)__ldg(indices + p + u);
+      a[u] = __ldg(vals + p + u);
+    }
+    Pack<V, VEC> xv[4][CH];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const V* xr = X + col[u] * ldx + j0;
+#pragma unroll
+      for (int c = 0; c < CH; c++)
+        if (on[c]) xv[u][c].load(xr + c * jstep);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+#pragma unroll
+      for (int c = 0; c < CH; c++)
+        if (on[c]) {
+#pragma unroll
+          for (int e = 0; e < VEC; e++) acc[c].v[e] = fma(a[u], xv[u][c].v[e], acc[c].v[e]);
+        }
+    }
+  }
+  for (; p < pe; p++) {
+    const int64_t col = (int64_t)__ldg(indices + p);
+    const V a = __ldg(vals + p);
+    const V* xr = X + col * ldx + j0;
+#pragma unroll
+    for (int c = 0; c < CH; c++)
+      if (on[c]) {
+        Pack<V, VEC> xv;
+        xv.load(xr + c * jstep);
+#pragma unroll
+        for (int e = 0; e < VEC; e++) acc[c].v[e] = fma(a, xv.v[e], acc[c].v[e]);
+      }
+  }
+  V* yr = Y + row * ldy + j0;
+#pragma unroll
+  for (int c = 0; c < CH; c++)
+    if (on[c]) acc[c].store(yr + c * jstep);
+}
+
+template <typename V, typename I, typename P, int VEC>
+static int launch_spmm(int64_t nrows, int64_t k, const void* indptr, const void* indices, const void* vals,
+                       const void* X, int64_t ldx, void* Y, int64_t ldy, cudaStream_t st) {
+  const int64_t packs = (k + VEC - 1) / VEC;  // owned column packs per row
+  int shift = 0;
+  while ((1 << shift) < 32 && (int64_t)(1 << shift) < packs) shift++;
+  const int lpr = 1 << shift;
+  const int64_t gx = (nrows * lpr + SPMM_THREADS - 1) / SPMM_THREADS;
+  B2S_CHECK_ARG(gx < 2147483647LL, "SpMM grid too large");
+  if (packs <= lpr) {
+    dim3 grid((unsigned)gx, 1, 1);
+    spmm_row_kernel<V, I, P, VEC, 1><<<grid, SPMM_THREADS, 0, st>>>(
+        nrows, k, (const P*)indptr, (const I*)indices, (const V*)vals, (const V*)X, ldx, (V*)Y, ldy, shift);
+  } else {
+    constexpr int CH = 4;
+    const int64_t per_pass = (int64_t)CH * lpr * VEC;
+    const int64_t gy = (k + per_pass - 1) / per_pass;
+    B2S_CHECK_ARG(gy <= 65535, "SpMM with k = %lld dense columns is not supported (limit %lld)", (long long)k,
+                  (long long)(65535 * per_pass));
+    dim3 grid((unsigned)gx, (unsigned)gy, 1);
+    spmm_row_kernel<V, I, P, VEC, CH><<<grid, SPMM_THREADS, 0, st>>>(
+        nrows, k, (const P*)indptr, (const I*)indices, (const V*)vals, (const V*)X, ldx, (V*)Y, ldy, shift);
+  }
+  B2S_LAUNCH_CHECK();
+  return B2S_OK;
+}
+
+template <typename V, typename I, typename P>
+static int spmm_vec(int64_t nrows, int64_t k, const void* indptr, const void* indices, const void* vals, const void* X,
+                    int64_t ldx, void* Y, int64_t ldy, cudaStream_t st) {
+  constexpr int VEC = 16 / sizeof(V);
+  const bool vec_ok = (k % VEC == 0) && (ldx % VEC == 0) && (ldy % VEC == 0) && aligned16(X) && aligned16(Y);
+  if (vec_ok) return launch_spmm<V, I, P, VEC>(nrows, k, indptr, indices, vals, X, ldx, Y, ldy, st);
+  return launch_spmm<V, I, P, 1>(nrows, k, indptr, indices, vals, X, ldx, Y, ldy, st);
+}
+
+template <typename V>
+static int spmm_idx(int it, int pt, int64_t nrows, int64_t k, const void* indptr, const void* indices, const void* vals,
+                    const void* X, int64_t ldx, void* Y, int64_t ldy, cudaStream_t st) {
+  if (it == B2S_I32 && pt == B2S_I32) return spmm_vec<V, int32_t, int32_t>(nrows, k, indptr, indices, vals, X, ldx, Y, ldy, st);
+  if (it == B2S_I32 && pt == B2S_I64) return spmm_vec<V, int32_t, int64_t>(nrows, k, indptr, indices, vals, X, ldx, Y, ldy, st);
+  if (it == B2S_I64 && pt == B2S_I32) return spmm_vec<V, int64_t, int32_t>(nrows, k, indptr, indices, vals, X, ldx, Y, ldy, st);
+  return spmm_vec<V, int64_t, int64_t>(nrows, k, indptr, indices, vals, X, ldx, Y, ldy, st);
+}
+
+}  // namespace b2s
+
+using namespace b2s;
+
+extern "C" {
+
+int b2s_spmm_csr(int vt, int it, int pt, int64_t nrows, int64_t ncols, int64_t nnz, int64_t k, const void* indptr,
+                 const void* indices, const void* vals, const void* X, int64_t ldx, void* Y, int64_t ldy,
+                 void* stream) {
+  B2S_CHECK_ARG(vt == B2S_F32 || vt == B2S_F64, "bad value type code %d", vt);
+  B2S_CHECK_ARG(it == B2S_I32 || it == B2S_I64, "bad index type code %d", it);
+  B2S_CHECK_ARG(pt == B2S_I32 || pt == B2S_I64, "bad indptr type code %d", pt);
+  B2S_CHECK_ARG(nrows >= 0 && ncols >= 0 && nnz >= 0 && k >= 0, "negative dimension");
+  B2S_CHECK_ARG(nrows < 2147483647LL, "nrows >= 2^31-1 is not supported");
+  B2S_CHECK_ARG(pt == B2S_I64 || nnz < 2147483647LL, "int32 indptr cannot address nnz >= 2^31-1");
+  B2S_CHECK_ARG(ldx >= k && ldy >= k, "leading dimensions (%lld, %lld) smaller than k = %lld", (long long)ldx,
+                (long long)ldy, (long long)k);
+  if (nrows == 0 || k == 0) return B2S_OK;
+  B2S_CHECK_ARG(indptr != nullptr, "indptr is NULL");
+  B2S_CHECK_ARG(nnz == 0 || (indices != nullptr && vals != nullptr), "indices/vals NULL with nnz > 0");
+  B2S_CHECK_ARG(ncols == 0 || nnz == 0 || X != nullptr, "X is NULL");
+  B2S_CHECK_ARG(Y != nullptr, "Y is NULL");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (vt == B2S_F32) return spmm_idx<float>(it, pt, nrows, k, indptr, indices, vals, X, ldx, Y, ldy, st);
+  return spmm_idx<double>(it, pt, nrows, k, indptr, indices, vals, X, ldx, Y, ldy, st);
+}
+
+}  // extern "C"

@@ -393,4 +393,14 @@ __all__ = [
     "make_linear_operator",
     "cg_axpby",
     "cg",
+    "cgs",
+    "bicg",
+    "bicgstab",
+    "gmres",
+    "lsqr",
+    "eigsh",
 ]
+
+
+# the other Krylov solvers of the reference module (linalg.py:570-1569) live in krylov.py
+from .krylov import bicg, bicgstab, cgs, eigsh, gmres, lsqr  # noqa: E402,F401

@@ -111,6 +111,34 @@ int orc_spmv_csr_omp(int vt, int it, int pt, int64_t nrows, const void* indptr,
 }
 
 /* ------------------------------------------------------------------------
+ * CSR SpMM  Y = A @ X, X dense row-major (ncols x k, leading dimension ldx), Y (nrows x k, ldy).
+ * src/sparse/array/csr/spmm.cc:37-50: zero the output block, then for each row i and each
+ * nonzero kB of it (left to right), Y[i, j] += vals[kB] * X[crd[kB], j] for every j.
+ * ---------------------------------------------------------------------- */
+#define SPMM_BODY(T)                                                        \
+  do {                                                                      \
+    const T* A = (const T*)vals; const T* X = (const T*)x; T* Y = (T*)y;    \
+    for (int64_t i = 0; i < nrows; i++)                                     \
+      for (int64_t j = 0; j < k; j++) Y[i * ldy + j] = (T)0;                \
+    for (int64_t i = 0; i < nrows; i++) {                                   \
+      int64_t lo = ld_idx(indptr, pt, i), hi = ld_idx(indptr, pt, i + 1);   \
+      for (int64_t p = lo; p < hi; p++) {                                   \
+        int64_t c = ld_idx(indices, it, p);                                 \
+        for (int64_t j = 0; j < k; j++) Y[i * ldy + j] += A[p] * X[c * ldx + j]; \
+      }                                                                     \
+    }                                                                       \
+  } while (0)
+
+int orc_spmm_csr(int vt, int it, int pt, int64_t nrows, int64_t k, const void* indptr,
+                 const void* indices, const void* vals, const void* x, int64_t ldx, void* y, int64_t ldy)
+{
+  if (vt == 0) SPMM_BODY(float);
+  else if (vt == 1) SPMM_BODY(double);
+  else return ORC_EINVAL;
+  return ORC_OK;
+}
+
+/* ------------------------------------------------------------------------
  * AXPBY (fused CG vector update).  src/sparse/linalg/axpby.cc:34-42
  *   val = a[0]/b[0]; if NEGATE val = -1*val;
  *   IS_ALPHA: y = val*x + y   else: y = x + val*y

@@ -92,6 +92,20 @@ def spmv(indptr, indices, data, x, omp: bool = False, out=None) -> np.ndarray:
     return y
 
 
+def spmm(indptr, indices, data, X) -> np.ndarray:
+    """Y = A @ X for a dense row-major X (ncols, k); spmm.cc:37-50, dtype promotion as csr.py:557."""
+    indptr, indices = _c(indptr), _c(indices)
+    dt = np.result_type(data.dtype, X.dtype)
+    data, X = _c(data, dt), _c(X, dt)
+    assert X.ndim == 2
+    nrows, k = indptr.shape[0] - 1, X.shape[1]
+    Y = np.empty((nrows, k), dtype=dt)
+    rc = lib().orc_spmm_csr(_vt(dt), _wide(indices), _wide(indptr), ctypes.c_int64(nrows), ctypes.c_int64(k),
+                            _p(indptr), _p(indices), _p(data), _p(X), ctypes.c_int64(k), _p(Y), ctypes.c_int64(k))
+    assert rc == 0, rc
+    return Y
+
+
 def axpby(y, x, a, b, isalpha=True, negate=False) -> np.ndarray:
     """In-place fused update, sparse/linalg.py:479-496 / axpby.cc:34-42. a, b: 1-element arrays."""
     assert y.flags.c_contiguous and y.dtype == x.dtype

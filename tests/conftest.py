@@ -51,3 +51,20 @@ def sample_spd(N, density, seed):
     xs = np.asarray(scpy.random(N, 1, density=density, format="csr", dtype=np.float64, random_state=seed,
                                 data_rvs=Normal(seed=seed)().rvs).todense()).squeeze()
     return A, xs
+
+
+def sample(N, D, density, seed):
+    """Seeded random N x D matrix with normal entries and its dense test vector, as reference
+    tests/integration/utils/sample.py:25-44 (`sample`, `sample_dense_vector`)."""
+    import scipy.sparse as scpy
+    import scipy.stats as stats
+
+    class Normal(stats.rv_continuous):
+        def _rvs(self, *args, size=None, random_state=None):
+            return random_state.standard_normal(size)
+
+    S = scpy.random(N, D, density=density, format="csr", dtype=np.float64, random_state=seed,
+                    data_rvs=Normal(seed=seed)().rvs)
+    xs = np.asarray(scpy.random(D, 1, density=density, format="csr", dtype=np.float64, random_state=seed,
+                                data_rvs=Normal(seed=seed)().rvs).todense()).squeeze()
+    return S, xs

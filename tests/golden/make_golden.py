@@ -33,6 +33,10 @@ for name in MTX_FILES:
     out[f"{key}_x"] = x
     out[f"{key}_y"] = A @ x
     out[f"{key}_y32"] = (A.astype(np.float32) @ x.astype(np.float32))
+    # SpMM with a dense row-major operand, k = 8 (tests/integration/test_csr_dot.py's 2-D branch; csr.py:552-579)
+    X = np.random.default_rng(1).random((n, 8))
+    out[f"{key}_spmm_x"] = X
+    out[f"{key}_spmm_y"] = A @ X
     C = A @ A
     C.sort_indices()
     out[f"{key}_c_indptr"] = C.indptr.astype(np.int64)

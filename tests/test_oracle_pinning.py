@@ -61,6 +61,21 @@ def test_spmv_mixed_dtype_promotion(oracle, golden, key):
 
 
 @pytest.mark.parametrize("key", KEYS)
+@pytest.mark.parametrize("idx", [np.int32, np.int64])
+def test_spmm_golden(oracle, golden, key, idx):
+    indptr, indices, data = (golden[f"{key}_{n}"] for n in ("indptr", "indices", "data"))
+    X = golden[f"{key}_spmm_x"]
+    Y = oracle.spmm(indptr.astype(idx), indices.astype(idx), data, X)
+    # same left-to-right accumulation per output entry as scipy's csr_matvecs: bit-exact in fp64
+    assert np.array_equal(Y, golden[f"{key}_spmm_y"])
+    # a column of the SpMM is the SpMV with that column
+    assert np.array_equal(Y[:, 3], oracle.spmv(indptr, indices, data, np.ascontiguousarray(X[:, 3])))
+    Y32 = oracle.spmm(indptr.astype(idx), indices.astype(idx), data.astype(np.float32), X.astype(np.float32))
+    assert Y32.dtype == np.float32
+    assert np.allclose(Y32, golden[f"{key}_spmm_y"], rtol=1e-4, atol=1e-5 * np.abs(golden[f"{key}_spmm_y"]).max())
+
+
+@pytest.mark.parametrize("key", KEYS)
 def test_spgemm_golden(oracle, golden, key):
     indptr, indices, data = (golden[f"{key}_{n}"] for n in ("indptr", "indices", "data"))
     n = indptr.shape[0] - 1
