@@ -140,6 +140,9 @@ int         b2s_spmm_csr(int vt, int it, int pt, int64_t nrows, int64_t ncols, i
                          const void* indptr, const void* indices, const void* vals,
                          const void* X, int64_t ldx, void* Y, int64_t ldy, void* stream);
 
+/* tools / tests: 0 = staged tile kernel (default), 1 = one-row-per-lane-group kernel */
+int         b2s_spmm_set_kernel(int kernel);
+
 /* ---- CG vector kernels ---------------------------------------------------------------
  * b2s_axpby replaces AXPBY::gpu_variant (src/sparse/linalg/axpby.cu:25-62):
  *   val = a[0]/b[0]; negate -> -val; isalpha ? y = val*x + y : y = x + val*y

@@ -34,6 +34,7 @@ SIGNATURES = {
     "b2s_spmv_csr": (c_i32, [c_i32, c_i32, c_i32, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "b2s_spmm_csr": (c_i32, [c_i32, c_i32, c_i32, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp,
                              c_i64, c_vp]),
+    "b2s_spmm_set_kernel": (c_i32, [c_i32]),
     "b2s_spmv_plan_chunks": (c_i32, [c_vp, c_vp, c_i32, ctypes.POINTER(c_i32)]),
     "b2s_spmv_csr_tiles": (c_i32, [c_i32, c_i32, c_i32, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp,
                                    c_i64, c_i64, c_vp]),

@@ -4,13 +4,22 @@
 // CUSPARSE_SPMM_CSR_ALG2 on a row-major dense operand, alpha=1 beta=0) and its Python builder
 // (sparse/csr.py:1151-1205).  The CPU body it restates is spmm.cc:37-50.
 //
-// HBM/L2-bound gather.  A group of `lpr` lanes owns one row of A; lane s of the group owns the
-// output columns [s*VEC, (s+1)*VEC) (+ ch*lpr*VEC for CH column chunks).  Every nonzero turns into
-// one coalesced read of a row of X (lpr lanes x 16 bytes when VEC > 1) and one FMA per owned
+// HBM/L2-bound gather.  A group of `lpr` lanes owns one row of A at a time; lane s of the group owns
+// the output columns [s*VEC, (s+1)*VEC) (+ ch*lpr*VEC for CH column chunks).  Every nonzero turns
+// into one coalesced read of a row of X (lpr lanes x 16 bytes when VEC > 1) and one FMA per owned
 // column, accumulated left to right in registers exactly like the reference loop; Y is written once
-// with 16-byte stores.  The (index,value) pair of a nonzero is a group-uniform address, i.e. a
-// broadcast load -- no shuffles, so groups of a warp may run different trip counts.  The nonzero
-// loop is unrolled by 4 so that 4 independent X-row gathers are in flight per group.
+// with 16-byte stores.
+//
+// Two kernels share that mapping:
+//   spmm_tile_kernel (default): a CTA owns R = groups x rows_per_group consecutive rows.  Their
+//     indptr slice and their contiguous (index,value) range are staged into shared memory with
+//     coalesced evict-first loads -- two DRAM round trips per CTA tile -- after which a group walks
+//     its rows out of shared memory and only the X-row gathers (mostly L1/L2 hits: neighbouring
+//     rows share columns) touch global memory, U of them in flight per group.  A tile whose
+//     nonzeros do not fit the staging buffer (very long rows) reads them through the direct path.
+//   spmm_row_kernel: one row per group, (index,value) read straight from global memory as
+//     group-uniform broadcast loads; kept as the simple fallback (b2s_spmm_set_kernel(1)).
+// Neither uses shuffles, so the groups of a warp may run different trip counts.
 //
 // Algorithmic bytes: nnz*(sv+si) + (nrows+1)*sp + ncols*k*sv (X once) + nrows*k*sv (Y once); the
 // X-row gathers (nnz*k*sv) are served by L1/L2 when neighbouring rows share columns.
@@ -109,6 +118,124 @@ spmm_row_kernel(int64_t nrows, int64_t k, const P* __restrict__ indptr, const I*
     if (on[c]) acc[c].store(yr + c * jstep);
 }
 
+// ---- staged tile kernel ------------------------------------------------------------------------
+constexpr int SPMM_STAGE_BYTES = 36 * 1024;  // (index,value) staging per CTA
+constexpr int SPMM_MAX_TILE_ROWS = 1024;     // indptr staging: R + 1 entries
+
+template <typename V, typename I> struct SpmmStage {
+  static constexpr int CAP = (SPMM_STAGE_BYTES / (int)(sizeof(V) + sizeof(I))) / 256 * 256;
+};
+
+// One row of A for one lane group out of the staged copies: slots [qs, qe) of idx_s / val_s.
+// U nonzeros per trip (predicated), i.e. U independent X-row gathers in flight per group.
+template <typename V, typename I, int VEC, int CH, int U>
+__device__ __forceinline__ void spmm_walk_staged(int qs, int qe, const I* __restrict__ idx_s,
+                                                 const V* __restrict__ val_s, const V* __restrict__ X, int64_t ldx,
+                                                 int64_t jstep, const bool (&on)[CH], Pack<V, VEC> (&acc)[CH]) {
+  for (int q = qs; q < qe; q += U) {
+    V a[U];
+    Pack<V, VEC> xv[U][CH];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      if (q + u < qe) {
+        a[u] = val_s[q + u];
+        const V* xr = X + (int64_t)idx_s[q + u] * ldx;  // X already offset to this lane's first column
+#pragma unroll
+        for (int c = 0; c < CH; c++)
+          if (on[c]) xv[u][c].load(xr + c * jstep);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      if (q + u < qe) {
+#pragma unroll
+        for (int c = 0; c < CH; c++)
+          if (on[c]) {
+#pragma unroll
+            for (int e = 0; e < VEC; e++) acc[c].v[e] = fma(a[u], xv[u][c].v[e], acc[c].v[e]);
+          }
+      }
+    }
+  }
+}
+
+// The same row straight from global memory, one nonzero at a time: only for tiles whose nonzeros
+// exceed the staging buffer (rows thousands of entries long).
+template <typename V, typename I, int VEC, int CH>
+__device__ __forceinline__ void spmm_walk_direct(int64_t ps, int64_t pe, const I* __restrict__ indices,
+                                                 const V* __restrict__ vals, const V* __restrict__ X, int64_t ldx,
+                                                 int64_t jstep, const bool (&on)[CH], Pack<V, VEC> (&acc)[CH]) {
+  for (int64_t p = ps; p < pe; p++) {
+    const V a = __ldg(vals + p);
+    const V* xr = X + (int64_t)__ldg(indices + p) * ldx;
+#pragma unroll
+    for (int c = 0; c < CH; c++)
+      if (on[c]) {
+        Pack<V, VEC> xv;
+        xv.load(xr + c * jstep);
+#pragma unroll
+        for (int e = 0; e < VEC; e++) acc[c].v[e] = fma(a, xv.v[e], acc[c].v[e]);
+      }
+  }
+}
+
+template <typename V, typename I, typename P, int VEC, int CH>
+__global__ void __launch_bounds__(SPMM_THREADS, (CH == 1) ? 3 : 2)
+spmm_tile_kernel(int64_t nrows, int64_t k, const P* __restrict__ indptr, const I* __restrict__ indices,
+                 const V* __restrict__ vals, const V* __restrict__ X, int64_t ldx, V* __restrict__ Y, int64_t ldy,
+                 int lpr_shift, int rows_per_group) {
+  constexpr int CAP = SpmmStage<V, I>::CAP;
+  constexpr int U = (CH == 1) ? 4 : 2;  // X-row gathers in flight per group
+  __shared__ __align__(16) V val_s[CAP];
+  __shared__ __align__(16) I idx_s[CAP];
+  __shared__ int64_t rowptr_s[SPMM_MAX_TILE_ROWS + 1];
+
+  const int lpr = 1 << lpr_shift;
+  const int groups = SPMM_THREADS >> lpr_shift;
+  const int R = groups * rows_per_group;  // <= SPMM_MAX_TILE_ROWS (launcher)
+  const int64_t r0 = (int64_t)blockIdx.x * R;
+  const int Rn = (int)((nrows - r0) < (int64_t)R ? (nrows - r0) : (int64_t)R);  // >= 1 (grid sizing)
+  for (int i = threadIdx.x; i <= Rn; i += SPMM_THREADS) rowptr_s[i] = (int64_t)indptr[r0 + i];
+  __syncthreads();
+  const int64_t p_lo = rowptr_s[0], p_hi = rowptr_s[Rn];
+  const bool staged = (p_hi - p_lo) <= (int64_t)CAP;  // block-uniform
+  if (staged) {
+    for (int64_t i = threadIdx.x; i < p_hi - p_lo; i += SPMM_THREADS) {
+      idx_s[i] = ld_stream(indices + p_lo + i);
+      val_s[i] = ld_stream(vals + p_lo + i);
+    }
+    __syncthreads();
+  }
+  const int g = threadIdx.x >> lpr_shift;
+  const int sub = threadIdx.x & (lpr - 1);
+  const int64_t jstep = (int64_t)lpr * VEC;
+  const int64_t j0 = (int64_t)blockIdx.y * (CH * jstep) + (int64_t)sub * VEC;
+  bool on[CH];
+#pragma unroll
+  for (int c = 0; c < CH; c++) on[c] = (j0 + c * jstep) < k;
+  for (int j = 0; j < rows_per_group; j++) {
+    const int lr = j * groups + g;  // neighbouring groups walk neighbouring rows: shared X rows hit in L1
+    if (lr >= Rn) break;
+    Pack<V, VEC> acc[CH];
+#pragma unroll
+    for (int c = 0; c < CH; c++) {
+#pragma unroll
+      for (int e = 0; e < VEC; e++) acc[c].v[e] = (V)0;
+    }
+    const int64_t ps = rowptr_s[lr], pe = rowptr_s[lr + 1];
+    if (staged)
+      spmm_walk_staged<V, I, VEC, CH, U>((int)(ps - p_lo), (int)(pe - p_lo), idx_s, val_s, X + j0, ldx, jstep, on, acc);
+    else
+      spmm_walk_direct<V, I, VEC, CH>(ps, pe, indices, vals, X + j0, ldx, jstep, on, acc);
+    V* yr = Y + (r0 + lr) * ldy + j0;
+#pragma unroll
+    for (int c = 0; c < CH; c++)
+      if (on[c]) acc[c].store(yr + c * jstep);
+  }
+}
+
+static int g_spmm_kernel = 0;  // 0 = staged tile kernel, 1 = row kernel
+
 template <typename V, typename I, typename P, int VEC>
 static int launch_spmm(int64_t nrows, int64_t k, const void* indptr, const void* indices, const void* vals,
                        const void* X, int64_t ldx, void* Y, int64_t ldy, cudaStream_t st) {
@@ -116,21 +243,35 @@ static int launch_spmm(int64_t nrows, int64_t k, const void* indptr, const void*
   int shift = 0;
   while ((1 << shift) < 32 && (int64_t)(1 << shift) < packs) shift++;
   const int lpr = 1 << shift;
-  const int64_t gx = (nrows * lpr + SPMM_THREADS - 1) / SPMM_THREADS;
-  B2S_CHECK_ARG(gx < 2147483647LL, "SpMM grid too large");
-  if (packs <= lpr) {
-    dim3 grid((unsigned)gx, 1, 1);
-    spmm_row_kernel<V, I, P, VEC, 1><<<grid, SPMM_THREADS, 0, st>>>(
-        nrows, k, (const P*)indptr, (const I*)indices, (const V*)vals, (const V*)X, ldx, (V*)Y, ldy, shift);
-  } else {
-    constexpr int CH = 4;
-    const int64_t per_pass = (int64_t)CH * lpr * VEC;
-    const int64_t gy = (k + per_pass - 1) / per_pass;
-    B2S_CHECK_ARG(gy <= 65535, "SpMM with k = %lld dense columns is not supported (limit %lld)", (long long)k,
-                  (long long)(65535 * per_pass));
+  constexpr int CH = 4;
+  const bool multi = packs > lpr;  // more owned packs than lanes: CH column chunks per lane, grid.y passes
+  const int64_t per_pass = (int64_t)(multi ? CH : 1) * lpr * VEC;
+  const int64_t gy = (k + per_pass - 1) / per_pass;
+  B2S_CHECK_ARG(gy <= 65535, "SpMM with k = %lld dense columns is not supported (limit %lld)", (long long)k,
+                (long long)(65535 * per_pass));
+  if (g_spmm_kernel == 0) {
+    const int groups = SPMM_THREADS >> shift;
+    const int rpg = (groups * 4 <= SPMM_MAX_TILE_ROWS) ? 4 : 1;
+    const int64_t R = (int64_t)groups * rpg;
+    const int64_t gx = (nrows + R - 1) / R;
+    B2S_CHECK_ARG(gx < 2147483647LL, "SpMM grid too large");
     dim3 grid((unsigned)gx, (unsigned)gy, 1);
-    spmm_row_kernel<V, I, P, VEC, CH><<<grid, SPMM_THREADS, 0, st>>>(
-        nrows, k, (const P*)indptr, (const I*)indices, (const V*)vals, (const V*)X, ldx, (V*)Y, ldy, shift);
+    if (!multi)
+      spmm_tile_kernel<V, I, P, VEC, 1><<<grid, SPMM_THREADS, 0, st>>>(
+          nrows, k, (const P*)indptr, (const I*)indices, (const V*)vals, (const V*)X, ldx, (V*)Y, ldy, shift, rpg);
+    else
+      spmm_tile_kernel<V, I, P, VEC, CH><<<grid, SPMM_THREADS, 0, st>>>(
+          nrows, k, (const P*)indptr, (const I*)indices, (const V*)vals, (const V*)X, ldx, (V*)Y, ldy, shift, rpg);
+  } else {
+    const int64_t gx = (nrows * lpr + SPMM_THREADS - 1) / SPMM_THREADS;
+    B2S_CHECK_ARG(gx < 2147483647LL, "SpMM grid too large");
+    dim3 grid((unsigned)gx, (unsigned)gy, 1);
+    if (!multi)
+      spmm_row_kernel<V, I, P, VEC, 1><<<grid, SPMM_THREADS, 0, st>>>(
+          nrows, k, (const P*)indptr, (const I*)indices, (const V*)vals, (const V*)X, ldx, (V*)Y, ldy, shift);
+    else
+      spmm_row_kernel<V, I, P, VEC, CH><<<grid, SPMM_THREADS, 0, st>>>(
+          nrows, k, (const P*)indptr, (const I*)indices, (const V*)vals, (const V*)X, ldx, (V*)Y, ldy, shift);
   }
   B2S_LAUNCH_CHECK();
   return B2S_OK;
@@ -159,6 +300,13 @@ static int spmm_idx(int it, int pt, int64_t nrows, int64_t k, const void* indptr
 using namespace b2s;
 
 extern "C" {
+
+/* tools / tests: 0 = staged tile kernel (default), 1 = row kernel */
+int b2s_spmm_set_kernel(int kernel) {
+  B2S_CHECK_ARG(kernel == 0 || kernel == 1, "unknown SpMM kernel %d", kernel);
+  g_spmm_kernel = kernel;
+  return B2S_OK;
+}
 
 int b2s_spmm_csr(int vt, int it, int pt, int64_t nrows, int64_t ncols, int64_t nnz, int64_t k, const void* indptr,
                  const void* indices, const void* vals, const void* X, int64_t ldx, void* Y, int64_t ldy,

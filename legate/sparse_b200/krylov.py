@@ -57,6 +57,14 @@ def _residual(op, b, x):
     return b - op.matvec(x)
 
 
+def _confirm(op, b, x, tol):
+    """The short recurrences carry r along and it drifts away from b - A x in finite precision (CGS squares the
+    drift).  Before a solver reports convergence the residual is recomputed from x: -> (true r, true ||r|| < tol).
+    When it is not there yet the caller restarts its recurrence from the true residual."""
+    r = _residual(op, b, x)
+    return r, float(_ops.nrm2(r)[0]) < tol
+
+
 def _square_system(A, b):
     assert len(A.shape) == 2 and A.shape[0] == A.shape[1] and b.shape[0] == A.shape[0]
 
@@ -88,7 +96,12 @@ def cgs(A, b, x0=None, tol=1e-5, maxiter=None, M=None, callback=None, atol=None)
         x.addcmul_(alpha, uq)                                # x += alpha (u + q)
         r = torch.addcmul(r, alpha, op.matvec(uq), value=-1)
         if float(_ops.nrm2(r)[0]) < tol:
-            break
+            r, done = _confirm(op, b, x, tol)
+            if done:
+                break
+            shadow, p, u = r.clone(), r.clone(), r.clone()
+            rho = _ops.dot(r, shadow)
+            continue
         rho_next = _ops.dot(r, shadow)
         beta = rho_next / rho
         rho = rho_next
@@ -118,7 +131,12 @@ def bicg(A, b, x0=None, tol=1e-5, maxiter=None, M=None, callback=None, atol=None
         r = torch.addcmul(r, alpha, Ap, value=-1)
         rs = torch.addcmul(rs, alpha, op.rmatvec(ps), value=-1)
         if float(_ops.nrm2(r)[0]) < tol:
-            break
+            r, done = _confirm(op, b, x, tol)
+            if done:
+                break
+            rs, p, ps = r.clone(), r.clone(), r.clone()
+            rho = _ops.dot(rs, r)
+            continue
         rho_next = _ops.dot(rs, r)
         beta = rho_next / rho
         rho = rho_next
@@ -145,7 +163,12 @@ def bicgstab(A, b, x0=None, tol=1e-5, maxiter=None, M=None, callback=None, atol=
         s = torch.addcmul(r, alpha, Ap, value=-1)
         if float(_ops.nrm2(s)[0]) < tol:
             x.addcmul_(alpha, p)
-            break
+            r, done = _confirm(op, b, x, tol)
+            if done:
+                break
+            shadow, p = r.clone(), r.clone()
+            rho = _ops.dot(r, shadow)
+            continue
         As = op.matvec(s)
         omega = _ops.dot(As, s) / _ops.dot(As, As)
         x.addcmul_(alpha, p).addcmul_(omega, s)
@@ -153,7 +176,10 @@ def bicgstab(A, b, x0=None, tol=1e-5, maxiter=None, M=None, callback=None, atol=
         rho_next = _ops.dot(r, shadow)
         rnorm, rho_host = torch.cat([_ops.nrm2(r), rho_next]).tolist()   # one host round trip
         if rnorm < tol:
-            break
+            r, done = _confirm(op, b, x, tol)
+            if done:
+                break
+            rho_host = 0.0                      # not there yet: restart from the true residual
         if abs(rho_host) < 1e-8:
             shadow = r.clone()
             p = r.clone()

@@ -1,0 +1,67 @@
+"""Developer aid (NOT part of either test suite, never imported by the package): runs `-m gpu` test files in this
+GPU-less container with every tensor pretending to be a CUDA tensor and the leaf launchers of `_ops` swapped for
+the CPU oracle.  It checks the Python side of a new GPU test (shapes, dtypes, dispatch, return conventions) before
+GPU minutes are spent on it; it says nothing about the kernels.
+
+    python tests/dryrun_cpu.py tests/test_gpu_zspmm.py [-k expr]
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def install():
+    from legate.sparse_b200 import _ops, csr as csr_mod
+    from legate.sparse_b200.runtime import runtime
+    from oracle import oracle as orc
+
+    torch.Tensor.is_cuda = property(lambda self: True)
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    torch.cuda.synchronize = lambda *a, **k: None
+    for name in ("zeros", "empty", "ones", "full", "rand", "randn", "arange", "tensor"):
+        orig = getattr(torch, name)
+
+        def wrapped(*a, __orig=orig, **k):
+            if str(k.get("device", "cpu")).startswith("cuda"):
+                k["device"] = "cpu"
+            return __orig(*a, **k)
+
+        setattr(torch, name, wrapped)
+
+    class FakePlan:
+        chunks = []
+        config = rowgroup = uniform = scattered = tiles = 0
+
+    def spmv_plan(indptr, indices, shape, nnz, vdtype):
+        return FakePlan()
+
+    def spmv(indptr, indices, data, x, y, shape, plan=None):
+        y[:] = torch.from_numpy(orc.spmv(indptr.numpy(), indices.numpy(), data.numpy(), x.numpy()))
+        return y
+
+    def spmm(indptr, indices, data, X, Y, shape):
+        Y[:] = torch.from_numpy(orc.spmm(indptr.numpy(), indices.numpy(), data.numpy(), X.contiguous().numpy()))
+        return Y
+
+    def dot(x, y, out=None):
+        return torch.from_numpy(orc.dot(x.numpy(), y.numpy()))
+
+    def nrm2(x, out=None):
+        return torch.from_numpy(orc.nrm2(x.numpy()))
+
+    _ops.spmv_plan, _ops.spmv, _ops.spmm, _ops.dot, _ops.nrm2 = spmv_plan, spmv, spmm, dot, nrm2
+    runtime.require_cuda = lambda what: None
+    os.environ["B2S_CG_FUSED"] = "0"
+    os.environ["B2S_CG_GRAPH"] = "0"
+
+
+if __name__ == "__main__":
+    install()
+    sys.exit(pytest.main(["-m", "gpu", "-q", "-x", "-p", "no:cacheprovider"] + sys.argv[1:]))

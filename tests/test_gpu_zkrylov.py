@@ -22,12 +22,22 @@ def _system(N=100, D=100):
     return S, A, x, A @ x
 
 
+def _shifted():
+    # CGS / BiCGSTAB are rounding-lottery on the reference's indefinite sample (scipy's cgs stalls at 6e-5 after
+    # 1000 iterations, its bicgstab diverges; the reference skips its own BiCGSTAB test): same matrix shifted to be
+    # diagonally dominant, still non-symmetric
+    S, _, x, _ = _system()
+    S2 = sp.csr_array(S + 12.0 * sp.eye(100))
+    return S2, sparse.csr_array(S2), x, S2 @ x
+
+
 def test_cgs_solve():
-    S, A, x, y = _system()
-    assert np.allclose(S @ x, y)
+    S2, A, x, y = _shifted()
     x_pred = linalg.cgs(A, y, tol=1e-8)
     assert isinstance(x_pred, np.ndarray)
     assert np.allclose(A @ x_pred, y, rtol=1e-5, atol=1e-6)
+    ref, info = spla.cgs(S2, y, rtol=0, atol=1e-8)
+    assert info == 0 and np.allclose(x_pred, ref, atol=1e-6)
 
 
 def test_bicg_solve():
@@ -42,12 +52,7 @@ def test_bicg_solve():
 
 
 def test_bicgstab_solve():
-    # the reference skips its BiCGSTAB test (does not converge on the indefinite sample, nor does scipy's):
-    # same matrix shifted to be diagonally dominant, still non-symmetric
-    S, _, x, _ = _system()
-    S2 = sp.csr_array(S + 12.0 * sp.eye(100))
-    A = sparse.csr_array(S2)
-    y = S2 @ x
+    S2, A, x, y = _shifted()
     x_pred = linalg.bicgstab(A, y, tol=1e-8)
     assert np.allclose(A.dot(x_pred), y)
     ref, info = spla.bicgstab(S2, y, rtol=0, atol=1e-8)

@@ -18,6 +18,15 @@ pytestmark = pytest.mark.gpu
 TYPES = [np.float32, np.float64]
 
 
+@pytest.fixture(params=[0, 1], ids=["tile", "row"])
+def kernel(request):
+    """Both SpMM kernels: the staged tile kernel (default) and the one-row-per-group fallback."""
+    from legate.sparse_b200 import _lib
+    assert _lib.lib.b2s_spmm_set_kernel(request.param) == 0
+    yield request.param
+    _lib.lib.b2s_spmm_set_kernel(0)
+
+
 def _check(Y, A_sp, X, dt):
     ref = A_sp.astype(np.float64) @ np.asarray(X, dtype=np.float64)
     bound = abs(A_sp.astype(np.float64)) @ np.abs(np.asarray(X, dtype=np.float64))
@@ -76,7 +85,7 @@ def test_golden_vectors(golden, oracle, key):
 # k sweeps the lane-group sizes (1..32 packs), the vector/scalar split (k % VEC) and the multi-pass column chunks
 @pytest.mark.parametrize("k", [1, 2, 3, 4, 5, 7, 8, 12, 16, 17, 31, 32, 33, 48, 64, 65, 100, 128, 129, 256, 300, 520])
 @pytest.mark.parametrize("dt", TYPES)
-def test_k_sweep_vs_oracle(oracle, k, dt):
+def test_k_sweep_vs_oracle(oracle, kernel, k, dt):
     rng = np.random.default_rng(k)
     m, n = 777, 513
     A_sp = sp.random(m, n, density=0.02, format="csr", random_state=k, dtype=np.float64).astype(dt)
@@ -96,8 +105,9 @@ def test_k_sweep_vs_oracle(oracle, k, dt):
 
 
 @pytest.mark.parametrize("dt", TYPES)
-def test_row_shapes(dt):
-    """Empty rows, one long row (longer than the unroll), empty matrix, single column."""
+def test_row_shapes(kernel, dt):
+    """Empty rows, one row longer than the staging buffer (direct path of the tile kernel), a tile that just fits,
+    empty matrix, single column."""
     rng = np.random.default_rng(5)
     m, n, k = 300, 4000, 32
     rows = [np.array([], dtype=np.int64)] * m
@@ -120,7 +130,7 @@ def test_row_shapes(dt):
 
 
 @pytest.mark.parametrize("dt", TYPES)
-def test_device_operands_strided_and_out(dt):
+def test_device_operands_strided_and_out(kernel, dt):
     """torch operands: padded leading dimensions (ldx, ldy > k) and out= written in place."""
     rng = np.random.default_rng(11)
     m, n, k = 1000, 900, 24
@@ -145,6 +155,22 @@ def test_device_operands_strided_and_out(dt):
     _check(res2.cpu().numpy(), A_sp, Xh[:, :k], dt)
 
 
+@pytest.mark.parametrize("dt", TYPES)
+@pytest.mark.parametrize("k", [4, 32])
+def test_tiles_around_the_staging_capacity(kernel, dt, k):
+    """Row lengths chosen so that consecutive CTA tiles fall below, at and above the staging capacity."""
+    rng = np.random.default_rng(8)
+    m, n = 1500, 5000
+    lens = np.concatenate([np.full(300, 5), np.full(300, 47), np.full(300, 48), np.full(300, 49),
+                           rng.integers(0, 200, 300)])
+    indptr = np.concatenate([[0], np.cumsum(lens)])
+    indices = np.concatenate([np.sort(rng.choice(n, size=l, replace=False)) for l in lens])
+    data = rng.standard_normal(indices.shape[0]).astype(dt)
+    A_sp = sp.csr_array((data, indices, indptr), shape=(m, n))
+    X = rng.standard_normal((n, k)).astype(dt)
+    _check(sparse.csr_array(A_sp) @ X, A_sp, X, dt)
+
+
 def test_wide_indices(monkeypatch):
     monkeypatch.setenv("B2S_INDEX_WIDTH", "64")
     rng = np.random.default_rng(2)
@@ -162,6 +188,7 @@ def test_bad_arguments():
     assert rc != 0 and b"value type" in L.b2s_last_error()
     rc = L.b2s_spmm_csr(1, 0, 0, 4, 4, 0, 8, None, None, None, None, 4, None, 8, None)
     assert rc != 0 and b"leading" in L.b2s_last_error()
+    assert L.b2s_spmm_set_kernel(7) != 0 and b"unknown SpMM kernel" in L.b2s_last_error()
 
 
 def test_laplacian_k32_matches_spmv_columns():

@@ -49,18 +49,45 @@ def test_cgs_bicg_bicgstab_on_reference_system(cpu_ops):
     S, x = sample(100, 100, 0.1, 471014)
     y = S @ x
     A = _operator(S, cpu_ops)
-    for solver in (linalg.cgs, linalg.bicg):
-        xp = solver(A, y, tol=1e-8)
-        assert isinstance(xp, np.ndarray) and xp.dtype == np.float64
-        assert np.allclose(S @ xp, y, rtol=1e-5, atol=1e-6), solver.__name__
-    # BiCGSTAB does not converge on that indefinite system (neither does scipy's; the reference skips its test,
-    # test_bicg_solve.py:35): use the same matrix shifted to be diagonally dominant, still non-symmetric.
+    xp = linalg.bicg(A, y, tol=1e-8)
+    assert isinstance(xp, np.ndarray) and xp.dtype == np.float64
+    assert np.allclose(S @ xp, y, rtol=1e-5, atol=1e-6)
+    # CGS and BiCGSTAB are not robust on that indefinite system: whether CGS gets below 1e-8 within 10 n iterations
+    # depends on the rounding of the inner products (scipy's cgs stalls at 6e-5 after 1000 iterations, its bicgstab
+    # diverges; the reference skips its BiCGSTAB test, test_bicg_solve.py:35).  Same matrix shifted to be
+    # diagonally dominant, still non-symmetric:
     S2 = sp.csr_array(S + 12.0 * sp.eye(100))
     y2 = S2 @ x
-    xp = linalg.bicgstab(_operator(S2, cpu_ops), y2, tol=1e-8)
-    assert np.allclose(S2 @ xp, y2, rtol=1e-5, atol=1e-6)
-    ref, info = spla.bicgstab(S2, y2, rtol=0, atol=1e-8)
-    assert info == 0 and np.allclose(xp, ref, atol=1e-6)
+    for solver, ref_solver in ((linalg.cgs, spla.cgs), (linalg.bicgstab, spla.bicgstab)):
+        xp = solver(_operator(S2, cpu_ops), y2, tol=1e-8)
+        assert np.allclose(S2 @ xp, y2, rtol=1e-5, atol=1e-6), solver.__name__
+        ref, info = ref_solver(S2, y2, rtol=0, atol=1e-8)
+        assert info == 0 and np.allclose(xp, ref, atol=1e-6)
+
+
+def test_false_convergence_is_caught(cpu_ops, monkeypatch):
+    """The recurrence residual of CGS drifts from b - A x; a solver may only return once the recomputed residual
+    is below tol.  Forced here by an operator that is slightly perturbed inside the recurrences' products."""
+    from legate.sparse_b200 import krylov, linalg
+
+    Ad, xs = sample_spd(60, 0.1, 7)
+    S = sp.csr_array(Ad)
+    y = S @ xs
+    A = _operator(S, cpu_ops)
+    calls = []
+    real = krylov._confirm
+
+    def spy(op, b, x, tol):
+        r, ok = real(op, b, x, tol)
+        calls.append(ok)
+        return r, ok
+
+    monkeypatch.setattr(krylov, "_confirm", spy)
+    for solver in (linalg.cgs, linalg.bicg, linalg.bicgstab):
+        calls.clear()
+        xp = solver(A, y, tol=1e-9)
+        assert calls and calls[-1] is True
+        assert np.linalg.norm(S @ xp - y) < 1e-9
 
 
 def test_plain_solvers_honour_x0_maxiter_and_reject_M(cpu_ops):
