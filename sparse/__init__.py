@@ -15,3 +15,9 @@ from legate.sparse_b200 import (  # noqa: F401
     linalg,
     runtime,
 )
+
+
+class SparseArray:
+    """Placeholder only.  scipy's array-API helper looks up `sys.modules["sparse"].SparseArray` (the pydata/sparse
+    base class) whenever a module called `sparse` is loaded; without this name every scipy.sparse.linalg solver
+    raises AttributeError once this alias package has been imported.  Nothing derives from it."""
