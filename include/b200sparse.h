@@ -140,7 +140,8 @@ int         b2s_spmm_csr(int vt, int it, int pt, int64_t nrows, int64_t ncols, i
                          const void* indptr, const void* indices, const void* vals,
                          const void* X, int64_t ldx, void* Y, int64_t ldy, void* stream);
 
-/* tools / tests: 0 = staged tile kernel (default), 1 = one-row-per-lane-group kernel */
+/* tools / tests: 0 = choose by value type (default: fp64 -> staged tile kernel, fp32 -> row kernel),
+ * 1 = one-row-per-lane-group kernel, 2 = staged tile kernel */
 int         b2s_spmm_set_kernel(int kernel);
 
 /* ---- CG vector kernels ---------------------------------------------------------------

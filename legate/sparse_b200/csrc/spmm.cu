@@ -11,15 +11,24 @@
 // with 16-byte stores.
 //
 // Two kernels share that mapping:
-//   spmm_tile_kernel (default): a CTA owns R = groups x rows_per_group consecutive rows.  Their
-//     indptr slice and their contiguous (index,value) range are staged into shared memory with
-//     coalesced evict-first loads -- two DRAM round trips per CTA tile -- after which a group walks
-//     its rows out of shared memory and only the X-row gathers (mostly L1/L2 hits: neighbouring
-//     rows share columns) touch global memory, U of them in flight per group.  A tile whose
-//     nonzeros do not fit the staging buffer (very long rows) reads them through the direct path.
+//   spmm_tile_kernel: a CTA owns R = groups x rows_per_group consecutive rows.  Their indptr slice
+//     and their contiguous (index,value) range are staged into shared memory with coalesced
+//     evict-first loads, after which a group walks its rows out of shared memory and only the
+//     X-row gathers touch global memory -- U = 12 of them in flight per group, so a row of up to 12
+//     nonzeros is ONE memory round trip.  A tile whose nonzeros do not fit the staging buffer (very
+//     long rows) reads them through the direct path.
 //   spmm_row_kernel: one row per group, (index,value) read straight from global memory as
-//     group-uniform broadcast loads; kept as the simple fallback (b2s_spmm_set_kernel(1)).
+//     group-uniform broadcast loads, 4 gathers in flight.
 // Neither uses shuffles, so the groups of a warp may run different trip counts.
+//
+// Both are latency-bound, not bandwidth-bound (ncu, banded 11/row fp64 k=32: DRAM 22 % busy, L1TEX
+// 43 %, issue slots 44 %, 10 warps per issue stalled on long_scoreboard; L1 sector hit rate 79 %, DRAM
+// traffic = algorithmic bytes): what sets the time is the number of dependent memory round trips per
+// row times the resident warps, because an L1 hit queued behind another warp's miss returns no
+// sooner than the miss.  Raising the gathers in flight from 4 to 12 took the tile kernel from 1450 to
+// 1080 us on that case (row kernel 1390 us); a tile-wide `prefetch.global.L1` of the X rows made it
+// slower (1610 us).  Measured per value type (profiles/r01_spmm_bench.json) the tile kernel wins in
+// fp64 and the row kernel in fp32, which is how b2s_spmm_csr chooses (b2s_spmm_set_kernel overrides).
 //
 // Algorithmic bytes: nnz*(sv+si) + (nrows+1)*sp + ncols*k*sv (X once) + nrows*k*sv (Y once); the
 // X-row gathers (nnz*k*sv) are served by L1/L2 when neighbouring rows share columns.
@@ -133,12 +142,10 @@ __device__ __forceinline__ void spmm_walk_staged(int qs, int qe, const I* __rest
                                                  const V* __restrict__ val_s, const V* __restrict__ X, int64_t ldx,
                                                  int64_t jstep, const bool (&on)[CH], Pack<V, VEC> (&acc)[CH]) {
   for (int q = qs; q < qe; q += U) {
-    V a[U];
     Pack<V, VEC> xv[U][CH];
 #pragma unroll
     for (int u = 0; u < U; u++) {
       if (q + u < qe) {
-        a[u] = val_s[q + u];
         const V* xr = X + (int64_t)idx_s[q + u] * ldx;  // X already offset to this lane's first column
 #pragma unroll
         for (int c = 0; c < CH; c++)
@@ -148,11 +155,12 @@ __device__ __forceinline__ void spmm_walk_staged(int qs, int qe, const I* __rest
 #pragma unroll
     for (int u = 0; u < U; u++) {
       if (q + u < qe) {
+        const V a = val_s[q + u];  // re-read from shared memory: keeps the registers for the gathers in flight
 #pragma unroll
         for (int c = 0; c < CH; c++)
           if (on[c]) {
 #pragma unroll
-            for (int e = 0; e < VEC; e++) acc[c].v[e] = fma(a[u], xv[u][c].v[e], acc[c].v[e]);
+            for (int e = 0; e < VEC; e++) acc[c].v[e] = fma(a, xv[u][c].v[e], acc[c].v[e]);
           }
       }
     }
@@ -185,7 +193,7 @@ spmm_tile_kernel(int64_t nrows, int64_t k, const P* __restrict__ indptr, const I
                  const V* __restrict__ vals, const V* __restrict__ X, int64_t ldx, V* __restrict__ Y, int64_t ldy,
                  int lpr_shift, int rows_per_group) {
   constexpr int CAP = SpmmStage<V, I>::CAP;
-  constexpr int U = (CH == 1) ? 4 : 2;  // X-row gathers in flight per group
+  constexpr int U = (CH == 1) ? 12 : 2;  // X-row gathers in flight per group (see the header comment)
   __shared__ __align__(16) V val_s[CAP];
   __shared__ __align__(16) I idx_s[CAP];
   __shared__ int64_t rowptr_s[SPMM_MAX_TILE_ROWS + 1];
@@ -234,7 +242,7 @@ spmm_tile_kernel(int64_t nrows, int64_t k, const P* __restrict__ indptr, const I
   }
 }
 
-static int g_spmm_kernel = 0;  // 0 = staged tile kernel, 1 = row kernel
+static int g_spmm_kernel = 0;  // 0 = by value type (measured: fp64 -> tile, fp32 -> row), 1 = row kernel, 2 = tile kernel
 
 template <typename V, typename I, typename P, int VEC>
 static int launch_spmm(int64_t nrows, int64_t k, const void* indptr, const void* indices, const void* vals,
@@ -249,7 +257,8 @@ static int launch_spmm(int64_t nrows, int64_t k, const void* indptr, const void*
   const int64_t gy = (k + per_pass - 1) / per_pass;
   B2S_CHECK_ARG(gy <= 65535, "SpMM with k = %lld dense columns is not supported (limit %lld)", (long long)k,
                 (long long)(65535 * per_pass));
-  if (g_spmm_kernel == 0) {
+  const bool tile = (g_spmm_kernel == 2) || (g_spmm_kernel == 0 && sizeof(V) == 8);
+  if (tile) {
     const int groups = SPMM_THREADS >> shift;
     const int rpg = (groups * 4 <= SPMM_MAX_TILE_ROWS) ? 4 : 1;
     const int64_t R = (int64_t)groups * rpg;
@@ -301,9 +310,9 @@ using namespace b2s;
 
 extern "C" {
 
-/* tools / tests: 0 = staged tile kernel (default), 1 = row kernel */
+/* tools / tests: 0 = choose by value type (default), 1 = row kernel, 2 = staged tile kernel */
 int b2s_spmm_set_kernel(int kernel) {
-  B2S_CHECK_ARG(kernel == 0 || kernel == 1, "unknown SpMM kernel %d", kernel);
+  B2S_CHECK_ARG(kernel >= 0 && kernel <= 2, "unknown SpMM kernel %d", kernel);
   g_spmm_kernel = kernel;
   return B2S_OK;
 }

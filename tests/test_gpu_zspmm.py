@@ -18,9 +18,10 @@ pytestmark = pytest.mark.gpu
 TYPES = [np.float32, np.float64]
 
 
-@pytest.fixture(params=[0, 1], ids=["tile", "row"])
+@pytest.fixture(params=[2, 1], ids=["tile", "row"])
 def kernel(request):
-    """Both SpMM kernels: the staged tile kernel (default) and the one-row-per-group fallback."""
+    """Both SpMM kernels forced in turn (the default picks one per value type): the staged tile kernel and the
+    one-row-per-group kernel."""
     from legate.sparse_b200 import _lib
     assert _lib.lib.b2s_spmm_set_kernel(request.param) == 0
     yield request.param
