@@ -197,8 +197,9 @@ class csr_array:
         return csr_array._from_parts(self._indptr.clone(), self._indices.clone(), self._data.clone(), self.shape)
 
     def conj(self, copy=True):
-        # real dtypes only: conj is the identity
-        return self.copy() if copy else self
+        if self.dtype.kind == "c":
+            return csr_array._from_parts(self._indptr, self._indices, self._data.conj().resolve_conj(), self.shape)
+        return self.copy() if copy else self   # real: the identity
 
     def tocsr(self, copy=False):
         return self.copy() if copy else self
@@ -301,6 +302,87 @@ class csr_array:
                        self.shape, plan)
         return out
 
+    # -- complex operands ------------------------------------------------------------------------------
+    def _real_expansion(self, rdt):
+        """Real (2m x 2n) CSR matrix E with E @ interleave(re x, im x) = interleave(re (A x), im (A x)): every
+        complex entry a at (r, c) becomes the block [[re a, -im a], [im a, re a]] at rows 2r, 2r+1 / columns
+        2c, 2c+1.  Built once per matrix with tensor ops and cached, so a complex SpMV is ONE launch of the real
+        SpMV kernel on interleaved (re, im) storage -- which is exactly how complex vectors sit in memory."""
+        hit = self.__dict__.get("_expansion")
+        key = (self._data.data_ptr(), self._indptr.data_ptr(), np.dtype(rdt))
+        if hit is not None and hit[0] == key:
+            return hit[1]
+        m, n = self.shape
+        dev = self.device
+        nnz = self.nnz
+        tdt = torch_dtype(rdt)
+        ptr64 = self._indptr.to(torch.int64)
+        lens = ptr64[1:] - ptr64[:-1]
+        rows = torch.repeat_interleave(torch.arange(m, dtype=torch.int64, device=dev), lens)
+        q = torch.arange(nnz, dtype=torch.int64, device=dev) - ptr64[rows]      # position inside its row
+        top = 4 * ptr64[rows] + 2 * q                                           # slot of (2r, 2c)
+        bot = top + 2 * lens[rows]                                              # slot of (2r+1, 2c)
+        cols = self._indices.to(torch.int64)
+        data = self._data.to(torch.complex128 if np.dtype(rdt) == np.float64 else torch.complex64)
+        re, im = data.real.to(tdt), data.imag.to(tdt)
+        e_idx = torch.empty(4 * nnz, dtype=torch.int64, device=dev)
+        e_val = torch.empty(4 * nnz, dtype=tdt, device=dev)
+        e_idx[top], e_idx[top + 1], e_idx[bot], e_idx[bot + 1] = 2 * cols, 2 * cols + 1, 2 * cols, 2 * cols + 1
+        e_val[top], e_val[top + 1], e_val[bot], e_val[bot + 1] = re, -im, im, re
+        e_ptr = torch.empty(2 * m + 1, dtype=torch.int64, device=dev)
+        e_ptr[0:2 * m:2] = 4 * ptr64[:-1]
+        e_ptr[1:2 * m:2] = 4 * ptr64[:-1] + 2 * lens
+        e_ptr[2 * m] = 4 * nnz
+        wide = _force_wide()
+        idx_dt = torch.int64 if (wide or 2 * n > _INT32_MAX) else torch.int32
+        ptr_dt = torch.int64 if (wide or 4 * nnz > _INT32_MAX) else torch.int32
+        E = csr_array._from_parts(e_ptr.to(ptr_dt), e_idx.to(idx_dt), e_val, (2 * m, 2 * n))
+        self._expansion = (key, E)
+        return E
+
+    def _dot_complex(self, other, out):
+        """A @ x / A @ X when the resolved dtype is complex (the reference dispatches its SpMV / SpMM tasks over
+        complex64/128 too, src/sparse/util/dispatch.h).  No complex kernels: a real A with a complex operand is the
+        real SpMM on the (re, im)-interleaved view of the operand (twice the columns); a complex A goes through its
+        real expansion (`_real_expansion`)."""
+        runtime.require_cuda("csr_array.dot")
+        assert self.shape[1] == other.shape[0]
+        m, n = self.shape
+        common = np.result_type(self.dtype, numpy_dtype(other.dtype))
+        rdt = np.dtype(np.float32) if common == np.complex64 else np.dtype(np.float64)
+        if out is not None and numpy_dtype(out.dtype) != common:
+            raise ValueError(f"Output type {numpy_dtype(out.dtype)} is not consistent with resolved dtype {common}")
+        on_device = is_device_array(other) and other.is_cuda
+        X = to_device(other, dtype=common)
+        vector = X.ndim == 1
+        k = 1 if vector else X.shape[1]
+        Xr = torch.view_as_real(X.reshape(n, k))                                  # (n, k, 2) real view
+        if self.dtype.kind != "c":
+            Ar = self._promoted(rdt)
+            Yr = torch.empty((m, 2 * k), dtype=Xr.dtype, device=Xr.device)
+            _ops.spmm(Ar._indptr, Ar._indices, Ar._data, Xr.reshape(n, 2 * k), Yr, Ar.shape)
+            Y = torch.view_as_complex(Yr.reshape(m, k, 2))
+        else:
+            E = self._real_expansion(rdt)
+            if k == 1:
+                yr = torch.empty(2 * m, dtype=Xr.dtype, device=Xr.device)
+                _ops.spmv(E._indptr, E._indices, E._data, Xr.reshape(2 * n), yr, E.shape, plan=E._get_plan())
+                Y = torch.view_as_complex(yr.reshape(m, 1, 2))
+            else:
+                Xe = Xr.permute(0, 2, 1).reshape(2 * n, k).contiguous()           # rows: re x_0, im x_0, re x_1, ...
+                Ye = torch.empty((2 * m, k), dtype=Xr.dtype, device=Xr.device)
+                _ops.spmm(E._indptr, E._indices, E._data, Xe, Ye, E.shape)
+                Y = torch.view_as_complex(Ye.reshape(m, 2, k).permute(0, 2, 1).contiguous())
+        Y = Y.reshape(m) if vector else Y.reshape(m, k)
+        if out is not None:
+            assert tuple(out.shape) == tuple(Y.shape)
+            if isinstance(out, torch.Tensor):
+                out.copy_(Y)
+            else:
+                out[...] = to_host(Y)
+            return out
+        return Y if on_device else to_host(Y)
+
     def dot(self, other, out=None, spmv_domain_part=False):
         """`A.dot(x)` / `A @ B`; see reference sparse/csr.py:442-582.
 
@@ -324,6 +406,11 @@ class csr_array:
             other_originally_sparse = False
         if not isinstance(other, (np.ndarray, torch.Tensor)):
             other = np.asarray(other)
+        if other.ndim in (1, 2) and np.result_type(self.dtype, numpy_dtype(other.dtype)).kind == "c":
+            res = self._dot_complex(other, out)
+            if other_originally_sparse:
+                return csr_array(np.asarray(to_host(res)).reshape(self.shape[0], -1))
+            return res
         if other.ndim == 1 or (other.ndim == 2 and other.shape[1] == 1):
             runtime.require_cuda("csr_array.dot")
             assert self.shape[1] == other.shape[0]

@@ -245,7 +245,7 @@ spmm_tile_kernel(int64_t nrows, int64_t k, const P* __restrict__ indptr, const I
 static int g_spmm_kernel = 0;  // 0 = by value type (measured: fp64 -> tile, fp32 -> row), 1 = row kernel, 2 = tile kernel
 
 template <typename V, typename I, typename P, int VEC>
-static int launch_spmm(int64_t nrows, int64_t k, const void* indptr, const void* indices, const void* vals,
+static int launch_spmm(int64_t nrows, int64_t nnz, int64_t k, const void* indptr, const void* indices, const void* vals,
                        const void* X, int64_t ldx, void* Y, int64_t ldy, cudaStream_t st) {
   const int64_t packs = (k + VEC - 1) / VEC;  // owned column packs per row
   int shift = 0;
@@ -257,10 +257,15 @@ static int launch_spmm(int64_t nrows, int64_t k, const void* indptr, const void*
   const int64_t gy = (k + per_pass - 1) / per_pass;
   B2S_CHECK_ARG(gy <= 65535, "SpMM with k = %lld dense columns is not supported (limit %lld)", (long long)k,
                 (long long)(65535 * per_pass));
-  const bool tile = (g_spmm_kernel == 2) || (g_spmm_kernel == 0 && sizeof(V) == 8);
+  // rows per lane group: as many (<= 4) as keep an average tile's nonzeros inside the staging buffer (tiles
+  // that exceed it anyway fall back to the direct path inside the kernel); a narrow operand (many groups per CTA) on rows too long even for one row per group has nothing to
+  // gain from staging and takes the row kernel.
+  const int groups = SPMM_THREADS >> shift;
+  const double avg_row = nrows > 0 ? (double)nnz / (double)nrows : 0.0;
+  const double fit = (double)SpmmStage<V, I>::CAP / ((avg_row > 1.0 ? avg_row : 1.0) * groups);
+  const int rpg = fit >= 4.0 ? 4 : (fit >= 1.0 ? (int)fit : 1);
+  const bool tile = (g_spmm_kernel == 2) || (g_spmm_kernel == 0 && sizeof(V) == 8 && fit >= 1.0);
   if (tile) {
-    const int groups = SPMM_THREADS >> shift;
-    const int rpg = (groups * 4 <= SPMM_MAX_TILE_ROWS) ? 4 : 1;
     const int64_t R = (int64_t)groups * rpg;
     const int64_t gx = (nrows + R - 1) / R;
     B2S_CHECK_ARG(gx < 2147483647LL, "SpMM grid too large");
@@ -287,21 +292,21 @@ static int launch_spmm(int64_t nrows, int64_t k, const void* indptr, const void*
 }
 
 template <typename V, typename I, typename P>
-static int spmm_vec(int64_t nrows, int64_t k, const void* indptr, const void* indices, const void* vals, const void* X,
+static int spmm_vec(int64_t nrows, int64_t nnz, int64_t k, const void* indptr, const void* indices, const void* vals, const void* X,
                     int64_t ldx, void* Y, int64_t ldy, cudaStream_t st) {
   constexpr int VEC = 16 / sizeof(V);
   const bool vec_ok = (k % VEC == 0) && (ldx % VEC == 0) && (ldy % VEC == 0) && aligned16(X) && aligned16(Y);
-  if (vec_ok) return launch_spmm<V, I, P, VEC>(nrows, k, indptr, indices, vals, X, ldx, Y, ldy, st);
-  return launch_spmm<V, I, P, 1>(nrows, k, indptr, indices, vals, X, ldx, Y, ldy, st);
+  if (vec_ok) return launch_spmm<V, I, P, VEC>(nrows, nnz, k, indptr, indices, vals, X, ldx, Y, ldy, st);
+  return launch_spmm<V, I, P, 1>(nrows, nnz, k, indptr, indices, vals, X, ldx, Y, ldy, st);
 }
 
 template <typename V>
-static int spmm_idx(int it, int pt, int64_t nrows, int64_t k, const void* indptr, const void* indices, const void* vals,
+static int spmm_idx(int it, int pt, int64_t nrows, int64_t nnz, int64_t k, const void* indptr, const void* indices, const void* vals,
                     const void* X, int64_t ldx, void* Y, int64_t ldy, cudaStream_t st) {
-  if (it == B2S_I32 && pt == B2S_I32) return spmm_vec<V, int32_t, int32_t>(nrows, k, indptr, indices, vals, X, ldx, Y, ldy, st);
-  if (it == B2S_I32 && pt == B2S_I64) return spmm_vec<V, int32_t, int64_t>(nrows, k, indptr, indices, vals, X, ldx, Y, ldy, st);
-  if (it == B2S_I64 && pt == B2S_I32) return spmm_vec<V, int64_t, int32_t>(nrows, k, indptr, indices, vals, X, ldx, Y, ldy, st);
-  return spmm_vec<V, int64_t, int64_t>(nrows, k, indptr, indices, vals, X, ldx, Y, ldy, st);
+  if (it == B2S_I32 && pt == B2S_I32) return spmm_vec<V, int32_t, int32_t>(nrows, nnz, k, indptr, indices, vals, X, ldx, Y, ldy, st);
+  if (it == B2S_I32 && pt == B2S_I64) return spmm_vec<V, int32_t, int64_t>(nrows, nnz, k, indptr, indices, vals, X, ldx, Y, ldy, st);
+  if (it == B2S_I64 && pt == B2S_I32) return spmm_vec<V, int64_t, int32_t>(nrows, nnz, k, indptr, indices, vals, X, ldx, Y, ldy, st);
+  return spmm_vec<V, int64_t, int64_t>(nrows, nnz, k, indptr, indices, vals, X, ldx, Y, ldy, st);
 }
 
 }  // namespace b2s
@@ -334,8 +339,8 @@ int b2s_spmm_csr(int vt, int it, int pt, int64_t nrows, int64_t ncols, int64_t n
   B2S_CHECK_ARG(ncols == 0 || nnz == 0 || X != nullptr, "X is NULL");
   B2S_CHECK_ARG(Y != nullptr, "Y is NULL");
   cudaStream_t st = (cudaStream_t)stream;
-  if (vt == B2S_F32) return spmm_idx<float>(it, pt, nrows, k, indptr, indices, vals, X, ldx, Y, ldy, st);
-  return spmm_idx<double>(it, pt, nrows, k, indptr, indices, vals, X, ldx, Y, ldy, st);
+  if (vt == B2S_F32) return spmm_idx<float>(it, pt, nrows, nnz, k, indptr, indices, vals, X, ldx, Y, ldy, st);
+  return spmm_idx<double>(it, pt, nrows, nnz, k, indptr, indices, vals, X, ldx, Y, ldy, st);
 }
 
 }  // extern "C"

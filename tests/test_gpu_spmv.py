@@ -75,7 +75,7 @@ def test_wrong_out_dtype_and_shapes():
     with pytest.raises(AssertionError):
         A.dot(np.ones(8))
     with pytest.raises(NotImplementedError):
-        A.dot(np.ones(9, dtype=np.complex128))
+        A.dot(np.ones((9, 2, 2)))
 
 
 def test_device_resident_vectors():

@@ -202,3 +202,60 @@ def test_laplacian_k32_matches_spmv_columns():
     for j in (0, 13, 31):
         y = A @ X[:, j].contiguous()
         assert torch.allclose(Y[:, j], y, rtol=1e-12, atol=1e-9)
+
+
+# ---- complex operands (the reference dispatches SpMV / SpMM over complex64/128 as well) -------------------
+CTYPES = [np.complex64, np.complex128]
+
+
+def _crand(rng, shape, dt):
+    return (rng.standard_normal(shape) + 1j * rng.standard_normal(shape)).astype(dt)
+
+
+@pytest.mark.parametrize("a_type", TYPES + CTYPES)
+@pytest.mark.parametrize("x_type", TYPES + CTYPES)
+def test_complex_spmv_and_spmm(a_type, x_type):
+    if np.dtype(a_type).kind != "c" and np.dtype(x_type).kind != "c":
+        pytest.skip("real x real is covered above")
+    rng = np.random.default_rng(17)
+    m, n = 333, 257
+    S = sp.random(m, n, density=0.05, format="csr", random_state=4, dtype=np.float64)
+    S.sort_indices()
+    data = _crand(rng, S.nnz, a_type) if np.dtype(a_type).kind == "c" else rng.standard_normal(S.nnz).astype(a_type)
+    S = sp.csr_array((data, S.indices, S.indptr), shape=(m, n))
+    A = sparse.csr_array(S)
+    assert A.dtype == np.dtype(a_type)
+    common = np.result_type(a_type, x_type)
+    tol = dict(rtol=2e-4, atol=2e-4) if common == np.complex64 else dict(rtol=1e-11, atol=1e-11)
+    x = _crand(rng, n, x_type) if np.dtype(x_type).kind == "c" else rng.standard_normal(n).astype(x_type)
+    y = A @ x
+    assert y.dtype == common and y.shape == (m,)
+    assert np.allclose(y, S @ x, **tol)
+    assert np.allclose(A.dot(x.reshape(n, 1)), (S @ x).reshape(m, 1), **tol)
+    X = _crand(rng, (n, 5), x_type) if np.dtype(x_type).kind == "c" else rng.standard_normal((n, 5)).astype(x_type)
+    Y = A @ X
+    assert Y.dtype == common and Y.shape == (m, 5)
+    assert np.allclose(Y, S @ X, **tol)
+    out = np.zeros(m, dtype=common)
+    assert A.dot(x, out=out) is out and np.allclose(out, S @ x, **tol)
+    with pytest.raises(ValueError):
+        A.dot(x, out=np.zeros(m, dtype=np.float64))
+    xd = torch.from_numpy(x).cuda()
+    yd = A @ xd
+    assert isinstance(yd, torch.Tensor) and yd.is_cuda and np.allclose(yd.cpu().numpy(), S @ x, **tol)
+
+
+def test_complex_matrix_helpers():
+    rng = np.random.default_rng(3)
+    S = sp.random(40, 30, density=0.2, format="csr", random_state=1, dtype=np.float64)
+    S = sp.csr_array((_crand(rng, S.nnz, np.complex128), S.indices, S.indptr), shape=S.shape)
+    A = sparse.csr_array(S)
+    x = _crand(rng, 40, np.complex128)
+    assert np.allclose(A.conj().todense(), S.conj().toarray())
+    assert np.allclose(A.T.conj() @ x, S.T.conj() @ x)
+    E = A._real_expansion(np.float64)
+    assert E.shape == (80, 60) and E.nnz == 4 * A.nnz and A._real_expansion(np.float64) is E
+    Ed = np.asarray(E.todense())
+    Sd = S.toarray()
+    assert np.array_equal(Ed[0::2, 0::2], Sd.real) and np.array_equal(Ed[1::2, 1::2], Sd.real)
+    assert np.array_equal(Ed[1::2, 0::2], Sd.imag) and np.array_equal(Ed[0::2, 1::2], -Sd.imag)
