@@ -8,7 +8,6 @@ GPU minutes are spent on it; it says nothing about the kernels.
 import os
 import sys
 
-import numpy as np
 import pytest
 import torch
 
@@ -18,13 +17,22 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 
 def install():
-    from legate.sparse_b200 import _ops, csr as csr_mod
+    from legate.sparse_b200 import _ops
     from legate.sparse_b200.runtime import runtime
     from oracle import oracle as orc
 
     torch.Tensor.is_cuda = property(lambda self: True)
     torch.Tensor.cuda = lambda self, *a, **k: self
     torch.cuda.synchronize = lambda *a, **k: None
+    real_to = torch.Tensor.to
+
+    def to(self, *a, **k):
+        a = tuple("cpu" if (isinstance(v, (str, torch.device)) and str(v).startswith("cuda")) else v for v in a)
+        if str(k.get("device", "cpu")).startswith("cuda"):
+            k["device"] = "cpu"
+        return real_to(self, *a, **k)
+
+    torch.Tensor.to = to
     for name in ("zeros", "empty", "ones", "full", "rand", "randn", "arange", "tensor"):
         orig = getattr(torch, name)
 

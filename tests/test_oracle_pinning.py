@@ -6,7 +6,6 @@ import numpy as np
 import pytest
 import scipy.io as sio
 import scipy.sparse as sp
-import scipy.sparse.linalg as spla
 
 from conftest import MTX_FILES, mtx_path, sample_spd
 
