@@ -446,6 +446,35 @@ class dist_csr_array:
             self.dot(x_full, out=out)
         return out
 
+    # -- SpMM ---------------------------------------------------------------------------------------------
+    def new_full_matrix(self, k: int, dtype=None) -> torch.Tensor:
+        """(ncols padded to P*T, k) row-major buffer for a dense operand sharded by rows like the vectors."""
+        dt = torch_dtype(numpy_dtype(self.dtype if dtype is None else dtype))
+        return torch.zeros((max(self.col_plan.padded, 1), int(k)), dtype=dt, device=runtime.device)
+
+    def spmm(self, X_full: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+        """Y_local (local rows, k) = A_local @ X (reference spmm(), csr.py:1151-1205: rows of A tiled, the image
+        of `crd` into the rows of the dense operand decides what each shard needs).  `X_full` is a full-height
+        buffer whose rows [my_cols) are current; the rows of this shard's column window are fetched with the same
+        exchange plan as the SpMV vector (all-gather or point-to-point halo, k values per exchanged row)."""
+        A = self.local
+        assert X_full.ndim == 2 and X_full.is_contiguous()
+        if out is None:
+            out = torch.empty((A.shape[0], X_full.shape[1]), dtype=X_full.dtype, device=X_full.device)
+        self.exchange(X_full)
+        _ops.spmm(A.indptr, A.indices, A.data, X_full[: A.shape[1]], out, A.shape)
+        return out
+
+    def matmat_global(self, X_global):
+        """Convenience for tests: replicated dense X in, replicated Y out (numpy)."""
+        X_global = np.asarray(X_global, dtype=self.dtype)
+        full = self.new_full_matrix(X_global.shape[1])
+        lo, hi = self.my_cols
+        full[lo:hi] = to_device(X_global[lo:hi], dtype=self.dtype)
+        Y = self.spmm(full)
+        cols = [gather_vector(Y[:, j].contiguous(), self.row_plan, self.rank, self.group) for j in range(Y.shape[1])]
+        return np.stack(cols, axis=1) if cols else np.zeros((self.shape[0], 0), dtype=self.dtype)
+
     def dot_fused(self, x_full, out, w, dot_out):
         """y_local = A_local @ x and dot_out = all-reduced sum_i w_i y_i."""
         self.exchange(x_full)

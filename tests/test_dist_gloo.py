@@ -33,6 +33,10 @@ def _patch_ops_with_oracle():
         y[:] = torch.from_numpy(orc.spmv(indptr.numpy(), indices.numpy(), data.numpy(), x.numpy()[: shape[1]]))
         return y
 
+    def spmm(indptr, indices, data, X, Y, shape):
+        Y[:] = torch.from_numpy(orc.spmm(indptr.numpy(), indices.numpy(), data.numpy(), X.numpy()[: shape[1]]))
+        return Y
+
     def spmv_dot(indptr, indices, data, x, y, w, out, shape, plan):
         spmv(indptr, indices, data, x, y, shape)
         out[:] = torch.from_numpy(orc.dot(w.numpy(), y.numpy()))
@@ -65,6 +69,7 @@ def _patch_ops_with_oracle():
 
     _ops.spmv, _ops.spmv_dot, _ops.axpby, _ops.dot, _ops.cg_update_xr = spmv, spmv_dot, axpby, dot, cg_update_xr
     _ops.spgemm = spgemm
+    _ops.spmm = spmm
     csr_mod.csr_array._get_plan = lambda self: None
     csr_mod.runtime.require_cuda = lambda what: None
 
@@ -123,6 +128,33 @@ def _worker(rank, world, port, case, q):
             assert not A.row_plan.uniform or world == 1
             xs = rng.standard_normal(600)
             assert np.allclose(A.matvec_global(xs), S @ xs, rtol=1e-12, atol=1e-12)
+            out["ok"] = True
+        elif case == "spmm":
+            rng = np.random.default_rng(21)
+            for name in ("karate.mtx", "cage4.mtx"):
+                S = sio.mmread(mtx_path(name), spmatrix=False).tocsr().astype(np.float64)
+                X = rng.random((S.shape[1], 6))
+                for mode in ("allgather", "p2p"):
+                    os.environ["B2S_EXCHANGE"] = mode
+                    A = bd.dist_csr_array.from_global(S)
+                    assert np.allclose(A.matmat_global(X), S @ X, rtol=1e-13), (name, mode)
+            # banded: only halo ROWS of the dense operand travel; rectangular: x sharded by its own plan
+            os.environ["B2S_EXCHANGE"] = "auto"
+            S = sp.diags([1.0, 2.0, 3.0], [-37, 0, 37], shape=(4000, 4000), format="csr")
+            A = bd.dist_csr_array.from_global(S)
+            assert A.exchange_mode == "p2p"
+            X = rng.random((4000, 3))
+            assert np.allclose(A.matmat_global(X), S @ X, rtol=1e-13)
+            S = sp.random(130, 90, density=0.05, random_state=rng, format="csr", dtype=np.float64)
+            A = bd.dist_csr_array.from_global(S)
+            X = rng.random((90, 4))
+            assert np.allclose(A.matmat_global(X), S @ X, rtol=1e-12, atol=1e-13)
+            lo, hi = A.row_plan.rows(rank)
+            full = A.new_full_matrix(4)
+            clo, chi = A.my_cols
+            full[clo:chi] = torch.from_numpy(X[clo:chi])
+            Yl = A.spmm(full)
+            assert tuple(Yl.shape) == (hi - lo, 4) and np.allclose(Yl.numpy(), (S @ X)[lo:hi], rtol=1e-12, atol=1e-13)
             out["ok"] = True
         elif case == "spgemm":
             rng = np.random.default_rng(5)
@@ -193,6 +225,11 @@ def test_sharded_cg_gloo():
 
 def test_sharded_spgemm_gloo():
     _run(3, "spgemm")
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_spmm_gloo(world):
+    _run(world, "spmm")
 
 
 def test_row_block_plan_matches_oracle(oracle, golden):
