@@ -401,7 +401,7 @@ def run_gpu(args):
 
 
 def other_rows_of_the_path(torch, gallery, peak):
-    """The other hot-path rows of SURVEY 8 at N=1, so one bench line records them all (bounded: ~5 s).
+    """The other hot-path rows of SURVEY 8 at N=1, so one bench line records them all (bounded: ~6 s).
     CG: examples/pde.py -nx 4096 -ny 4096 -throughput -max_iter 300 (BASELINE config 3).
     SpGEMM: examples/spgemm_microbenchmark.py shape (banded, 11 nnz/row) at n = 1M."""
     from legate.sparse_b200 import linalg
@@ -441,6 +441,27 @@ def other_rows_of_the_path(torch, gallery, peak):
                                   "gflops": 2 * info["products"] / min(ts) / 1e9}
     except Exception as exc:  # pragma: no cover
         out["spgemm_error"] = str(exc)
+    try:
+        # SpMM: examples/dot_microbenchmark.py -op spmm -k 32 shape at n = 4M, fp64
+        n, k = 4_000_000, 32
+        B = gallery.banded(n, 11, np.float64)
+        X = torch.rand((n, k), dtype=torch.float64, device="cuda")
+        Y = torch.empty((n, k), dtype=torch.float64, device="cuda")
+        for _ in range(3):
+            B.dot(X, out=Y)
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(20)]
+        for s, e in ev:
+            s.record()
+            B.dot(X, out=Y)
+            e.record()
+        torch.cuda.synchronize()
+        t = float(np.median([s.elapsed_time(e) for s, e in ev])) * 1e-3
+        byts = B.nnz * 12 + 4 * (n + 1) + 2 * n * k * 8
+        out["spmm_banded4m_k32"] = {"us": t * 1e6, "gflops": 2 * B.nnz * k / t / 1e9, "algorithmic_bytes": byts,
+                                    "frac_of_hbm_peak": byts / t / 1e9 / peak}
+        del B, X, Y
+    except Exception as exc:  # pragma: no cover
+        out["spmm_error"] = str(exc)
     return out
 
 
