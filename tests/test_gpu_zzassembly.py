@@ -77,3 +77,21 @@ def test_wide_indices(monkeypatch):
     ref = sp.coo_array((v, (r, c)), shape=(300, 200)).tocsr()
     x = np.random.default_rng(0).random(200)
     assert np.allclose(A @ x, ref @ x)
+
+
+def test_spectral_norm_example():
+    """examples/spectral_norm.py (the reference's example of the same name) runs on the GPU and agrees with scipy."""
+    import os
+    import re
+    import subprocess
+    import sys
+
+    from conftest import ROOT
+
+    def run(*extra):
+        r = subprocess.run([sys.executable, "spectral_norm.py", "-n", "100", *extra], capture_output=True, text=True,
+                           timeout=300, cwd=os.path.join(ROOT, "examples"))
+        assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+        return float(re.search(r"estimate: ([0-9.]+)", r.stdout).group(1))
+
+    assert abs(run() - run("--package", "scipy")) < 1e-8
