@@ -505,6 +505,36 @@ class dist_csr_array:
             pc.close()
         self._peer = {}
 
+    def as_linear_operator(self):
+        """This shard as a `linalg.LinearOperator` on row-sharded vectors: matvec(x_local) -> y_local exchanges the
+        halo / all-gathers x, and the `allreduce` it carries makes the Krylov solvers of linalg (cgs, bicgstab, gmres,
+        eigsh; cg has its own fused loop, `dist.cg`) sum their inner products over the ranks.  No rmatvec: the
+        transpose of a row-sharded matrix is column-sharded."""
+        from .linalg import LinearOperator
+
+        shard = self
+
+        class _ShardOperator(LinearOperator):
+            def __init__(self):
+                assert shard.shape[0] == shard.shape[1], "row-sharded solvers need a square matrix"
+                lo, hi = shard.my_cols
+                super().__init__(shard.dtype, (shard.local.shape[0], hi - lo))
+                self.global_shape = shard.shape
+                self._full = {}
+
+            def _matvec(self, x, out=None):
+                key = numpy_dtype(x.dtype)
+                full = self._full.get(key)
+                if full is None:
+                    full = self._full[key] = shard.new_full_vector(key)
+                shard.local_view(full).copy_(x.reshape(-1))
+                return shard.dot(full, out=out)
+
+            def allreduce(self, t):
+                return shard.allreduce(t)
+
+        return _ShardOperator()
+
     def matvec_global(self, x_global):
         """Convenience for tests: replicated x in, replicated y out (numpy)."""
         full = self.scatter_vector(np.asarray(x_global, dtype=self.dtype))

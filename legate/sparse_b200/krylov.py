@@ -32,8 +32,32 @@ def _work_dtype(A, *arrays):
     return dt if dt in (np.dtype(np.float32), np.dtype(np.float64)) else np.dtype(np.float64)
 
 
+class _Space:
+    """Inner products of the vector space the operator acts on.  For a single-GPU operator these are the plain
+    `b2s_dot` / `b2s_nrm2` launches; an operator that carries an `allreduce` (a row shard of a distributed matrix,
+    dist.dist_csr_array.as_linear_operator) gets its partial sums all-reduced, so the same solver code runs with
+    every vector sharded by rows."""
+
+    def __init__(self, op):
+        self.reduce = getattr(op, "allreduce", None)
+
+    def dot(self, x, y):
+        d = _ops.dot(x, y)
+        return d if self.reduce is None else self.reduce(d)
+
+    def nrm2(self, x):
+        if self.reduce is None:
+            return _ops.nrm2(x)
+        return torch.sqrt(self.reduce(_ops.dot(x, x)))
+
+    def gram(self, basis, u):
+        """basis (j, n) @ u (n): the j projections of u, summed over the shards."""
+        h = basis @ u
+        return h if self.reduce is None else self.reduce(h)
+
+
 def _setup(A, b, x0, what):
-    """-> (operator, b on device (1-D), x on device (fresh copy), return-on-device flag)."""
+    """-> (operator, its _Space, b on device (1-D), x on device (fresh copy), return-on-device flag)."""
     from .linalg import make_linear_operator
 
     runtime.require_cuda(what)
@@ -46,7 +70,12 @@ def _setup(A, b, x0, what):
         x = torch.zeros(op.shape[1], dtype=torch_dtype(dt), device=bd.device)
     else:
         x = to_device(x0, dtype=dt, copy=True).reshape(-1)
-    return op, bd, x, on_device
+    return op, _Space(op), bd, x, on_device
+
+
+def _global_rows(op, b):
+    """System size for the default iteration cap (10 n): the global row count when b is a row shard."""
+    return int(getattr(op, "global_shape", (b.shape[0],))[0])
 
 
 def _finish(x, on_device):
@@ -57,16 +86,28 @@ def _residual(op, b, x):
     return b - op.matvec(x)
 
 
-def _confirm(op, b, x, tol):
+def _confirm(op, sp, b, x, tol):
     """The short recurrences carry r along and it drifts away from b - A x in finite precision (CGS squares the
     drift).  Before a solver reports convergence the residual is recomputed from x: -> (true r, true ||r|| < tol).
     When it is not there yet the caller restarts its recurrence from the true residual."""
     r = _residual(op, b, x)
-    return r, float(_ops.nrm2(r)[0]) < tol
+    return r, float(sp.nrm2(r)[0]) < tol
+
+
+def _project_out(sp, basis, u):
+    """u minus its components along the orthonormal rows of `basis`, by classical Gram-Schmidt applied TWICE, and
+    the summed coefficients.  One pass (what the reference's gmres / eigsh do, linalg.py:753-755, :1420) loses
+    orthogonality by a factor ||A v|| / ||u|| per step -- on a matrix like 10 I + E the Lanczos basis is garbage
+    after ~18 steps -- the second pass restores it to rounding level ("twice is enough")."""
+    h = sp.gram(basis, u)
+    u = u - h @ basis
+    h2 = sp.gram(basis, u)
+    return u - h2 @ basis, h + h2
 
 
 def _square_system(A, b):
-    assert len(A.shape) == 2 and A.shape[0] == A.shape[1] and b.shape[0] == A.shape[0]
+    rows = A.local.shape[0] if hasattr(A, "local") else A.shape[0]   # b of a row shard holds the shard's rows
+    assert len(A.shape) == 2 and A.shape[0] == A.shape[1] and b.shape[0] == rows
 
 
 def _plain_only(M, callback):
@@ -79,30 +120,30 @@ def cgs(A, b, x0=None, tol=1e-5, maxiter=None, M=None, callback=None, atol=None)
     """Conjugate Gradient Squared (Sonneveld); reference linalg.py:570-617.  Returns x."""
     _square_system(A, b)
     _plain_only(M, callback)
-    op, b, x, on_device = _setup(A, b, x0, "linalg.cgs")
-    maxiter = 10 * b.shape[0] if maxiter is None else maxiter
+    op, sp, b, x, on_device = _setup(A, b, x0, "linalg.cgs")
+    maxiter = 10 * _global_rows(op, b) if maxiter is None else maxiter
     r = _residual(op, b, x)
-    if float(_ops.nrm2(r)[0]) < tol:
+    if float(sp.nrm2(r)[0]) < tol:
         return _finish(x, on_device)
     shadow = r.clone()              # fixed shadow residual
     p = r.clone()
     u = r.clone()
-    rho = _ops.dot(r, shadow)
+    rho = sp.dot(r, shadow)
     for _ in range(maxiter):
         Ap = op.matvec(p)
-        alpha = rho / _ops.dot(Ap, shadow)
+        alpha = rho / sp.dot(Ap, shadow)
         q = torch.addcmul(u, alpha, Ap, value=-1)            # q = u - alpha A p
         uq = u + q
         x.addcmul_(alpha, uq)                                # x += alpha (u + q)
         r = torch.addcmul(r, alpha, op.matvec(uq), value=-1)
-        if float(_ops.nrm2(r)[0]) < tol:
-            r, done = _confirm(op, b, x, tol)
+        if float(sp.nrm2(r)[0]) < tol:
+            r, done = _confirm(op, sp, b, x, tol)
             if done:
                 break
             shadow, p, u = r.clone(), r.clone(), r.clone()
-            rho = _ops.dot(r, shadow)
+            rho = sp.dot(r, shadow)
             continue
-        rho_next = _ops.dot(r, shadow)
+        rho_next = sp.dot(r, shadow)
         beta = rho_next / rho
         rho = rho_next
         u = torch.addcmul(r, beta, q)                        # u = r + beta q
@@ -115,29 +156,29 @@ def bicg(A, b, x0=None, tol=1e-5, maxiter=None, M=None, callback=None, atol=None
     linalg.py:622-667.  Returns x."""
     _square_system(A, b)
     _plain_only(M, callback)
-    op, b, x, on_device = _setup(A, b, x0, "linalg.bicg")
-    maxiter = 10 * b.shape[0] if maxiter is None else maxiter
+    op, sp, b, x, on_device = _setup(A, b, x0, "linalg.bicg")
+    maxiter = 10 * _global_rows(op, b) if maxiter is None else maxiter
     r = _residual(op, b, x)
-    if float(_ops.nrm2(r)[0]) < tol:
+    if float(sp.nrm2(r)[0]) < tol:
         return _finish(x, on_device)
     rs = b.clone()                  # shadow residual b - A^T 0 (linalg.py:646-647)
     p = r.clone()
     ps = rs.clone()
-    rho = _ops.dot(rs, r)
+    rho = sp.dot(rs, r)
     for _ in range(maxiter):
         Ap = op.matvec(p)
-        alpha = rho / _ops.dot(ps, Ap)
+        alpha = rho / sp.dot(ps, Ap)
         x.addcmul_(alpha, p)
         r = torch.addcmul(r, alpha, Ap, value=-1)
         rs = torch.addcmul(rs, alpha, op.rmatvec(ps), value=-1)
-        if float(_ops.nrm2(r)[0]) < tol:
-            r, done = _confirm(op, b, x, tol)
+        if float(sp.nrm2(r)[0]) < tol:
+            r, done = _confirm(op, sp, b, x, tol)
             if done:
                 break
             rs, p, ps = r.clone(), r.clone(), r.clone()
-            rho = _ops.dot(rs, r)
+            rho = sp.dot(rs, r)
             continue
-        rho_next = _ops.dot(rs, r)
+        rho_next = sp.dot(rs, r)
         beta = rho_next / rho
         rho = rho_next
         p = torch.addcmul(r, beta, p)
@@ -149,41 +190,41 @@ def bicgstab(A, b, x0=None, tol=1e-5, maxiter=None, M=None, callback=None, atol=
     """BiCGSTAB (van der Vorst) with the reference's restart safeguard: when r.rhat collapses below 1e-8 the
     shadow vector and the search direction are reset to the current residual (linalg.py:798-838).  Returns x."""
     _plain_only(M, callback)
-    op, b, x, on_device = _setup(A, b, x0, "linalg.bicgstab")
-    maxiter = 10 * b.shape[0] if maxiter is None else maxiter
+    op, sp, b, x, on_device = _setup(A, b, x0, "linalg.bicgstab")
+    maxiter = 10 * _global_rows(op, b) if maxiter is None else maxiter
     r = _residual(op, b, x)
-    if float(_ops.nrm2(r)[0]) < tol:
+    if float(sp.nrm2(r)[0]) < tol:
         return _finish(x, on_device)
     shadow = r.clone()
     p = r.clone()
-    rho = _ops.dot(r, shadow)
+    rho = sp.dot(r, shadow)
     for _ in range(maxiter):
         Ap = op.matvec(p)
-        alpha = rho / _ops.dot(Ap, shadow)
+        alpha = rho / sp.dot(Ap, shadow)
         s = torch.addcmul(r, alpha, Ap, value=-1)
-        if float(_ops.nrm2(s)[0]) < tol:
+        if float(sp.nrm2(s)[0]) < tol:
             x.addcmul_(alpha, p)
-            r, done = _confirm(op, b, x, tol)
+            r, done = _confirm(op, sp, b, x, tol)
             if done:
                 break
             shadow, p = r.clone(), r.clone()
-            rho = _ops.dot(r, shadow)
+            rho = sp.dot(r, shadow)
             continue
         As = op.matvec(s)
-        omega = _ops.dot(As, s) / _ops.dot(As, As)
+        omega = sp.dot(As, s) / sp.dot(As, As)
         x.addcmul_(alpha, p).addcmul_(omega, s)
         r = torch.addcmul(s, omega, As, value=-1)
-        rho_next = _ops.dot(r, shadow)
-        rnorm, rho_host = torch.cat([_ops.nrm2(r), rho_next]).tolist()   # one host round trip
+        rho_next = sp.dot(r, shadow)
+        rnorm, rho_host = torch.cat([sp.nrm2(r), rho_next]).tolist()   # one host round trip
         if rnorm < tol:
-            r, done = _confirm(op, b, x, tol)
+            r, done = _confirm(op, sp, b, x, tol)
             if done:
                 break
             rho_host = 0.0                      # not there yet: restart from the true residual
         if abs(rho_host) < 1e-8:
             shadow = r.clone()
             p = r.clone()
-            rho = _ops.dot(r, shadow)
+            rho = sp.dot(r, shadow)
             continue
         beta = (alpha / omega) * (rho_next / rho)
         rho = rho_next
@@ -199,15 +240,15 @@ def gmres(A, b, x0=None, tol=1e-5, restart=None, maxiter=None, M=None, callback=
     from .linalg import IdentityOperator, make_linear_operator
 
     assert len(A.shape) == 2 and A.shape[0] == A.shape[1]
-    op, b, x, on_device = _setup(A, b, x0, "linalg.gmres")
+    op, sp, b, x, on_device = _setup(A, b, x0, "linalg.gmres")
     n = op.shape[0]
     M = IdentityOperator(op.shape, dtype=op.dtype) if M is None else make_linear_operator(M)
-    b_norm = float(_ops.nrm2(b)[0])
+    b_norm = float(sp.nrm2(b)[0])
     if b_norm == 0:
         return _finish(b, on_device), 0
     atol = tol * b_norm if atol is None else max(float(atol), tol * b_norm)
-    maxiter = 10 * n if maxiter is None else maxiter
-    restart = min(20 if restart is None else restart, n)
+    maxiter = 10 * _global_rows(op, b) if maxiter is None else maxiter
+    restart = min(20 if restart is None else restart, _global_rows(op, b))
     if callback_type is None:
         callback_type = "pr_norm"
     if callback_type not in ("x", "pr_norm"):
@@ -221,7 +262,7 @@ def gmres(A, b, x0=None, tol=1e-5, restart=None, maxiter=None, M=None, callback=
     while True:
         mx = M.matvec(x)
         r = _residual(op, b, mx)
-        r_norm = float(_ops.nrm2(r)[0])
+        r_norm = float(sp.nrm2(r)[0])
         if callback_type == "x":
             callback(_finish(mx, on_device))
         elif callback_type == "pr_norm" and iters > 0:
@@ -232,11 +273,9 @@ def gmres(A, b, x0=None, tol=1e-5, restart=None, maxiter=None, M=None, callback=
         H.zero_()
         for j in range(restart):
             u = op.matvec(M.matvec(V[j]))
-            basis = V[: j + 1]
-            h = basis @ u                       # classical Gram-Schmidt against the basis so far
-            u = u - h @ basis
+            u, h = _project_out(sp, V[: j + 1], u)
             H[: j + 1, j] = h
-            unorm = _ops.nrm2(u)
+            unorm = sp.nrm2(u)
             H[j + 1, j] = unorm[0]
             if j + 1 < restart:
                 V[j + 1] = u / unorm
@@ -272,6 +311,7 @@ def lsqr(A, b, damp=0.0, atol=1e-6, btol=1e-6, conlim=1e8, iter_lim=None, show=F
 
     runtime.require_cuda("linalg.lsqr")
     op = make_linear_operator(A)
+    sp = _Space(op)
     m, n = op.shape
     on_device = is_device_array(b) and b.is_cuda
     dt = _work_dtype(op, b, x0)
@@ -287,18 +327,18 @@ def lsqr(A, b, damp=0.0, atol=1e-6, btol=1e-6, conlim=1e8, iter_lim=None, show=F
     cs2, sn2 = -1.0, 0.0
     itn = istop = 0
 
-    bnorm = float(_ops.nrm2(u)[0])
+    bnorm = float(sp.nrm2(u)[0])
     if x0 is None:
         x = torch.zeros(n, dtype=tdt, device=u.device)
         beta = bnorm
     else:
         x = to_device(x0, dtype=dt, copy=True).reshape(-1)
         u = u - op.matvec(x)
-        beta = float(_ops.nrm2(u)[0])
+        beta = float(sp.nrm2(u)[0])
     if beta > 0:
         u = u / beta
         v = op.rmatvec(u)
-        alfa = float(_ops.nrm2(v)[0])
+        alfa = float(sp.nrm2(v)[0])
     else:
         v = x.clone()
         alfa = 0.0
@@ -315,12 +355,12 @@ def lsqr(A, b, damp=0.0, atol=1e-6, btol=1e-6, conlim=1e8, iter_lim=None, show=F
         itn += 1
         # next step of the bidiagonalisation: beta u = A v - alfa u ; alfa v = A^T u - beta v
         u = op.matvec(v) - alfa * u
-        beta = float(_ops.nrm2(u)[0])
+        beta = float(sp.nrm2(u)[0])
         if beta > 0:
             u = u / beta
             anorm = np.sqrt(anorm * anorm + alfa * alfa + beta * beta + dampsq)
             v = op.rmatvec(u) - beta * v
-            alfa = float(_ops.nrm2(v)[0])
+            alfa = float(sp.nrm2(v)[0])
             if alfa > 0:
                 v = v / alfa
         # eliminate the damping parameter, then the sub-diagonal of the bidiagonal
@@ -341,7 +381,7 @@ def lsqr(A, b, damp=0.0, atol=1e-6, btol=1e-6, conlim=1e8, iter_lim=None, show=F
         dk = w / rho
         x = x + (phi / rho) * w
         w = v - (theta / rho) * w
-        ddnorm += float(_ops.dot(dk, dk)[0])
+        ddnorm += float(sp.dot(dk, dk)[0])
         if calc_var:
             var = var + dk * dk
         # norm estimates (rotation on the right removes the super-diagonal of the upper bidiagonal)
@@ -394,14 +434,13 @@ def lsqr(A, b, damp=0.0, atol=1e-6, btol=1e-6, conlim=1e8, iter_lim=None, show=F
             float(arnorm), float(xnorm), _finish(var, on_device))
 
 
-def _lanczos(op, V, u, alpha, beta, start, end):
+def _lanczos(op, sp, V, u, alpha, beta, start, end):
     """Lanczos steps start..end-1 with full re-orthogonalisation against the rows of V (linalg.py:1416-1424)."""
     for i in range(start, end):
         u = op.matvec(V[i])
-        alpha[i] = _ops.dot(V[i], u)[0]
-        basis = V[: i + 1]
-        u = u - (basis @ u) @ basis
-        bnorm = _ops.nrm2(u)
+        alpha[i] = sp.dot(V[i], u)[0]
+        u, _ = _project_out(sp, V[: i + 1], u)
+        bnorm = sp.nrm2(u)
         beta[i] = bnorm[0]
         if i >= end - 1:
             break
@@ -429,31 +468,33 @@ def eigsh(a, k=6, *, which="LM", ncv=None, maxiter=None, tol=0, return_eigenvect
     from .linalg import make_linear_operator
 
     runtime.require_cuda("linalg.eigsh")
-    n = a.shape[0]
     if len(a.shape) != 2 or a.shape[0] != a.shape[1]:
         raise ValueError("expected square matrix (shape: {})".format(a.shape))
+    op = make_linear_operator(a)
+    sp = _Space(op)
+    n = op.shape[0]                                            # length of this process's vectors
+    n_glob = int(getattr(op, "global_shape", op.shape)[0])     # size of the eigenproblem (row-sharded operators)
     dt = np.dtype(a.dtype)
     if dt.char not in "fd":
         raise TypeError("unsupprted dtype (actual: {})".format(a.dtype))
     if k <= 0:
         raise ValueError("k must be greater than 0 (actual: {})".format(k))
-    if k >= n:
+    if k >= n_glob:
         raise ValueError("k must be smaller than n (actual: {})".format(k))
     if which not in ("LM", "LA"):
         raise ValueError("which must be 'LM' or 'LA' (actual: {})".format(which))
-    ncv = min(max(2 * k, k + 32), n - 1) if ncv is None else min(max(ncv, k + 2), n - 1)
-    maxiter = 10 * n if maxiter is None else maxiter
+    ncv = min(max(2 * k, k + 32), n_glob - 1) if ncv is None else min(max(ncv, k + 2), n_glob - 1)
+    maxiter = 10 * n_glob if maxiter is None else maxiter
     if tol == 0:
         tol = float(np.finfo(dt).eps)
-    op = make_linear_operator(a)
     tdt = torch_dtype(dt)
     dev = runtime.device
     alpha = torch.zeros(ncv, dtype=tdt, device=dev)
     beta = torch.zeros(ncv, dtype=tdt, device=dev)
     V = torch.empty((ncv, n), dtype=tdt, device=dev)
     u = to_device(np.random.random(n).astype(dt))
-    V[0] = u / _ops.nrm2(u)
-    u = _lanczos(op, V, u, alpha, beta, 0, ncv)
+    V[0] = u / sp.nrm2(u)
+    u = _lanczos(op, sp, V, u, alpha, beta, 0, ncv)
     spent = ncv
     w, s, beta_last = _ritz(alpha, beta, None, k, which)
     s_dev = torch.from_numpy(np.ascontiguousarray(s.T)).to(device=dev, dtype=tdt)    # (k, ncv)
@@ -466,16 +507,16 @@ def eigsh(a, k=6, *, which="LM", ncv=None, maxiter=None, tol=0, return_eigenvect
         alpha[:k] = torch.from_numpy(w).to(device=dev, dtype=tdt)
         V[:k] = x
         basis = V[:k]
-        u = u - (basis @ u) @ basis
-        V[k] = u / _ops.nrm2(u)
+        u, _ = _project_out(sp, basis, u)
+        V[k] = u / sp.nrm2(u)
         u = op.matvec(V[k])
-        alpha[k] = _ops.dot(V[k], u)[0]
+        alpha[k] = sp.dot(V[k], u)[0]
         u = u - alpha[k] * V[k]
         u = u - torch.from_numpy(beta_k).to(device=dev, dtype=tdt) @ basis
-        bnorm = _ops.nrm2(u)
+        bnorm = sp.nrm2(u)
         beta[k] = bnorm[0]
         V[k + 1] = u / bnorm
-        u = _lanczos(op, V, u, alpha, beta, k + 1, ncv)
+        u = _lanczos(op, sp, V, u, alpha, beta, k + 1, ncv)
         spent += ncv - k
         w, s, beta_last = _ritz(alpha, beta, beta_k, k, which)
         s_dev = torch.from_numpy(np.ascontiguousarray(s.T)).to(device=dev, dtype=tdt)

@@ -171,6 +171,8 @@ class IdentityOperator(LinearOperator):
 def make_linear_operator(A):
     if isinstance(A, LinearOperator):
         return A
+    if hasattr(A, "as_linear_operator"):  # a row shard of a distributed matrix (dist.dist_csr_array)
+        return A.as_linear_operator()
     return _SparseMatrixLinearOperator(A)
 
 

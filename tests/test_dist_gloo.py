@@ -55,6 +55,9 @@ def _patch_ops_with_oracle():
             return out
         return r
 
+    def nrm2(x, out=None):
+        return torch.from_numpy(orc.nrm2(x.numpy()))
+
     def cg_update_xr(x, r, p, q, rho, pq, rr_out):
         axpby(x, p, rho, pq, True, False)
         axpby(r, q, rho, pq, True, True)
@@ -70,6 +73,7 @@ def _patch_ops_with_oracle():
     _ops.spmv, _ops.spmv_dot, _ops.axpby, _ops.dot, _ops.cg_update_xr = spmv, spmv_dot, axpby, dot, cg_update_xr
     _ops.spgemm = spgemm
     _ops.spmm = spmm
+    _ops.nrm2 = nrm2
     csr_mod.csr_array._get_plan = lambda self: None
     csr_mod.runtime.require_cuda = lambda what: None
 
@@ -156,6 +160,51 @@ def _worker(rank, world, port, case, q):
             Yl = A.spmm(full)
             assert tuple(Yl.shape) == (hi - lo, 4) and np.allclose(Yl.numpy(), (S @ X)[lo:hi], rtol=1e-12, atol=1e-13)
             out["ok"] = True
+        elif case == "krylov":
+            import scipy.sparse.linalg as spla
+            from legate.sparse_b200 import linalg
+
+            # non-symmetric, diagonally dominant system sharded by rows: every vector of the solvers is a shard,
+            # inner products are all-reduced (krylov._Space), the operator exchanges x per product
+            rng = np.random.default_rng(33)
+            n = 240
+            S = sp.csr_array(sp.random(n, n, density=0.05, random_state=rng, format="csr", dtype=np.float64)
+                             + 10.0 * sp.eye(n))
+            xs = rng.standard_normal(n)
+            y = S @ xs
+            for mode in ("allgather", "p2p"):
+                os.environ["B2S_EXCHANGE"] = mode
+                A = bd.dist_csr_array.from_global(S)
+                lo, hi = A.row_plan.rows(rank)
+                bl = torch.from_numpy(y[lo:hi].copy())
+                for solver in (linalg.cgs, linalg.bicgstab):
+                    xl = solver(A, bl, tol=1e-9)
+                    xg = bd.gather_vector(xl if isinstance(xl, torch.Tensor) else torch.from_numpy(xl), A.row_plan, rank)
+                    assert np.linalg.norm(S @ xg - y) < 1e-8, (solver.__name__, mode)
+                xl, info = linalg.gmres(A, bl, tol=1e-10, restart=25)
+                xg = bd.gather_vector(xl if isinstance(xl, torch.Tensor) else torch.from_numpy(xl), A.row_plan, rank)
+                assert info == 0 and np.linalg.norm(S @ xg - y) <= 1.01e-10 * np.linalg.norm(y)
+                ref = spla.gmres(S, y, rtol=1e-10, atol=0.0, restart=25)[0]
+                assert np.allclose(xg, ref, atol=1e-7)
+                for solver in (linalg.bicg, linalg.lsqr):      # need A^T: not available on a row shard
+                    try:
+                        solver(A, bl)
+                        raise AssertionError("expected NotImplementedError")
+                    except NotImplementedError:
+                        pass
+            # symmetric eigenproblem, sharded Lanczos
+            Sym = sp.csr_array(0.5 * (S + S.T))
+            A = bd.dist_csr_array.from_global(Sym)
+            lo, hi = A.row_plan.rows(rank)
+            np.random.seed(5)
+            w, Vl = linalg.eigsh(A, k=4, tol=1e-10)
+            exact = np.linalg.eigvalsh(Sym.toarray())
+            assert np.allclose(w, np.sort(exact[np.argsort(np.abs(exact))[-4:]]), atol=1e-8)
+            assert Vl.shape == (hi - lo, 4)
+            for i in range(4):
+                vg = bd.gather_vector(torch.from_numpy(np.ascontiguousarray(Vl[:, i])), A.row_plan, rank)
+                assert np.allclose(Sym @ vg, w[i] * vg, atol=1e-6)
+            out["ok"] = True
         elif case == "spgemm":
             rng = np.random.default_rng(5)
             SA = sp.random(130, 90, density=0.05, random_state=rng, format="csr", dtype=np.float64)
@@ -230,6 +279,10 @@ def test_sharded_spgemm_gloo():
 @pytest.mark.parametrize("world", [2, 3])
 def test_sharded_spmm_gloo(world):
     _run(world, "spmm")
+
+
+def test_sharded_krylov_gloo():
+    _run(2, "krylov")
 
 
 def test_row_block_plan_matches_oracle(oracle, golden):
