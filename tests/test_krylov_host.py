@@ -2,7 +2,7 @@
 applies the matrix with the CPU oracle and the reductions are the oracle's dot / nrm2 (tests only), so what is
 exercised here is the recurrences, the stopping rules and the return conventions, against scipy on the seeded
 systems of the reference tests (tests/integration/test_cgs_solve.py, test_bicg_solve.py, test_gmres_solve.py,
-test_lsqr_solve.py, test_eigsh.py).  The same code drives the CUDA kernels in tests/test_gpu_zkrylov.py."""
+test_lsqr_solve.py, test_eigsh.py).  The same code drives the CUDA kernels in tests/test_gpu_zy_krylov.py."""
 import numpy as np
 import pytest
 import scipy.sparse as sp
