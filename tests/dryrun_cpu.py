@@ -8,6 +8,7 @@ GPU minutes are spent on it; it says nothing about the kernels.
 import os
 import sys
 
+import numpy as np
 import pytest
 import torch
 
@@ -64,12 +65,43 @@ def install():
     def nrm2(x, out=None):
         return torch.from_numpy(orc.nrm2(x.numpy()))
 
+    def axpby(y, x, a, b, isalpha=True, negate=False):
+        yy = y.numpy().copy()
+        orc.axpby(yy, x.numpy(), a.numpy(), b.numpy(), isalpha=isalpha, negate=negate)
+        y[:] = torch.from_numpy(yy)
+        return y
+
+    def spmv_dot(indptr, indices, data, x, y, w, out, shape, plan):
+        spmv(indptr, indices, data, x, y, shape)
+        out[:] = torch.from_numpy(orc.dot(w.numpy(), y.numpy()))
+        return y
+
+    def cg_update_xr(x, r, p, q, rho, pq, rr_out):
+        axpby(x, p, rho, pq, True, False)
+        axpby(r, q, rho, pq, True, True)
+        rr_out[:] = torch.from_numpy(orc.dot(r.numpy(), r.numpy()))
+        return rr_out
+
+    def csr_diagonal(indptr, indices, data, nrows):
+        import scipy.sparse as sp
+
+        n = int(indices.max()) + 1 if indices.numel() else 0
+        S = sp.csr_array((data.numpy(), indices.numpy(), indptr.numpy()), shape=(nrows, max(n, nrows)))
+        return torch.from_numpy(np.ascontiguousarray(S.diagonal()[:nrows]))
+
+    def spgemm(a_ptr, a_idx, a_val, b_ptr, b_idx, b_val, shape_a, shape_b):
+        cp, ci, cv = orc.spgemm((a_ptr.numpy(), a_idx.numpy(), a_val.numpy()), (b_ptr.numpy(), b_idx.numpy(), b_val.numpy()),
+                                shape_a, shape_b, sort_rows=True)
+        return (torch.from_numpy(cp), torch.from_numpy(ci.astype(np.int32)), torch.from_numpy(cv),
+                {"nnz": int(cp[-1]), "products": 0, "dense_rows": 0})
+
     _ops.spmv_plan, _ops.spmv, _ops.spmm, _ops.dot, _ops.nrm2 = spmv_plan, spmv, spmm, dot, nrm2
+    _ops.axpby, _ops.spmv_dot, _ops.cg_update_xr, _ops.csr_diagonal, _ops.spgemm = (axpby, spmv_dot, cg_update_xr,
+                                                                                      csr_diagonal, spgemm)
     runtime.require_cuda = lambda what: None
-    os.environ["B2S_CG_FUSED"] = "0"
     os.environ["B2S_CG_GRAPH"] = "0"
 
 
 if __name__ == "__main__":
     install()
-    sys.exit(pytest.main(["-m", "gpu", "-q", "-x", "-p", "no:cacheprovider"] + sys.argv[1:]))
+    sys.exit(pytest.main(["-m", "gpu", "-q", "-p", "no:cacheprovider"] + sys.argv[1:]))
