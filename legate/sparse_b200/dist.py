@@ -215,6 +215,57 @@ class dist_csr_array:
                           shape=(hi - lo, S.shape[1]))
         return cls(local, S.shape, rank=rank, nranks=nranks, row_plan=plan)
 
+    @classmethod
+    def from_triplets(cls, data, row, col, shape, rank=None, nranks=None, group=None):
+        """Assemble the row shards from COO triplets scattered over the ranks in any order (each rank passes the
+        triplets it happens to hold, global row / column ids).  The reference does this with a distributed
+        sort-by-key over NCCL followed by counts -> pos (sparse/coo.py:233-347, src/sparse/sort/sort.cu,
+        base.py:30-48).  Here the splitters are known -- the row blocks of the partition -- so one exchange
+        routes every triplet to the owner of its row (counts all-gathered, then grouped point-to-point
+        send/recv of the three arrays) and each rank sorts what it received by (row, col) on its own device
+        (`coo_array.tocsr`).  Duplicates are assumed absent, as in the reference."""
+        from .coo import coo_array
+
+        r, w = world()
+        rank = r if rank is None else rank
+        nranks = w if nranks is None else nranks
+        shape = tuple(int(s) for s in shape)
+        plan = RowBlockPlan(shape[0], nranks)
+        dev = runtime.device
+        vals = to_device(data).reshape(-1)
+        rows = to_device(row).reshape(-1).to(torch.int64)
+        cols = to_device(col).reshape(-1).to(torch.int64)
+        dest = torch.clamp(rows // max(plan.tile, 1), max=nranks - 1)
+        order = torch.sort(dest, stable=True).indices
+        vals, rows, cols = vals[order], rows[order], cols[order]
+        send_counts = torch.bincount(dest, minlength=nranks).to(torch.int64)
+        if nranks > 1:
+            all_counts = torch.empty(nranks * nranks, dtype=torch.int64, device=dev)
+            dist.all_gather_into_tensor(all_counts, send_counts, group=group)
+            all_counts = all_counts.reshape(nranks, nranks).cpu()      # [sender, receiver]
+            recv_counts = [int(all_counts[q, rank]) for q in range(nranks)]
+            send_off = np.concatenate([[0], np.cumsum(send_counts.cpu().numpy())])
+            pieces = {}
+            for name, arr in (("vals", vals), ("rows", rows), ("cols", cols)):
+                recv = [torch.empty(c, dtype=arr.dtype, device=dev) for c in recv_counts]
+                ops = []
+                for q in range(nranks):
+                    if q == rank:
+                        recv[q] = arr[send_off[q]:send_off[q + 1]]
+                        continue
+                    if recv_counts[q]:
+                        ops.append(dist.P2POp(dist.irecv, recv[q], q, group=group))
+                    if send_off[q + 1] > send_off[q]:
+                        ops.append(dist.P2POp(dist.isend, arr[send_off[q]:send_off[q + 1]].contiguous(), q, group=group))
+                if ops:
+                    for req in dist.batch_isend_irecv(ops):
+                        req.wait()
+                pieces[name] = torch.cat(recv)
+            vals, rows, cols = pieces["vals"], pieces["rows"], pieces["cols"]
+        lo, hi = plan.rows(rank)
+        local = coo_array((vals, (rows - lo, cols)), shape=(hi - lo, shape[1])).tocsr()
+        return cls(local, shape, rank=rank, nranks=nranks, group=group, row_plan=plan)
+
     # -- exchange plan --------------------------------------------------------------------------------
     def _build_exchange(self):
         """Column window of this shard + who sends what to whom."""

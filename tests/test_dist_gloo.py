@@ -205,6 +205,29 @@ def _worker(rank, world, port, case, q):
                 vg = bd.gather_vector(torch.from_numpy(np.ascontiguousarray(Vl[:, i])), A.row_plan, rank)
                 assert np.allclose(Sym @ vg, w[i] * vg, atol=1e-6)
             out["ok"] = True
+        elif case == "assemble":
+            # triplets dealt to the ranks at random -> row shards identical to slicing the global CSR
+            rng = np.random.default_rng(77)
+            for (m, n, nnz) in ((500, 300, 4000), (7, 900, 600), (901, 40, 3000)):
+                flat = np.random.default_rng(m).choice(m * n, size=nnz, replace=False)      # same on every rank
+                r, c = flat // n, flat % n
+                v = np.random.default_rng(n).standard_normal(nnz)
+                S = sp.coo_array((v, (r, c)), shape=(m, n)).tocsr()
+                S.sort_indices()
+                holder = np.random.default_rng(nnz).integers(0, world, nnz)              # who holds which triplet
+                mine = holder == rank
+                if m == 7:            # the last rank holds nothing: rank 0 also passes what it would have held
+                    mine = np.zeros(nnz, dtype=bool) if rank == world - 1 else (mine | ((holder == world - 1) & (rank == 0)))
+                A = bd.dist_csr_array.from_triplets(torch.from_numpy(v[mine]), torch.from_numpy(r[mine]),
+                                                    torch.from_numpy(c[mine]), (m, n))
+                lo, hi = A.row_plan.rows(rank)
+                loc = A.local.to_scipy_sparse_csr()
+                assert np.array_equal(loc.indptr, S.indptr[lo : hi + 1] - S.indptr[lo]), (m, n)
+                assert np.array_equal(loc.indices, S.indices[S.indptr[lo] : S.indptr[hi]])
+                assert np.array_equal(loc.data, S.data[S.indptr[lo] : S.indptr[hi]])
+                x = np.random.default_rng(1).random(n)
+                assert np.allclose(A.matvec_global(x), S @ x, rtol=1e-12, atol=1e-12)
+            out["ok"] = True
         elif case == "spgemm":
             rng = np.random.default_rng(5)
             SA = sp.random(130, 90, density=0.05, random_state=rng, format="csr", dtype=np.float64)
@@ -283,6 +306,11 @@ def test_sharded_spmm_gloo(world):
 
 def test_sharded_krylov_gloo():
     _run(2, "krylov")
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_assembly_from_scattered_triplets_gloo(world):
+    _run(world, "assemble")
 
 
 def test_row_block_plan_matches_oracle(oracle, golden):
