@@ -113,6 +113,26 @@ def test_constructors_match_scipy():
         sparse.csr_array((S.data, S.indices, S.indptr))          # shape required (reference csr.py:171)
 
 
+@pytest.mark.parametrize("name", MTX_FILES)
+def test_conversions_on_the_reference_fixtures(name):
+    """reference tests/integration/test_csr_conversion.py:26-83 and test_csr_misc.py:39-55 (format logic only)."""
+    s = sio.mmread(mtx_path(name), spmatrix=False)
+    coo = sparse.io.mmread(mtx_path(name))
+    arr = coo.tocsr()
+    dense = s.toarray()
+    assert np.array_equal(sparse.csr_array(coo.todense()).todense(), dense)                 # from dense
+    assert np.array_equal(arr.todense(), arr.tocoo().todense())                             # to COO
+    c = arr.tocoo()
+    assert np.array_equal(sparse.csr_array((c.data, (c.row, c.col)), dtype=c.dtype, shape=c.shape).todense(), dense)
+    assert np.array_equal(sparse.csr_array(sp.csr_array(dense).astype(np.float64)).todense(), dense)   # from scipy
+    assert np.array_equal(arr.conj(copy=False).todense(), s.tocsr().conj(copy=False).toarray())
+    assert np.array_equal(arr.to_scipy_sparse_csr().toarray(), dense)
+    for dt in (np.float32, np.float64):
+        assert np.array_equal(arr.astype(dt).todense(), s.tocsr().astype(dt).toarray())
+    assert np.array_equal(arr.T.todense(), np.ascontiguousarray(dense.T))                   # transpose
+    assert np.array_equal(np.asarray(arr.diagonal(k=0)), s.tocsr().diagonal(k=0))           # diagonal
+
+
 def test_diags_and_eye_match_scipy():
     n = 50
     for nnz_per_row in (1, 5, 11):
