@@ -137,3 +137,29 @@ class coo_array:
         return coo_array((self._vals, (self._j, self._i)), shape=(self.shape[1], self.shape[0]))
 
     T = property(transpose)
+
+    # products go through CSR, as in the reference (coo.py:467-477: `self.tocsr() @ other`)
+    def dot(self, other, out=None):
+        return self.tocsr().dot(other, out=out)
+
+    def __matmul__(self, other):
+        return self.dot(other)
+
+    def __rmatmul__(self, other):
+        return self.tocsr().__rmatmul__(other)
+
+    def __mul__(self, other):
+        if not np.isscalar(other):
+            raise NotImplementedError
+        if self._dev is not None:
+            return coo_array((self._dev[0] * other, (self._dev[1], self._dev[2])), shape=self.shape)
+        return coo_array((self._vals * other, (self._i, self._j)), shape=self.shape)
+
+    __rmul__ = __mul__
+
+    def asformat(self, format, copy=False):
+        if format in (None, "coo"):
+            return self
+        if format == "csr":
+            return self.tocsr()
+        raise NotImplementedError(f"format {format!r}")

@@ -95,3 +95,19 @@ def test_spectral_norm_example():
         return float(re.search(r"estimate: ([0-9.]+)", r.stdout).group(1))
 
     assert abs(run() - run("--package", "scipy")) < 1e-8
+
+
+@pytest.mark.parametrize("name", ["test.mtx", "cage4.mtx", "karate.mtx"])
+def test_coo_products_go_through_csr(name):
+    """reference tests/integration/test_coo.py:52-69 (coo @ dense, coo * scalar)."""
+    import scipy.io as sio
+
+    from conftest import mtx_path
+
+    arr = sparse.io.mmread(mtx_path(name)).tocoo()
+    s = sio.mmread(mtx_path(name), spmatrix=False).tocoo()
+    assert np.allclose(arr @ arr.todense(), s @ s.toarray())
+    assert np.allclose((arr * 3.0).todense(), (s * 3.0).toarray())
+    x = np.random.default_rng(0).random(arr.shape[1])
+    assert np.allclose(arr @ x, s @ x)
+    assert np.array_equal(arr.T.todense(), s.T.toarray())
