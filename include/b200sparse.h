@@ -71,7 +71,8 @@ int64_t     b2s_ws_bytes(void);
  *       (streaming vs deep-gather) and kernel flavour, and returns a small HOST handle.
  *       syncs the stream once (the reference's partition tasks also block, fast_image_range.cu:27-54).
  *   b2s_spmv_plan_destroy: frees the host handle (never the device buffer).
- *   b2s_spmv_plan_info  : out[0]=tile config id, out[1]=bit0 row-group kernel, bit1 uniform-row fast path, bit2 scattered, out[2]=tiles,
+ *   b2s_spmv_plan_info  : out[0]=tile config id, out[1]=bit0 row-group kernel, bit1 uniform-row path, bit2 scattered, bit3 short-row
+ *                         (one lane per row) path, bit4 TMA tile kind, out[2]=tiles,
  *                         out[3]=1000*lines-per-warp statistic. */
 int64_t     b2s_spmv_plan_tiles(int vt, int64_t nrows, int64_t nnz);
 int64_t     b2s_spmv_plan_bytes(int vt, int64_t nrows, int64_t nnz);
@@ -103,18 +104,48 @@ int         b2s_spmv_csr_tiles(int vt, int it, int pt, int64_t nrows, int64_t nc
                                const void* x, void* y, const void* plan,
                                int64_t tile_lo, int64_t tile_hi, void* stream);
 
-/* SpMV fused with the arrival of the x halo that peer GPUs are pushing (b2s_peer_halo_push): ONE kernel does
- * the compute and consumes the collective.  Tiles are visited range by range (ranges_host = nranges x
- * {tile_lo, tile_hi}); the first n_free ranges read only locally valid x; before its first other tile each
- * CTA polls the nflags arrival flags (addresses in this GPU's memory, written remotely over NVLink) until
- * they reach `expect`, so the exchange latency hides behind the interior tiles.  Bounded spin: on timeout
- * *error_flag_dev = 1.  Replaces Legion's implicit halo copy + cusparseSpMV pair (sparse/csr.py:928-968). */
-int         b2s_spmv_csr_halo(int vt, int it, int pt, int64_t nrows, int64_t ncols, int64_t nnz,
-                              const void* indptr, const void* indices, const void* vals,
-                              const void* x, void* y, const void* plan, int nranges,
-                              const int64_t* ranges_host, int n_free, int nflags,
-                              void* const* flag_ptrs_host, uint64_t expect, void* error_flag_dev,
-                              void* stream);
+/* SpMV with the x exchange FUSED into the kernel: one launch (a) pushes slices of the local x into neighbour GPUs'
+ * x buffers over NVLink (remote stores by the first n_sends CTAs while all others already compute), (b) waits --
+ * only before the first tile that reads remote columns -- for the slices the neighbours push here, (c)
+ * acknowledges the previous exchange and (d) advances a device-side epoch, so the step replays from a CUDA graph
+ * with no host-numbered arguments.  Replaces Legion's implicit halo copy + cusparseSpMV pair
+ * (sparse/csr.py:928-968, partition.py:139-208).  All pointers in the descriptor are DEVICE addresses (local,
+ * or peer-mapped through b2s_ipc_open where marked remote); the struct itself is read on the host.
+ *   ranges      : tiles are visited range by range, ranges[2i], ranges[2i+1] = [tile_lo, tile_hi); the first
+ *                 n_free ranges read only locally valid x
+ *   flag[i]     : local arrival words (PeerHeader fuse_flag[src]); polled until >= epoch (bounded; *error = 1 on timeout)
+ *   send_*[i]   : CTA i copies send_count[i] elements send_src[i] (local) -> send_dst[i] (remote) once
+ *                 *send_ack[i] (local, written by that neighbour) >= epoch-1, then stores epoch to send_flag[i] (remote)
+ *   ack_out[i]  : remote words that receive epoch-1 at kernel start (one per GPU that pushes into this one)
+ *   epoch       : *epoch_ctr + epoch_add (device counter; the last CTA stores the epoch back if epoch_bump, using
+ *                 *ticket for the election) or `expect` when epoch_ctr is NULL
+ *   accumulate  : y += A x instead of y = A x (column-blocked shards; not with the fused dot)
+ * w / dot_out / ws: as b2s_spmv_csr_dot, or all NULL. */
+typedef struct b2s_fuse_desc {
+  int32_t nranges, n_free;
+  int64_t ranges[12];
+  int32_t n_flags, n_sends, n_acks, accumulate;
+  const void* flag[8];
+  const void* send_src[4];
+  void*       send_dst[4];
+  int64_t     send_count[4];
+  void*       send_flag[4];
+  const void* send_ack[4];
+  void*       ack_out[8];
+  void*       epoch_ctr;
+  void*       ticket;
+  int32_t     epoch_add, epoch_bump;
+  uint64_t    expect;
+  void*       error;
+} b2s_fuse_desc;
+int         b2s_spmv_csr_fused(int vt, int it, int pt, int64_t nrows, int64_t ncols, int64_t nnz,
+                               const void* indptr, const void* indices, const void* vals,
+                               const void* x, void* y, const void* w, void* dot_out, const void* plan,
+                               void* ws, const b2s_fuse_desc* desc_host, void* stream);
+/* y += A x (needs a TMA tile plan): one column block of a column-blocked shard at a time */
+int         b2s_spmv_csr_add(int vt, int it, int pt, int64_t nrows, int64_t ncols, int64_t nnz,
+                             const void* indptr, const void* indices, const void* vals,
+                             const void* x, void* y, const void* plan, void* stream);
 
 /* y_host = A x_host for HOST vectors (the matrix stays resident): pipelined H2D / tiles / D2H over the plan's
  * chunks on internal copy streams; x_dev / y_dev are caller-owned device scratch (ncols / nrows elements).
@@ -217,13 +248,14 @@ int         b2s_peer_allreduce(int vt, int rank, int nranks, void* const* peers_
 int         b2s_peer_halo_exchange(int vt, int rank, int nranks, void* const* peers_host,
                                    const void* x_local_dev, int nsends, const int64_t* send_desc_host,
                                    int nrecvs, const int32_t* recv_peers_host, void* stream);
-/* push only (no wait kernel); `epoch` > 0 increases by one per exchange and is the same on every rank.
- * The consumer is b2s_spmv_csr_halo, which polls the arrival flags inside the SpMV kernel. */
-int         b2s_peer_halo_push(int vt, int rank, int nranks, void* const* peers_host,
-                               const void* x_local_dev, int nsends, const int64_t* send_desc_host,
-                               int nrecvs, const int32_t* recv_peers_host, int64_t epoch, void* stream);
-/* byte offset inside the peer header of the host-numbered arrival flag of source rank idx (which = 0) or of the
- * error word (which = 1) */
+/* fused protocol, all-gather style: slice i of the local x goes to peer i's x buffer with `ctas_per_send` CTAs per
+ * destination; no wait kernel -- the consumers are b2s_spmv_csr_fused launches (epoch_add = 0) that poll the
+ * arrival flag of the ONE source whose column block they multiply.  Device-side epochs (graph-replayable). */
+int         b2s_peer_push(int vt, int rank, int nranks, void* const* peers_host, const void* x_local_dev,
+                          int nsends, const int64_t* send_desc_host, int nrecvs,
+                          const int32_t* recv_peers_host, int ctas_per_send, void* stream);
+/* byte offset inside the peer header (fused protocol): which = 0 arrival flag of source rank idx, 1 error word,
+ * 2 acknowledgement word of destination rank idx, 3 epoch counter, 4 ticket word */
 int64_t     b2s_peer_header_offset(int which, int idx);
 int         b2s_peer_check(void* own_buf_dev, void* stream, int64_t* error_out_host);   /* syncs */
 /* dst[i] = src[i] for i in [0,n) elements of type vt where src is a (possibly peer) device

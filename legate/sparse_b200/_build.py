@@ -15,8 +15,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_NAME = "libb200sparse.so"
 LIB_PATH = os.path.join(HERE, LIB_NAME)
-SOURCES = ["capi.cu", "spmv.cu", "spmm.cu", "vecops.cu", "spgemm.cu", "peer.cu"]
-HEADERS = ["common.cuh", os.path.join("..", "..", "..", "include", "b200sparse.h")]
+SOURCES = ["capi.cu", "spmv.cu", "spmv_f32.cu", "spmv_f64.cu", "spmm.cu", "vecops.cu", "spgemm.cu", "peer.cu"]
+HEADERS = ["common.cuh", "spmv_common.cuh", "spmv_kernels.cuh", os.path.join("..", "..", "..", "include", "b200sparse.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -52,6 +52,22 @@ def build(force: bool = False, verbose: bool = False, ptxas_info: bool = False) 
     """Compile every .cu under csrc/ for sm_100a and link libb200sparse.so in-tree."""
     if not force and not needs_build():
         return LIB_PATH
+    # one builder at a time (torchrun imports the package on every rank at once): the others wait on the lock and
+    # then find the library up to date; the link goes to a temporary name and is renamed into place atomically
+    import fcntl
+
+    lock = open(os.path.join(HERE, ".build.lock"), "w")
+    fcntl.flock(lock, fcntl.LOCK_EX)
+    try:
+        if not force and not needs_build():
+            return LIB_PATH
+        return _build_locked(verbose, ptxas_info)
+    finally:
+        fcntl.flock(lock, fcntl.LOCK_UN)
+        lock.close()
+
+
+def _build_locked(verbose: bool, ptxas_info: bool) -> str:
     nvcc = _nvcc()
     objs = []
     build_dir = os.path.join(HERE, "build")
@@ -73,10 +89,12 @@ def build(force: bool = False, verbose: bool = False, ptxas_info: bool = False) 
             raise RuntimeError(f"nvcc failed on {s}:\n{out}")
         if (verbose or ptxas_info) and out:
             print(out, file=sys.stderr)
-    cmd = [nvcc, "-shared", *_host_compiler_args(), "-o", LIB_PATH, *objs, "-lcudart"]
+    tmp = LIB_PATH + f".tmp{os.getpid()}"
+    cmd = [nvcc, "-shared", *_host_compiler_args(), "-o", tmp, *objs, "-lcudart", "-ldl"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    os.replace(tmp, LIB_PATH)
     return LIB_PATH
 
 

@@ -38,8 +38,9 @@ SIGNATURES = {
     "b2s_spmv_plan_chunks": (c_i32, [c_vp, c_vp, c_i32, ctypes.POINTER(c_i32)]),
     "b2s_spmv_csr_tiles": (c_i32, [c_i32, c_i32, c_i32, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp,
                                    c_i64, c_i64, c_vp]),
-    "b2s_spmv_csr_halo": (c_i32, [c_i32, c_i32, c_i32, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32,
-                                  c_vp, c_i32, c_i32, c_vp, ctypes.c_uint64, c_vp, c_vp]),
+    "b2s_spmv_csr_fused": (c_i32, [c_i32, c_i32, c_i32, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp,
+                                   c_vp, c_vp, c_vp, c_vp]),
+    "b2s_spmv_csr_add": (c_i32, [c_i32, c_i32, c_i32, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "b2s_spmv_csr_host": (c_i32, [c_i32, c_i32, c_i32, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp,
                                   c_vp, c_vp]),
     "b2s_spmv_csr_dot": (c_i32, [c_i32, c_i32, c_i32, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp,
@@ -59,7 +60,7 @@ SIGNATURES = {
     "b2s_ipc_free": (c_i32, [c_vp]),
     "b2s_peer_allreduce": (c_i32, [c_i32, c_i32, c_i32, c_vp, c_vp, c_i32, c_vp]),
     "b2s_peer_halo_exchange": (c_i32, [c_i32, c_i32, c_i32, c_vp, c_vp, c_i32, c_vp, c_i32, c_vp, c_vp]),
-    "b2s_peer_halo_push": (c_i32, [c_i32, c_i32, c_i32, c_vp, c_vp, c_i32, c_vp, c_i32, c_vp, c_i64, c_vp]),
+    "b2s_peer_push": (c_i32, [c_i32, c_i32, c_i32, c_vp, c_vp, c_i32, c_vp, c_i32, c_vp, c_i32, c_vp]),
     "b2s_peer_header_offset": (c_i64, [c_i32, c_i32]),
     "b2s_peer_check": (c_i32, [c_vp, c_vp, c_vp]),
     "b2s_ipc_export": (c_i32, [c_vp, c_vp]),
@@ -71,7 +72,27 @@ SIGNATURES = {
     "b2s_spmv_get_config": (c_i32, []),
     "b2s_spmv_num_configs": (c_i32, []),
     "b2s_spmv_plan_set_kernel": (c_i32, [c_vp, c_i32]),
+    "b2s_spmv_plan_set_flavor": (c_i32, [c_vp, c_i32]),
 }
+
+
+class FuseDesc(ctypes.Structure):
+    """b2s_fuse_desc of include/b200sparse.h (the exchange fused into b2s_spmv_csr_fused)."""
+
+    _fields_ = [
+        ("nranges", ctypes.c_int32), ("n_free", ctypes.c_int32),
+        ("ranges", c_i64 * 12),
+        ("n_flags", ctypes.c_int32), ("n_sends", ctypes.c_int32), ("n_acks", ctypes.c_int32),
+        ("accumulate", ctypes.c_int32),
+        ("flag", c_vp * 8),
+        ("send_src", c_vp * 4), ("send_dst", c_vp * 4), ("send_count", c_i64 * 4),
+        ("send_flag", c_vp * 4), ("send_ack", c_vp * 4),
+        ("ack_out", c_vp * 8),
+        ("epoch_ctr", c_vp), ("ticket", c_vp),
+        ("epoch_add", ctypes.c_int32), ("epoch_bump", ctypes.c_int32),
+        ("expect", ctypes.c_uint64),
+        ("error", c_vp),
+    ]
 
 
 class B200SparseError(RuntimeError):

@@ -38,6 +38,7 @@ class SpmvPlan:
         out = (_lib.c_i64 * 4)()
         _lib.check(L.b2s_spmv_plan_info(handle, out), "b2s_spmv_plan_info")
         self.config, self.rowgroup, self.uniform, self.scattered = int(out[0]), bool(out[1] & 1), bool(out[1] & 2), bool(out[1] & 4)
+        self.short_rows, self.tma = bool(out[1] & 8), bool(out[1] & 16)
         self.tiles, self.lines_per_warp = int(out[2]), out[3] / 1000.0
 
     @property
@@ -54,6 +55,19 @@ class SpmvPlan:
     def set_kernel(self, rowgroup: bool):
         _lib.check(L.b2s_spmv_plan_set_kernel(self.handle, int(bool(rowgroup))), "b2s_spmv_plan_set_kernel")
         self.rowgroup = bool(rowgroup)
+
+    def set_flavor(self, flavor: int):
+        """tools / tests: 0 generic, 1 uniform rows, 2 short rows (one lane per row)."""
+        _lib.check(L.b2s_spmv_plan_set_flavor(self.handle, int(flavor)), "b2s_spmv_plan_set_flavor")
+        self.uniform, self.short_rows = flavor == 1, flavor == 2
+
+    @property
+    def kernel_name(self) -> str:
+        """The kernel this plan launches, for the bench line (derived from the plan, not a literal)."""
+        if self.rowgroup:
+            return "b2s::spmv_rowgroup_kernel"
+        fl = "short-rows(one lane per row)" if self.short_rows else ("uniform-rows" if self.uniform else "generic")
+        return f"b2s::spmv_{'tma' if self.tma else 'tile'}_kernel cfg {self.config} [{fl}]"
 
     def __del__(self):
         h, self.handle = getattr(self, "handle", None), None
@@ -268,29 +282,65 @@ def peer_halo_exchange(x_local: torch.Tensor, rank: int, peers, sends, recv_peer
                                         len(recv_peers), rp, _stream()), "b2s_peer_halo_exchange")
 
 
-def peer_halo_push(x_local: torch.Tensor, rank: int, peers, sends, recv_peers, epoch: int) -> None:
-    """Push halo slices into the neighbours' x buffers and raise their arrival flags (no wait kernel)."""
+def peer_push(x_local: torch.Tensor, rank: int, peers, sends, recv_peers, ctas_per_send: int = 8) -> None:
+    """Fused-protocol push (no wait kernel): slices of x_local go to the peers' x buffers, `ctas_per_send` CTAs each;
+    the arrival flags are consumed inside later `spmv_fused` launches."""
     _chk_dev(x_local)
     n = len(peers)
     arr = (_lib.c_vp * n)(*peers)
     flat = [int(v) for s in sends for v in s]
     desc = (_lib.c_i64 * max(len(flat), 1))(*flat)
     rp = (ctypes.c_int32 * max(len(recv_peers), 1))(*recv_peers)
-    _lib.check(L.b2s_peer_halo_push(vt_code(x_local.dtype), rank, n, arr, ptr(x_local), len(sends), desc,
-                                    len(recv_peers), rp, int(epoch), _stream()), "b2s_peer_halo_push")
+    _lib.check(L.b2s_peer_push(vt_code(x_local.dtype), rank, n, arr, ptr(x_local), len(sends), desc,
+                               len(recv_peers), rp, int(ctas_per_send), _stream()), "b2s_peer_push")
 
 
-def spmv_halo(indptr, indices, data, x, y, shape, plan, ranges, n_free: int, flag_ptrs, expect: int, error_ptr: int):
-    """SpMV that waits inside the kernel for the halo flags before its non-free tile ranges."""
+def fuse_desc(ranges, n_free=None, flags=(), sends=(), acks=(), epoch_ctr=0, ticket=0, epoch_add=1, epoch_bump=1,
+              expect=0, error=0, accumulate=False) -> "_lib.FuseDesc":
+    """Build a b2s_fuse_desc.  ranges: [(tile_lo, tile_hi)]; flags: local arrival-word addresses;
+    sends: [(src_ptr, dst_ptr, count, remote_flag_ptr, local_ack_ptr)]; acks: remote ack-word addresses."""
+    d = _lib.FuseDesc()
+    ranges = list(ranges)
+    d.nranges = len(ranges)
+    d.n_free = len(ranges) if n_free is None else int(n_free)
+    for i, (lo, hi) in enumerate(ranges):
+        d.ranges[2 * i], d.ranges[2 * i + 1] = int(lo), int(hi)
+    d.n_flags, d.n_sends, d.n_acks = len(flags), len(sends), len(acks)
+    d.accumulate = int(bool(accumulate))
+    for i, f in enumerate(flags):
+        d.flag[i] = int(f)
+    for i, (src, dst, cnt, rflag, lack) in enumerate(sends):
+        d.send_src[i], d.send_dst[i], d.send_count[i] = int(src), int(dst), int(cnt)
+        d.send_flag[i], d.send_ack[i] = int(rflag), int(lack)
+    for i, a in enumerate(acks):
+        d.ack_out[i] = int(a)
+    d.epoch_ctr = int(epoch_ctr) or None
+    d.ticket = int(ticket) or None
+    d.epoch_add, d.epoch_bump = int(epoch_add), int(epoch_bump)
+    d.expect = int(expect)
+    d.error = int(error) or None
+    return d
+
+
+def spmv_fused(indptr, indices, data, x, y, shape, plan, desc, w=None, dot_out=None):
+    """y = A @ x (or y += with desc.accumulate) with the x exchange fused into the kernel; optional fused w . y."""
+    _chk_dev(indptr, indices, data, x, y, w, dot_out)
+    nrows, ncols = shape
+    ws = ptr(runtime.workspace()) if w is not None else None
+    _lib.check(L.b2s_spmv_csr_fused(vt_code(data.dtype), idx_code(indices.dtype), idx_code(indptr.dtype), nrows, ncols,
+                                    data.shape[0], ptr(indptr), ptr(indices), ptr(data), ptr(x), ptr(y),
+                                    ptr(w) if w is not None else None, ptr(dot_out) if dot_out is not None else None,
+                                    _plan_handle(plan), ws, ctypes.byref(desc), _stream()), "b2s_spmv_csr_fused")
+    return y
+
+
+def spmv_add(indptr, indices, data, x, y, shape, plan):
+    """y += A @ x (TMA tile plans)."""
     _chk_dev(indptr, indices, data, x, y)
     nrows, ncols = shape
-    flat = [int(v) for r in ranges for v in r]
-    rg = (_lib.c_i64 * len(flat))(*flat)
-    fl = (_lib.c_vp * max(len(flag_ptrs), 1))(*flag_ptrs)
-    _lib.check(L.b2s_spmv_csr_halo(vt_code(data.dtype), idx_code(indices.dtype), idx_code(indptr.dtype), nrows, ncols,
-                                   data.shape[0], ptr(indptr), ptr(indices), ptr(data), ptr(x), ptr(y),
-                                   _plan_handle(plan), len(ranges), rg, n_free, len(flag_ptrs), fl, int(expect),
-                                   error_ptr, _stream()), "b2s_spmv_csr_halo")
+    _lib.check(L.b2s_spmv_csr_add(vt_code(data.dtype), idx_code(indices.dtype), idx_code(indptr.dtype), nrows, ncols,
+                                  data.shape[0], ptr(indptr), ptr(indices), ptr(data), ptr(x), ptr(y),
+                                  _plan_handle(plan), _stream()), "b2s_spmv_csr_add")
     return y
 
 

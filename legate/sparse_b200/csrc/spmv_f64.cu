@@ -1,0 +1,17 @@
+// spmv_f64.cu -- double instantiations of the CSR SpMV kernels (see spmv_kernels.cuh); split by value type so the
+// two halves of the template grid compile in parallel.
+#include "spmv_kernels.cuh"
+
+namespace b2s {
+
+int spmv_launch_f64(bool dot, int it, int pt, int cfg, const SpmvArgs& a) {
+  if (dot) return dispatch_idx<double, true>(it, pt, cfg, a);
+  return dispatch_idx<double, false>(it, pt, cfg, a);
+}
+
+int spmv_rowgroup_f64(int it, int pt, int64_t nrows, int64_t nnz, const void* indptr, const void* indices,
+                      const void* vals, const void* x, void* y, cudaStream_t st) {
+  return dispatch_rowgroup<double>(it, pt, nrows, nnz, indptr, indices, vals, x, y, st);
+}
+
+}  // namespace b2s

@@ -153,6 +153,47 @@ class PeerComm:
     def allreduce(self, t: torch.Tensor) -> torch.Tensor:
         return _ops.peer_allreduce(t, self.rank, self.peers)
 
+    # addresses of the fused-protocol words (PeerHeader::fuse_*, csrc/peer.cu) in my header or in a peer's
+    def _word(self, which: int, idx: int = 0, peer: int | None = None) -> int:
+        from . import _lib
+
+        base = self.own if peer is None else self.peers[peer]
+        return base + int(_lib.lib.b2s_peer_header_offset(which, idx))
+
+    def flag_local(self, src: int) -> int:        # written by `src` when its slice has landed here
+        return self._word(0, src)
+
+    def flag_remote(self, dst: int) -> int:       # my arrival word in dst's header
+        return self._word(0, self.rank, dst)
+
+    def ack_local(self, dst: int) -> int:         # written by `dst` when it has consumed my previous slice
+        return self._word(2, dst)
+
+    def ack_remote(self, src: int) -> int:        # my acknowledgement word in src's header
+        return self._word(2, self.rank, src)
+
+    @property
+    def epoch_ctr(self) -> int:
+        return self._word(3)
+
+    @property
+    def ticket(self) -> int:
+        return self._word(4)
+
+    @property
+    def error_word(self) -> int:
+        return self._word(1)
+
+    def x_remote(self, peer: int, elem: int) -> int:
+        """Device address (peer-mapped) of element `elem` of `peer`'s full-length x vector."""
+        return self.peers[peer] + self.header + (self.peer_x_off[peer] + elem) * self.dtype.itemsize
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
     def check(self):
         if _ops.peer_check(self.own):
             raise RuntimeError("NVLink peer exchange timed out waiting for another rank (PeerHeader.error set)")
@@ -310,23 +351,26 @@ class dist_csr_array:
             mode = "p2p"  # the in-place all-gather needs equal shards; uneven (balanced) plans exchange windows
         self.exchange_mode = mode if self.nranks > 1 else "none"
         self.recv_elems = need
-        # NVLink peer-memory path (csrc/peer.cu), for ranks that are CUDA devices of one box:
-        #   B2S_PEER=1 (default)      CG scalars are all-reduced by the one-shot peer kernel (one ~5 us launch
-        #                             instead of an NCCL all-reduce; 2 GPUs, PDE4096: 299 -> 271 us/iteration)
-        #   B2S_PEER_HALO=1 (opt-in)  x halo pieces are pushed by remote stores instead of NCCL send/recv.
-        #                             Measured equal to NCCL (two launches, ~20 us vs ~18 us per exchange at
-        #                             2 GPUs), so it stays off until the wait is fused into the SpMV kernel.
+        # NVLink peer-memory path (csrc/peer.cu), for ranks that are CUDA devices of ONE box (CUDA IPC):
+        #   B2S_PEER=1 (default)   CG scalars are all-reduced by the one-shot peer kernel, and the x exchange is
+        #                          FUSED into the SpMV kernel: a halo is pushed / awaited by the SpMV launch itself
+        #                          (`_fused_halo`), an all-gather becomes b2s_peer_push + one column block per
+        #                          source rank, each waiting in-kernel for its own slice (`_fused_blocks`).
+        #                          Device-side epochs: the whole step replays from a CUDA graph.
+        #   B2S_PEER_FUSED=0       keep the peer all-reduce but exchange x with NCCL (the round-1 path)
+        #   B2S_PEER_HALO=1        explicit `exchange()` calls push halos with peer kernels instead of NCCL p2p
         self._peer = {}
+        self._fused = {}
         peer_ok = self.nranks > 1 and runtime.has_cuda and self.nranks <= 16
+        if peer_ok:
+            import socket
+
+            hosts = [None] * self.nranks
+            dist.all_gather_object(hosts, socket.gethostname(), group=self.group)
+            peer_ok = len(set(hosts)) == 1       # CUDA IPC maps memory of GPUs in the same box only
         self.use_peer = peer_ok and os.environ.get("B2S_PEER", "1") != "0"
-        halo = os.environ.get("B2S_PEER_HALO", "0")
-        self.use_peer_halo = self.use_peer and halo in ("1", "fused")
-        # "fused" (EXPERIMENTAL): halo slices are pushed by remote stores and the SpMV kernel itself waits for them
-        # before its boundary tiles (b2s_spmv_csr_halo) -- compute and collective in one kernel, no NCCL on the
-        # SpMV path.  Measured 158.5 us/step at 2 GPUs (NCCL + graph replay: 157.7): the per-step coupling of
-        # the ranks, not the exchange mechanism, is what costs the ~16 us over the bare 141 us kernel.
-        self.fused_halo = self.use_peer and halo == "fused"
-        self._halo_epoch = 0
+        self.use_peer_halo = self.use_peer and os.environ.get("B2S_PEER_HALO", "0") == "1"
+        self.use_fused = self.use_peer and os.environ.get("B2S_PEER_FUSED", "1") != "0"
 
     def _comm_device(self):
         return runtime.device
@@ -337,7 +381,18 @@ class dist_csr_array:
         pc = self._peer.get(key)
         if pc is None:
             n = max(self.col_plan.padded, 1)
-            pc = PeerComm(n, key, self.rank, self.nranks, self.group)
+            try:
+                pc = PeerComm(n, key, self.rank, self.nranks, self.group)
+                ok = 1
+            except Exception:  # no peer access between some pair of GPUs, IPC refused, out of memory ...
+                pc, ok = None, 0
+            flag = torch.tensor([ok], dtype=torch.int32, device=self._comm_device())
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+            if int(flag.item()) == 0:      # some rank failed: everybody falls back to NCCL, consistently
+                if pc is not None:
+                    pc.close()
+                self.use_peer = self.use_peer_halo = self.use_fused = False
+                return None
             per16 = 16 // key.itemsize
             pc.x_off = (-self.my_cols[0]) % per16  # own slice starts 16-byte aligned
             offs = [None] * self.nranks
@@ -353,10 +408,11 @@ class dist_csr_array:
         then take their 128-bit path on the shard views).  With the peer path enabled the buffer lives in
         this rank's IPC allocation (one per dtype, reused) so neighbours can push their halo pieces into it."""
         np_dt = numpy_dtype(self.dtype if dtype is None else dtype)
-        if self.use_peer_halo:
+        if self.use_peer_halo or self.use_fused:
             pc = self._peer_comm(np_dt)
-            pc.x_full.zero_()
-            return pc.x_full
+            if pc is not None:
+                pc.x_full.zero_()
+                return pc.x_full
         dt = torch_dtype(np_dt)
         n = max(self.col_plan.padded, 1)
         base = torch.zeros(n + 4, dtype=dt, device=runtime.device)
@@ -400,12 +456,14 @@ class dist_csr_array:
                 req.wait()
 
     # -- SpMV ---------------------------------------------------------------------------------------------
-    def _overlap_schedule(self):
-        """Split the local SpMV plan into runs of tiles that only read locally owned x (can run while the halo
-        is still in flight) and runs that touch remote columns (must wait for the exchange).  Uses the plan's
-        row chunks and their column windows; None when the plan is not chunked."""
-        if getattr(self, "_sched", None) is None:
-            plan = self.local._get_plan()
+    def _overlap_schedule(self, plan=None):
+        """Split an SpMV plan of the local shard into runs of tiles that only read locally owned x (can run while
+        the halo is still in flight) and runs that touch remote columns (must wait for the exchange).  Uses the
+        plan's row chunks and their column windows; None when the plan is not chunked."""
+        plan = self.local._get_plan() if plan is None else plan
+        cache = self.__dict__.setdefault("_scheds", {})
+        key = id(plan)
+        if key not in cache:
             lo, hi = self.my_cols
             interior, boundary = [], []
             for tile_lo, tile_hi, _, _, col_lo, col_hi in plan.chunks:
@@ -417,39 +475,143 @@ class dist_csr_array:
                     runs[-1][1] = tile_hi
                 else:
                     runs.append([tile_lo, tile_hi])
-            self._sched = (interior, boundary) if plan.chunks and interior else ()
-        return self._sched or None
+            cache[key] = (interior, boundary) if plan.chunks and interior else ()
+        return cache[key] or None
+
+    def _agree(self, ok: bool) -> bool:
+        """True iff `ok` on every rank (the fused protocols deadlock unless all ranks take the same path)."""
+        if self.nranks == 1:
+            return bool(ok)
+        t = torch.tensor([1 if ok else 0], dtype=torch.int32, device=self._comm_device())
+        dist.all_reduce(t, op=dist.ReduceOp.MIN, group=self.group)
+        return bool(int(t.item()))
+
+    def _fused_setup(self, A: csr_array, x_full: torch.Tensor):
+        """One-time (collective) setup of the fused exchange for products of `A` (the local shard or a promoted copy
+        of it) with the peer-resident vector `x_full`.  Returns a dict describing the path, or None (NCCL path).
+
+        halo   (exchange_mode p2p): ONE launch per product -- `b2s_spmv_csr_fused` pushes this rank's boundary
+               slices into the neighbours' x buffers, computes the interior tiles, and waits for the neighbours'
+               slices only before its boundary tiles.
+        blocks (exchange_mode allgather): the shard is cut at plan time into one CSR block per source rank (the
+               columns that rank owns; the reference gets the same effect from Legion's image partitions,
+               sparse/csr.py:930-968).  `b2s_peer_push` sends this rank's slice to everybody on a side stream while
+               the own-column block is multiplied; each remote block is one accumulating launch that waits
+               in-kernel for the arrival flag of ITS source only, so products start as slices land."""
+        key = (id(A), x_full.data_ptr())
+        if key in self._fused:
+            return self._fused[key]
+        info = None
+        np_dt = numpy_dtype(x_full.dtype)
+        pc = self._peer.get(np_dt) if self.use_fused else None
+        usable = (pc is not None and x_full.is_cuda and x_full.data_ptr() == pc.x_full.data_ptr()
+                  and A.dtype == np_dt and self.exchange_mode in ("p2p", "allgather"))
+        item = np.dtype(np_dt).itemsize
+        if self.exchange_mode == "p2p":
+            plan = A._get_plan() if usable else None
+            sched = self._overlap_schedule(plan) if usable and plan.tma else None
+            if sched is not None and len(sched[0]) + len(sched[1]) > 6:
+                sched = None
+            ok = bool(usable and plan.tma and len(self.sends) <= 4 and len(self.recvs) <= 8)
+            if self._agree(ok):
+                if sched is None:      # plan too small to be chunked: every tile waits for the halo (no overlap)
+                    ranges, n_free = [(0, plan.tiles)], (0 if self.recvs else 1)
+                else:
+                    ranges, n_free = [tuple(r) for r in sched[0] + sched[1]], len(sched[0])
+                sends = [(x_full.data_ptr() + a * item, pc.x_remote(q, a), b - a, pc.flag_remote(q), pc.ack_local(q))
+                         for q, a, b in self.sends]
+                desc = _ops.fuse_desc(ranges, n_free, flags=[pc.flag_local(q) for q, _, _ in self.recvs], sends=sends,
+                                      acks=[pc.ack_remote(q) for q, _, _ in self.recvs], epoch_ctr=pc.epoch_ctr,
+                                      ticket=pc.ticket, epoch_add=1, epoch_bump=1, error=pc.error_word)
+                info = {"mode": "halo", "desc": desc, "plan": plan, "pc": pc}
+        elif self.exchange_mode == "allgather":
+            ok = bool(usable and self.col_plan.uniform)
+            if self._agree(ok):
+                blocks = self._column_blocks(A)
+                lo, hi = self.my_cols
+                sends = [(q, lo, pc.peer_x_off[q] + lo, hi - lo) for q in range(self.nranks) if q != self.rank and hi > lo]
+                recv_peers = [q for q in range(self.nranks) if q != self.rank]
+                descs = {}
+                for q, Bq in blocks.items():
+                    if q == self.rank or Bq is None:
+                        continue
+                    pl = Bq._get_plan()
+                    if not pl.tma:
+                        raise RuntimeError("column block without a TMA tile plan")
+                    descs[q] = _ops.fuse_desc([(0, pl.tiles)], 0, flags=[pc.flag_local(q)], epoch_ctr=pc.epoch_ctr,
+                                              ticket=pc.ticket, epoch_add=0, epoch_bump=0, error=pc.error_word,
+                                              accumulate=True)
+                slice_bytes = (hi - lo) * item
+                info = {"mode": "blocks", "blocks": blocks, "descs": descs, "sends": sends, "recv_peers": recv_peers,
+                        "pc": pc, "cps": 16 if slice_bytes >= (1 << 22) else (4 if slice_bytes >= (1 << 18) else 1),
+                        "order": [(self.rank + d) % self.nranks for d in range(1, self.nranks)]}
+        self._fused[key] = info
+        return info
+
+    def _column_blocks(self, A: csr_array):
+        """{q: CSR of the entries of A whose column is owned by rank q (global column ids kept), or None if empty}."""
+        out = {}
+        idx = A.indices
+        nrows = A.shape[0]
+        counts_all = (A.indptr[1:] - A.indptr[:-1]).to(torch.int64)
+        rows = torch.repeat_interleave(torch.arange(nrows, device=idx.device, dtype=torch.int64), counts_all)
+        for q in range(self.nranks):
+            qlo, qhi = self.col_plan.rows(q)
+            mask = (idx >= qlo) & (idx < qhi)
+            nnz_q = int(mask.sum())
+            if nnz_q == 0:
+                out[q] = None
+                continue
+            cnt = torch.bincount(rows[mask], minlength=nrows)
+            indptr = torch.zeros(nrows + 1, dtype=torch.int64, device=idx.device)
+            torch.cumsum(cnt, 0, out=indptr[1:])
+            ptr_dt = torch.int32 if nnz_q < 2**31 - 1 else torch.int64
+            out[q] = csr_array._from_parts(indptr.to(ptr_dt), idx[mask].contiguous(), A.data[mask].contiguous(), A.shape)
+        return out
+
+    def _dot_fused(self, info, A, x_full, out, w=None, dot_out=None):
+        xin = x_full[: A.shape[1]]
+        if info["mode"] == "halo":
+            _ops.spmv_fused(A.indptr, A.indices, A.data, xin, out, A.shape, info["plan"], info["desc"], w=w, dot_out=dot_out)
+            return out
+        pc = info["pc"]
+        cur = torch.cuda.current_stream()
+        if getattr(self, "_comm_stream", None) is None:
+            self._comm_stream = torch.cuda.Stream()
+        cs = self._comm_stream
+        cs.wait_stream(cur)
+        with torch.cuda.stream(cs):
+            _ops.peer_push(x_full, self.rank, pc.peers, info["sends"], info["recv_peers"], info["cps"])
+            pushed = cs.record_event()
+        own = info["blocks"].get(self.rank)
+        if own is None:
+            out.zero_()
+        else:
+            _ops.spmv(own.indptr, own.indices, own.data, xin, out, own.shape, plan=own._get_plan())
+        cur.wait_event(pushed)   # the epoch counter the block launches read is the one this push advanced
+        for q in info["order"]:
+            Bq = info["blocks"].get(q)
+            if Bq is not None:
+                _ops.spmv_fused(Bq.indptr, Bq.indices, Bq.data, xin, out, Bq.shape, Bq._get_plan(), info["descs"][q])
+        if w is not None:
+            _ops.dot(w, out, out=dot_out)
+        return out
 
     def dot(self, x_full: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
         """y_local = A_local @ x.  `x_full` is a full-length buffer whose my_cols slice is current.
 
-        With B2S_OVERLAP=1, a chunked plan and a point-to-point halo, the exchange runs on a side stream while
-        the tiles that read only local columns are already being multiplied; the few boundary tiles follow once
-        the halo has landed.  Off by default: measured on 2 and 4 B200s the split into three tile launches costs
-        what the overlap gains (156 vs 157 us/step at 2 GPUs, 164 vs 159 at 4), so exchange and SpMV are simply
-        serialised; the remaining ~16 us is the NCCL send/recv kernel itself."""
+        Default on the GPUs of one box: the exchange is fused into the SpMV launch(es) (`_fused_setup`).  Otherwise
+        (B2S_PEER_FUSED=0, gloo, several hosts) x is exchanged with NCCL first -- optionally on a side stream while the
+        tiles that read only local columns run (B2S_OVERLAP=1)."""
         A = self.local
         if out is None:
             out = torch.empty(A.shape[0], dtype=x_full.dtype, device=x_full.device)
         xin = x_full[: A.shape[1]]
+        if self.use_fused and x_full.is_cuda and self.exchange_mode != "none":
+            info = self._fused_setup(A, x_full)
+            if info is not None:
+                return self._dot_fused(info, A, x_full, out)
         plan = A._get_plan()
-        if self.fused_halo and self.exchange_mode == "p2p" and x_full.is_cuda and A.dtype == numpy_dtype(x_full.dtype):
-            pc = self._peer.get(numpy_dtype(x_full.dtype))
-            sched = self._overlap_schedule()
-            if pc is not None and sched and x_full.data_ptr() == pc.x_full.data_ptr():
-                from . import _lib
-
-                self._halo_epoch += 1
-                e = self._halo_epoch
-                sends = [(q, a, pc.peer_x_off[q] + a, b - a) for q, a, b in self.sends]
-                recv_peers = [q for q, _, _ in self.recvs]
-                _ops.peer_halo_push(x_full, self.rank, pc.peers, sends, recv_peers, e)
-                interior, boundary = sched
-                flags = [pc.own + int(_lib.lib.b2s_peer_header_offset(0, q)) for q in recv_peers]
-                err = pc.own + int(_lib.lib.b2s_peer_header_offset(1, 0))
-                _ops.spmv_halo(A.indptr, A.indices, A.data, xin, out, A.shape, plan, interior + boundary,
-                               len(interior), flags, e, err)
-                return out
         sched = None
         if (self.exchange_mode == "p2p" and x_full.is_cuda and A.dtype == numpy_dtype(x_full.dtype)
                 and os.environ.get("B2S_OVERLAP", "0") == "1"):
@@ -474,15 +636,27 @@ class dist_csr_array:
             _ops.spmv_tiles(A.indptr, A.indices, A.data, xin, out, A.shape, plan, tile_lo, tile_hi)
         return out
 
+    def spmv_dot(self, Ad: csr_array, x_full, out, w, dot_out):
+        """q = A p and dot_out = all-reduced p.q for the CG loop (`Ad` = the local shard, possibly promoted): the x
+        exchange, the product and the local inner product are one launch on the fused halo path."""
+        info = None
+        if self.use_fused and x_full.is_cuda and self.exchange_mode != "none":
+            info = self._fused_setup(Ad, x_full)
+        if info is not None:
+            self._dot_fused(info, Ad, x_full, out, w=w, dot_out=dot_out)
+        else:
+            self.exchange(x_full)
+            _ops.spmv_dot(Ad._indptr, Ad._indices, Ad._data, x_full[: Ad.shape[1]], out, w, dot_out, Ad.shape, Ad._get_plan())
+        self.allreduce(dot_out)
+        return out
+
     def dot_graphed(self, x_full: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
         """`dot` replayed from a CUDA graph (captured on first use for this (x_full, out) pair): the exchange
-        (NCCL send/recv or peer kernels), the stream fork/join of the overlap schedule and the tile launches
-        cost one graph launch on the host instead of ~150 us of Python/NCCL call overhead per product, which
-        is what bounds a 140 us SpMV step otherwise."""
+        (fused launches with device-side epochs, NCCL send/recv or peer kernels), the stream fork/join and the tile
+        launches cost one graph launch on the host instead of ~150 us of Python/NCCL call overhead per product,
+        which is what bounds a 140 us SpMV step otherwise."""
         from .linalg import _try_capture
 
-        if self.fused_halo:
-            return self.dot(x_full, out=out)  # host-numbered epochs are kernel arguments: not replayable
         key = (x_full.data_ptr(), out.data_ptr(), os.environ.get("B2S_OVERLAP", "0"))
         cache = self.__dict__.setdefault("_dot_graphs", {})
         g = cache.get(key)
@@ -543,7 +717,8 @@ class dist_csr_array:
         if self.use_peer and t.is_cuda and t.numel() <= 4:
             # any of this shard's peer communicators will do: the scalar mailboxes do not depend on the x dtype
             pc = next(iter(self._peer.values())) if self._peer else self._peer_comm(self.dtype)
-            return pc.allreduce(t)
+            if pc is not None:
+                return pc.allreduce(t)
         return allreduce_scalar(t, self.group)
 
     def check_peer(self):
@@ -552,6 +727,7 @@ class dist_csr_array:
 
     def close(self):
         self.__dict__.pop("_dot_graphs", None)   # captured graphs reference the buffers freed below
+        self._fused = {}
         for pc in self._peer.values():
             pc.close()
         self._peer = {}
@@ -631,7 +807,8 @@ def spgemm(A: "dist_csr_array", B: "dist_csr_array") -> "dist_csr_array":
     assert A.shape[1] == B.shape[0]
     Bfull = gather_matrix(B)
     Cl = A.local @ Bfull
-    C = dist_csr_array(Cl, (A.shape[0], B.shape[1]), rank=A.rank, nranks=A.nranks, group=A.group)
+    C = dist_csr_array(Cl, (A.shape[0], B.shape[1]), rank=A.rank, nranks=A.nranks, group=A.group,
+                       row_plan=A.row_plan)
     nnzs = [None] * A.nranks
     if A.nranks > 1:
         dist.all_gather_object(nnzs, Cl.nnz, group=A.group)

@@ -269,6 +269,14 @@ class _LocalComm:
     def allreduce(self, t):
         return t
 
+    def dot(self, x_full, out=None, A=None):
+        _ops.spmv(A._indptr, A._indices, A._data, x_full[: A.shape[1]], out, A.shape, plan=A._get_plan())
+        return out
+
+    def spmv_dot(self, A, x_full, out, w, dot_out):
+        _ops.spmv_dot(A._indptr, A._indices, A._data, x_full[: A.shape[1]], out, w, dot_out, A.shape, A._get_plan())
+        return out
+
 
 def _cg_fused(A: csr_array, b, x, tol, maxiter, callback, conv_test_iters, on_device):
     dt = numpy_dtype(b.dtype)
@@ -302,8 +310,7 @@ def _cg_fused_loop(Ad: csr_array, comm, b, x, tol, maxiter, callback, conv_test_
 
     # r = b - A x
     p.copy_(x)
-    comm.exchange(p_full)
-    _ops.spmv(Ad._indptr, Ad._indices, Ad._data, xin, q, shape, plan=plan)
+    comm.spmv_dot(Ad, p_full, q, p, torch.empty(1, dtype=b.dtype, device=b.device))   # q = A x (the dot is discarded)
     r = b - q
     rho = _ops.dot(r, r)
     comm.allreduce(rho)
@@ -312,9 +319,7 @@ def _cg_fused_loop(Ad: csr_array, comm, b, x, tol, maxiter, callback, conv_test_
     pq = torch.empty_like(rho)
 
     def tail_of_iteration():
-        comm.exchange(p_full)
-        _ops.spmv_dot(Ad._indptr, Ad._indices, Ad._data, xin, q, p, pq, shape, plan)
-        comm.allreduce(pq)
+        comm.spmv_dot(Ad, p_full, q, p, pq)      # exchange of p (fused into the launch when sharded) + product + p.q
         _ops.cg_update_xr(x, r, p, q, rho, pq, rr)
         comm.allreduce(rr)
         rho_prev.copy_(rho)

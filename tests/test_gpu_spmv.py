@@ -147,6 +147,20 @@ def test_structures_vs_oracle(oracle, structure, dtype, wide):
     got = y.cpu().numpy()
     assert not np.isnan(got).any()
     assert _close_rowscaled(got, ref, absx, dtype), np.abs(got - ref).max()
+    if plan.tma:
+        # every kernel flavour (generic / uniform-row registers / one lane per short row) on the same tiles, and the
+        # accumulating form y += A x
+        auto = 2 if plan.short_rows else (1 if plan.uniform else 0)
+        for flavor in (0, 1, 2):
+            plan.set_flavor(flavor)
+            yf = torch.full_like(y, float("nan"))
+            _ops.spmv(d_ptr, d_idx, d_val, d_x, yf, (nrows, ncols), plan=plan)
+            assert _close_rowscaled(yf.cpu().numpy(), ref, absx, dtype), (flavor, structure)
+            y0 = torch.from_numpy(rng.standard_normal(nrows).astype(dtype)).cuda()
+            ya = y0.clone()
+            _ops.spmv_add(d_ptr, d_idx, d_val, d_x, ya, (nrows, ncols), plan)
+            assert _close_rowscaled((ya - y0).cpu().numpy(), ref, absx + np.abs(y0.cpu().numpy()), dtype), (flavor, "add")
+        plan.set_flavor(auto)
     # plan-free kernel (plan=NULL) must agree too
     y2 = torch.full_like(y, float("nan"))
     _ops.spmv(d_ptr, d_idx, d_val, d_x, y2, (nrows, ncols), plan=None)
@@ -181,7 +195,7 @@ def test_unaligned_base_pointers(oracle):
     assert np.allclose(y.cpu().numpy(), oracle.spmv(indptr, indices, data, x), rtol=1e-12, atol=1e-12)
 
 
-@pytest.mark.parametrize("cfg", range(14))
+@pytest.mark.parametrize("cfg", range(12))
 @pytest.mark.parametrize("dtype", TYPES)
 def test_all_tile_configs(oracle, cfg, dtype):
     rng = np.random.default_rng(100 + cfg)
@@ -189,7 +203,7 @@ def test_all_tile_configs(oracle, cfg, dtype):
     lens = np.where(np.arange(nrows) % 501 == 0, 9000, rng.integers(0, 12, nrows))
     indptr, indices, data = _random_csr(rng, nrows, ncols, lens, dtype)
     x = rng.standard_normal(ncols).astype(dtype)
-    assert _lib.lib.b2s_spmv_num_configs() == 14
+    assert _lib.lib.b2s_spmv_num_configs() == 12
     try:
         _lib.check(_lib.lib.b2s_spmv_set_config(cfg, cfg % 3))
         A = sparse.csr_array((data, indices, indptr), shape=(nrows, ncols))
@@ -265,9 +279,13 @@ def test_plan_kernel_choice_by_column_locality():
     pl, pb, pr = L5._get_plan(), B._get_plan(), R._get_plan()
     assert not pl.scattered and pl.lines_per_warp < 12
     assert not pb.scattered and pb.lines_per_warp < 6
-    assert not pl.uniform and not pb.uniform      # short odd rows keep the lean variant
+    assert not pl.uniform and not pb.uniform      # short odd rows: one lane per row, not the shuffle-tree path
+    assert pl.short_rows and pb.short_rows and pl.tma
     assert gallery.banded(100000, 32, np.float32)._get_plan().uniform
-    assert pr.scattered and pr.lines_per_warp > 28 and pr.config == 5   # deep-MLP tile shape for scattered fp32
+    assert pr.scattered and pr.lines_per_warp > 28 and pr.config == 4   # deep-MLP tile shape for scattered fp32
+    # scattered SHORT rows (a column block of a random shard) keep the default shape and go one lane per row
+    R4 = gallery.random_fixed(100000, 100000, 4, np.float32)._get_plan()
+    assert R4.scattered and R4.short_rows and R4.tma and R4.config == 5
     # both kernel families give the same answer on the same plan
     x = torch.rand(100000, dtype=torch.float32, device="cuda")
     y1 = R @ x
@@ -348,7 +366,8 @@ def test_host_vectors_pipelined_path(kind, pinned, monkeypatch):
 
 def test_plan_entries_follow_the_tile_rule():
     """White-box check of b2s_spmv_plan_create: tile t starts at the first row r with indptr[r] + r >= t*T,
-    its entry holds that row, indptr[row] and the common row length of the tile (0 if rows differ); so every
+    its entry holds that row, indptr[row] and the row-shape code of the tile (common row length L, or -longest when the
+    rows differ but none exceeds 16, else 0); so every
     tile has <= T rows and all rows but the last fit in T + 4 nonzeros."""
     rng = np.random.default_rng(77)
     nrows = 30011
@@ -381,6 +400,67 @@ def test_plan_entries_follow_the_tile_rule():
         if r1 > r0 + 1:
             assert indptr[r1 - 1] - indptr[r0] <= T        # all rows but the last fit in the staged chunk
         ls = lens[r0:r1]
-        want = int(ls[0]) if (r1 > r0 and ls[0] > 0 and (ls == ls[0]).all()) else 0
+        if r1 > r0 and ls[0] > 0 and (ls == ls[0]).all():
+            want = int(ls[0])                                # uniform tile: the common row length
+        elif r1 > r0 and ls.max() <= 16:
+            want = -max(int(ls.max()), 1)                    # short rows: minus the longest
+        else:
+            want = 0
         assert pad[t] == want, (t, pad[t], want)
     assert (pad[:ntiles] == 6).sum() >= 20                 # the uniform stretch is recognised
+
+
+def test_fused_entry_without_exchange_and_tile_ranges(oracle):
+    """b2s_spmv_csr_fused with an empty exchange: explicit tile ranges in any order give the plain product, the fused
+    dot works through it, and `accumulate` adds."""
+    from legate.sparse_b200 import gallery
+
+    A = gallery.laplacian_5pt(300, 200, np.float64)
+    plan = A._get_plan()
+    n = A.shape[0]
+    x = torch.rand(n, dtype=torch.float64, device="cuda")
+    ref = A @ x
+    nt = plan.tiles
+    cuts = [(nt // 2, nt), (0, nt // 3), (nt // 3, nt // 2)]
+    y = torch.full((n,), float("nan"), dtype=torch.float64, device="cuda")
+    _ops.spmv_fused(A.indptr, A.indices, A.data, x, y, A.shape, plan, _ops.fuse_desc(cuts))
+    assert torch.equal(y, ref)
+    w = torch.rand(n, dtype=torch.float64, device="cuda")
+    out = torch.zeros(1, dtype=torch.float64, device="cuda")
+    y2 = torch.empty_like(y)
+    _ops.spmv_fused(A.indptr, A.indices, A.data, x, y2, A.shape, plan, _ops.fuse_desc([(0, nt)]), w=w, dot_out=out)
+    assert torch.equal(y2, ref)
+    assert abs(float(out[0]) - float(torch.dot(w, ref))) <= 1e-12 * float(torch.dot(w.abs(), ref.abs()))
+    y3 = torch.ones_like(y)
+    _ops.spmv_fused(A.indptr, A.indices, A.data, x, y3, A.shape, plan, _ops.fuse_desc([(0, nt)], accumulate=True))
+    assert torch.allclose(y3, ref + 1.0, rtol=1e-13, atol=1e-7)
+
+
+def test_r32_full_size_vs_scipy_and_oracle(oracle):
+    """BASELINE config 4 at full size (10M x 10M, 32 random entries per row, fp32): the device product against scipy
+    (1e-6 of the row's |A||x| scale -- the north-star bar) and against the CPU oracle; fp64 on a 2M-row slice."""
+    from legate.sparse_b200 import gallery
+
+    n = 10_000_000
+    A = gallery.random_fixed(n, n, 32, np.float32)
+    assert A.nnz == 320_000_000
+    plan = A._get_plan()
+    assert plan.scattered and plan.uniform
+    x = torch.rand(n, dtype=torch.float32, device="cuda")
+    y = (A @ x).cpu().numpy()
+    ip, ix, dv = A.indptr.cpu().numpy(), A.indices.cpu().numpy(), A.data.cpu().numpy()
+    xh = x.cpu().numpy()
+    S = sp.csr_array((dv, ix, ip), shape=A.shape)
+    ref = S @ xh
+    absx = sp.csr_array((np.abs(dv), ix, ip), shape=A.shape) @ xh
+    assert np.all(np.abs(y - ref) <= 2e-6 * absx + 1e-30)
+    rows = 1_000_000
+    yo = oracle.spmv(ip[: rows + 1], ix[: 32 * rows], dv[: 32 * rows], xh, omp=True)
+    assert np.all(np.abs(y[:rows] - yo) <= 2e-6 * absx[:rows] + 1e-30)
+    del S, ref, absx
+    # size-independent property at full size: linearity
+    z = torch.rand(n, dtype=torch.float32, device="cuda")
+    lhs = A @ (x + z)
+    rhs = (A @ x) + (A @ z)
+    scale = float(rhs.abs().max())
+    assert float((lhs - rhs).abs().max()) <= 2e-5 * scale
