@@ -79,6 +79,11 @@ int64_t     b2s_spmv_plan_bytes(int vt, int64_t nrows, int64_t nnz);
 int         b2s_spmv_plan_create(int vt, int it, int pt, int64_t nrows, int64_t ncols, int64_t nnz,
                                  const void* indptr, const void* indices, void* plan_buf_dev,
                                  void* stream, void** plan_out);
+/* flags: B2S_PLAN_TMA_ONLY = the caller will use b2s_spmv_csr_fused / b2s_spmv_csr_add, which need the TMA tile kernel */
+#define B2S_PLAN_TMA_ONLY 1
+int         b2s_spmv_plan_create_ex(int vt, int it, int pt, int64_t nrows, int64_t ncols, int64_t nnz,
+                                    const void* indptr, const void* indices, void* plan_buf_dev,
+                                    void* stream, void** plan_out, int flags);
 int         b2s_spmv_plan_destroy(void* plan);
 int         b2s_spmv_plan_info(const void* plan, int64_t* out4_host);
 
@@ -261,6 +266,12 @@ int         b2s_peer_check(void* own_buf_dev, void* stream, int64_t* error_out_h
 /* dst[i] = src[i] for i in [0,n) elements of type vt where src is a (possibly peer) device
  * pointer; 128-bit loads when both are 16-byte aligned. */
 int         b2s_copy(int vt, int64_t n, void* dst, const void* src, void* stream);
+
+/* ---- measurement probe -------------------------------------------------------------------------------------
+ * ngathers independent reads x[hash(i) mod ncols] (16 in flight per thread, nothing else read or written): the gather
+ * rate the memory system sustains for the access pattern of a uniformly random CSR SpMV (BASELINE config 4).  Timed
+ * by bench.py beside the R32 product; not used by any product path. */
+int         b2s_probe_gather(int vt, int64_t ncols, int64_t ngathers, const void* x_dev, void* out_dev, void* stream);
 
 #ifdef __cplusplus
 }

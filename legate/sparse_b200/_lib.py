@@ -29,6 +29,8 @@ SIGNATURES = {
     "b2s_spmv_plan_bytes": (c_i64, [c_i32, c_i64, c_i64]),
     "b2s_spmv_plan_create": (c_i32, [c_i32, c_i32, c_i32, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp,
                                      ctypes.POINTER(c_vp)]),
+    "b2s_spmv_plan_create_ex": (c_i32, [c_i32, c_i32, c_i32, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp,
+                                        ctypes.POINTER(c_vp), c_i32]),
     "b2s_spmv_plan_destroy": (c_i32, [c_vp]),
     "b2s_spmv_plan_info": (c_i32, [c_vp, c_vp]),
     "b2s_spmv_csr": (c_i32, [c_i32, c_i32, c_i32, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
@@ -67,6 +69,7 @@ SIGNATURES = {
     "b2s_ipc_open": (c_i32, [c_vp, ctypes.POINTER(c_vp)]),
     "b2s_ipc_close": (c_i32, [c_vp]),
     "b2s_copy": (c_i32, [c_i32, c_i64, c_vp, c_vp, c_vp]),
+    "b2s_probe_gather": (c_i32, [c_i32, c_i64, c_i64, c_vp, c_vp, c_vp]),
     # tuning hooks (not in the public header)
     "b2s_spmv_set_config": (c_i32, [c_i32, c_i32]),
     "b2s_spmv_get_config": (c_i32, []),

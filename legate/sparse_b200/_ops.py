@@ -82,17 +82,18 @@ def _plan_handle(plan):
     return None if plan is None else plan.handle
 
 
-def spmv_plan(indptr: torch.Tensor, indices: torch.Tensor, shape, nnz: int, vdtype) -> SpmvPlan:
-    """Build the SpMV plan for a CSR structure (tile boundaries + kernel choice)."""
+def spmv_plan(indptr: torch.Tensor, indices: torch.Tensor, shape, nnz: int, vdtype, tma_only: bool = False) -> SpmvPlan:
+    """Build the SpMV plan for a CSR structure (tile boundaries + kernel choice).  `tma_only`: the plan must use the
+    TMA tile kernel (needed by spmv_add / spmv_fused)."""
     _chk_dev(indptr, indices)
     vt = vt_code(vdtype)
     nrows, ncols = shape
     nbytes = int(L.b2s_spmv_plan_bytes(vt, nrows, nnz))
     buf = torch.empty(max(nbytes, 16) // 4, dtype=torch.int32, device=indptr.device)
     out = _lib.c_vp()
-    _lib.check(L.b2s_spmv_plan_create(vt, idx_code(indices.dtype), idx_code(indptr.dtype), nrows, ncols, nnz,
-                                      ptr(indptr), ptr(indices), ptr(buf), _stream(), ctypes.byref(out)),
-               "b2s_spmv_plan_create")
+    _lib.check(L.b2s_spmv_plan_create_ex(vt, idx_code(indices.dtype), idx_code(indptr.dtype), nrows, ncols, nnz,
+                                         ptr(indptr), ptr(indices), ptr(buf), _stream(), ctypes.byref(out),
+                                         1 if tma_only else 0), "b2s_spmv_plan_create")
     return SpmvPlan(int(out.value), buf)
 
 

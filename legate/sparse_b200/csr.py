@@ -141,6 +141,10 @@ class csr_array:
     def data(self, value):
         self._data = to_device(value)
         self.dtype = numpy_dtype(self._data.dtype)
+        # derived matrices (promoted copy, real expansion of complex values, transpose) follow the values
+        self.__dict__.pop("_promo_cache", None)
+        self.__dict__.pop("_expansion", None)
+        self.__dict__.pop("_transposed", None)
 
     @property
     def indices(self):
@@ -258,15 +262,18 @@ class csr_array:
         return to_device(self.to_scipy_sparse_csr().diagonal())
 
     # -- the hot path -----------------------------------------------------------------------------------
-    def _get_plan(self):
+    def _get_plan(self, tma_only: bool = False):
         """Tile plan for the SpMV kernel, built once per structure and cached (the reference caches
-        its image partitions per store the same way, sparse/partition.py:96-120)."""
+        its image partitions per store the same way, sparse/partition.py:96-120).  `tma_only`: the plan must
+        launch the TMA tile kernel (accumulating / exchange-fused products); sticky once requested."""
         from . import _lib
 
+        tma_only = bool(tma_only or getattr(self, "_plan_tma_only", False))
+        self._plan_tma_only = tma_only
         key = (self._indptr.data_ptr(), self._indices.data_ptr(), int(_lib.lib.b2s_spmv_get_config()),
-               self.dtype.itemsize, self.nnz)
+               self.dtype.itemsize, self.nnz, tma_only)
         if self._plan is None or self._plan_key != key:
-            self._plan = _ops.spmv_plan(self._indptr, self._indices, self.shape, self.nnz, self.dtype)
+            self._plan = _ops.spmv_plan(self._indptr, self._indices, self.shape, self.nnz, self.dtype, tma_only=tma_only)
             self._plan_key = key
         return self._plan
 
@@ -277,8 +284,9 @@ class csr_array:
             return self
         cache = self.__dict__.setdefault("_promo_cache", {})
         hit = cache.get(common)
-        if hit is None or hit[0] != self._data.data_ptr():
-            cache[common] = (self._data.data_ptr(), self.astype(common, copy=False))
+        stamp = (self._data.data_ptr(), self._data._version)   # in-place edits of .data keep the pointer
+        if hit is None or hit[0] != stamp:
+            cache[common] = (stamp, self.astype(common, copy=False))
         return cache[common][1]
 
     def _dot_host_pipelined(self, x: np.ndarray, out, plan):
@@ -309,7 +317,7 @@ class csr_array:
         2c, 2c+1.  Built once per matrix with tensor ops and cached, so a complex SpMV is ONE launch of the real
         SpMV kernel on interleaved (re, im) storage -- which is exactly how complex vectors sit in memory."""
         hit = self.__dict__.get("_expansion")
-        key = (self._data.data_ptr(), self._indptr.data_ptr(), np.dtype(rdt))
+        key = (self._data.data_ptr(), self._data._version, self._indptr.data_ptr(), np.dtype(rdt))
         if hit is not None and hit[0] == key:
             return hit[1]
         m, n = self.shape
@@ -522,7 +530,7 @@ class csr_array:
         if other.ndim != 2:
             raise NotImplementedError
         assert other.shape[1] == self.shape[0]
-        key = (self._indptr.data_ptr(), self._indices.data_ptr(), self._data.data_ptr(), self.nnz)
+        key = (self._indptr.data_ptr(), self._indices.data_ptr(), self._data.data_ptr(), self._data._version, self.nnz)
         if getattr(self, "_transposed", None) is None or self._transposed[0] != key:
             self._transposed = (key, self.transpose())
         At = self._transposed[1]

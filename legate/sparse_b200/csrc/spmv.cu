@@ -185,8 +185,9 @@ int64_t b2s_spmv_plan_tiles(int vt, int64_t nrows, int64_t nnz) {
   // upper bound over the configurations plan_create may pick (it decides after sampling the matrix)
   int64_t m = 0;
   const int forced = g_cfg.load();
-  const int cands[3] = {forced >= 0 ? forced : (vt == B2S_F32 ? kDefaultCfgF32 : kDefaultCfgF64),
-                        vt == B2S_F32 ? kScatterCfgF32 : kScatterCfgF64, vt == B2S_F32 ? kDefaultCfgF32 : kDefaultCfgF64};
+  const int cands[4] = {forced >= 0 ? forced : (vt == B2S_F32 ? kDefaultCfgF32 : kDefaultCfgF64),
+                        vt == B2S_F32 ? kScatterCfgF32 : kScatterCfgF64, vt == B2S_F32 ? kDefaultCfgF32 : kDefaultCfgF64,
+                        kScatterCfgF32};
   for (int c : cands) { const int64_t t = tiles_for(c, vt, nrows, nnz); m = t > m ? t : m; }
   return m;
 }
@@ -196,8 +197,8 @@ int64_t b2s_spmv_plan_bytes(int vt, int64_t nrows, int64_t nnz) {
   return (b2s_spmv_plan_tiles(vt, nrows, nnz) + 2) * (int64_t)sizeof(PlanEntry);
 }
 
-int b2s_spmv_plan_create(int vt, int it, int pt, int64_t nrows, int64_t ncols, int64_t nnz, const void* indptr,
-                         const void* indices, void* plan_buf, void* stream, void** plan_out) {
+static int plan_create_impl(int vt, int it, int pt, int64_t nrows, int64_t ncols, int64_t nnz, const void* indptr,
+                            const void* indices, void* plan_buf, void* stream, void** plan_out, int flags) {
   B2S_CHECK_ARG(plan_out != nullptr, "plan_out is NULL");
   *plan_out = nullptr;
   if (int rc = check_common(vt, it, pt, nrows, ncols, nnz, indptr, indices, indices, plan_out, plan_out)) return rc;
@@ -227,7 +228,10 @@ int b2s_spmv_plan_create(int vt, int it, int pt, int64_t nrows, int64_t ncols, i
   // the deep-gather tile shapes are for scattered LONG rows; scattered short rows (e.g. one column block of a
   // column-blocked random shard, ~4 entries per row) take the one-lane-per-row path of the default shape
   const bool likely_short = nnz <= 8 * nrows;
-  const int cfg = resolve_cfg(vt, scattered && !likely_short);
+  int cfg = resolve_cfg(vt, scattered && !likely_short);
+  // B2S_PLAN_TMA_ONLY: the caller needs the TMA tile kernel (y += A x, fused exchange): swap an LDG-kind choice
+  // for the deep-gather TMA shape
+  if ((flags & B2S_PLAN_TMA_ONLY) && kCfgs[cfg].kind != 1) cfg = kScatterCfgF32;
   const int64_t ntiles = tiles_for(cfg, vt, nrows, nnz);
   // 2. tile boundaries + row-shape codes for the chosen tile shape
   if (ntiles > 0) {
@@ -301,6 +305,16 @@ int b2s_spmv_plan_create(int vt, int it, int pt, int64_t nrows, int64_t ncols, i
   }
   *plan_out = h;
   return B2S_OK;
+}
+
+int b2s_spmv_plan_create(int vt, int it, int pt, int64_t nrows, int64_t ncols, int64_t nnz, const void* indptr,
+                         const void* indices, void* plan_buf, void* stream, void** plan_out) {
+  return plan_create_impl(vt, it, pt, nrows, ncols, nnz, indptr, indices, plan_buf, stream, plan_out, 0);
+}
+
+int b2s_spmv_plan_create_ex(int vt, int it, int pt, int64_t nrows, int64_t ncols, int64_t nnz, const void* indptr,
+                            const void* indices, void* plan_buf, void* stream, void** plan_out, int flags) {
+  return plan_create_impl(vt, it, pt, nrows, ncols, nnz, indptr, indices, plan_buf, stream, plan_out, flags);
 }
 
 /* Row chunks of a plan for pipelined host<->device products: out = nchunks x {tile_lo, tile_hi, row_lo, row_hi,

@@ -133,22 +133,34 @@ class PeerComm:
         self.header = int(_lib.lib.b2s_peer_header_bytes())
         self.x_elems = int(x_elems)
         nbytes = self.header + (self.x_elems + 8) * self.dtype.itemsize
-        self.own = _ops.ipc_alloc(nbytes)
-        handle = _ops.ipc_export(self.own)
+        # Every rank takes part in every collective below even if one of its own steps fails (`ok` is agreed on by
+        # the caller with an all-reduce, which is also the barrier that orders the mappings before first use).
+        self.ok = True
+        self.own, self.peers, self._opened = 0, [], []
+        self.x_base = self._keep = None
+        handle = None
+        try:
+            self.own = _ops.ipc_alloc(nbytes)
+            handle = _ops.ipc_export(self.own)
+        except Exception:
+            self.ok = False
         handles = [None] * nranks
         dist.all_gather_object(handles, handle, group=group)
-        self.peers = []
-        self._opened = []
-        for q in range(nranks):
-            if q == rank:
-                self.peers.append(self.own)
-            else:
-                p = _ops.ipc_open(handles[q])
-                self._opened.append(p)
-                self.peers.append(p)
-        self._keep = _RawCudaBuffer(self.own + self.header, self.x_elems + 8, self.dtype)
-        self.x_base = torch.as_tensor(self._keep, device=runtime.device)
-        dist.barrier(group=group)
+        if self.ok and all(h is not None for h in handles):
+            try:
+                for q in range(nranks):
+                    if q == rank:
+                        self.peers.append(self.own)
+                    else:
+                        p = _ops.ipc_open(handles[q])
+                        self._opened.append(p)
+                        self.peers.append(p)
+                self._keep = _RawCudaBuffer(self.own + self.header, self.x_elems + 8, self.dtype)
+                self.x_base = torch.as_tensor(self._keep, device=runtime.device)
+            except Exception:
+                self.ok = False
+        else:
+            self.ok = False
 
     def allreduce(self, t: torch.Tensor) -> torch.Tensor:
         return _ops.peer_allreduce(t, self.rank, self.peers)
@@ -381,11 +393,8 @@ class dist_csr_array:
         pc = self._peer.get(key)
         if pc is None:
             n = max(self.col_plan.padded, 1)
-            try:
-                pc = PeerComm(n, key, self.rank, self.nranks, self.group)
-                ok = 1
-            except Exception:  # no peer access between some pair of GPUs, IPC refused, out of memory ...
-                pc, ok = None, 0
+            pc = PeerComm(n, key, self.rank, self.nranks, self.group)
+            ok = 1 if pc.ok else 0   # no peer access between some pair of GPUs, IPC refused, out of memory ...
             flag = torch.tensor([ok], dtype=torch.int32, device=self._comm_device())
             dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
             if int(flag.item()) == 0:      # some rank failed: everybody falls back to NCCL, consistently
@@ -535,7 +544,7 @@ class dist_csr_array:
                 for q, Bq in blocks.items():
                     if q == self.rank or Bq is None:
                         continue
-                    pl = Bq._get_plan()
+                    pl = Bq._get_plan(tma_only=True)
                     if not pl.tma:
                         raise RuntimeError("column block without a TMA tile plan")
                     descs[q] = _ops.fuse_desc([(0, pl.tiles)], 0, flags=[pc.flag_local(q)], epoch_ctr=pc.epoch_ctr,
@@ -849,7 +858,8 @@ def cg(A: dist_csr_array, b_local, x0_local=None, tol=1e-08, maxiter=None, callb
     n_global = A.shape[0]
     if maxiter is None:
         maxiter = n_global * 10
-    dt = np.result_type(np.float64 if x0_local is None else numpy_dtype(x0_local.dtype), numpy_dtype(b_local.dtype))
+    dt = np.result_type(np.float64 if x0_local is None else numpy_dtype(x0_local.dtype), numpy_dtype(b_local.dtype),
+                        A.local.dtype)   # never narrow the matrix (reference: r = b - A x in the promoted type)
     Al = A.local if A.local.dtype == dt else A.local._promoted(dt)  # same structure, promoted values
     b = to_device(b_local, dtype=dt).reshape(-1)
     n = b.shape[0]

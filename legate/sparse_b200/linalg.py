@@ -213,7 +213,10 @@ def cg(A, b, x0=None, tol=1e-08, maxiter=None, M=None, callback=None, atol=None,
     work_dtype = np.float64 if x0 is None else numpy_dtype(x0.dtype)
     if work_dtype not in (np.dtype(np.float32), np.dtype(np.float64)):
         work_dtype = np.float64
-    bd = to_device(b, dtype=np.result_type(work_dtype, numpy_dtype(b.dtype))).reshape(-1)
+    wide = [work_dtype, numpy_dtype(b.dtype)]
+    if isinstance(A, csr_array) and np.dtype(A.dtype) in (np.dtype(np.float32), np.dtype(np.float64)):
+        wide.append(A.dtype)   # r = b - A x is computed in the promoted type (reference linalg.py:532): never narrow A
+    bd = to_device(b, dtype=np.result_type(*wide)).reshape(-1)
     work_dtype = numpy_dtype(bd.dtype)
     x = _zeros(n, work_dtype) if x0 is None else to_device(x0, dtype=work_dtype, copy=True).reshape(-1)
 
@@ -280,9 +283,7 @@ class _LocalComm:
 
 def _cg_fused(A: csr_array, b, x, tol, maxiter, callback, conv_test_iters, on_device):
     dt = numpy_dtype(b.dtype)
-    Ad = A._promoted(dt) if A.dtype != dt else A
-    if numpy_dtype(Ad.dtype) != dt:
-        raise NotImplementedError("cg: matrix dtype wider than the work vectors")
+    Ad = A._promoted(dt) if A.dtype != dt else A      # dt >= A.dtype by construction (see cg): a widening cast
     return _cg_fused_loop(Ad, _LocalComm(), b, x, tol, maxiter, callback, conv_test_iters, on_device)
 
 

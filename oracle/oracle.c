@@ -53,6 +53,23 @@ void orc_set_num_threads(int n)
 #endif
 }
 
+/* Copy `nbytes` from src to dst page by page inside a static OpenMP loop, so that a freshly allocated dst is
+ * FIRST TOUCHED by all threads (pages spread over the NUMA nodes of the box instead of all landing on the node of
+ * the one Python thread that filled the source).  Measurement hygiene for bench.py's CPU arms; no reference
+ * counterpart (Legion places instances per processor). */
+#include <string.h>
+void orc_parallel_copy(void* dst, const void* src, int64_t nbytes)
+{
+  const int64_t page = 1 << 16;
+  const int64_t npages = (nbytes + page - 1) / page;
+  _Pragma("omp parallel for schedule(static)")
+  for (int64_t p = 0; p < npages; p++) {
+    const int64_t off = p * page;
+    const int64_t len = (off + page <= nbytes) ? page : nbytes - off;
+    memcpy((char*)dst + off, (const char*)src + off, (size_t)len);
+  }
+}
+
 int orc_num_threads(void)
 {
 #ifdef _OPENMP

@@ -76,6 +76,14 @@ def set_num_threads(n: int) -> None:
     lib().orc_set_num_threads(int(n))
 
 
+def first_touch_copy(arr: np.ndarray) -> np.ndarray:
+    """A copy of `arr` whose pages are first touched by all OpenMP threads (bench.py CPU arms)."""
+    arr = np.ascontiguousarray(arr)
+    out = np.empty_like(arr)
+    lib().orc_parallel_copy(_p(out), _p(arr), ctypes.c_int64(arr.nbytes))
+    return out
+
+
 def spmv(indptr, indices, data, x, omp: bool = False, out=None) -> np.ndarray:
     """y = A @ x; A and x are first promoted to a common dtype (sparse/csr.py:493).
     `out` (optional, right dtype/shape) avoids re-allocating y on every call (csr.py:509-513)."""

@@ -43,12 +43,48 @@ def main():
         assert np.allclose(Bm.matvec_global(xb), B @ xb, rtol=1e-12, atol=1e-12), mode
     os.environ["B2S_EXCHANGE"] = "auto"
 
-    # 2./3. with the NVLink peer-memory path (csrc/peer.cu) and with plain NCCL
-    modes = [("1", "1"), ("1", "0"), ("0", "0")]
-    if os.environ.get("B2S_TEST_FUSED_HALO") == "1":   # experimental in-kernel halo wait (b2s_spmv_csr_halo)
-        modes.insert(0, ("1", "fused"))
-    for peer, halo in modes:
+    # 1b. the same two matrices through the FUSED exchange (default on one box): the random one becomes one column
+    # block per source rank (b2s_peer_push + in-kernel arrival waits), the banded one pushes / awaits its halo
+    # inside the SpMV launch.  Vectors change between products, so stale halo data would be caught.
+    assert A.use_fused and Bd.use_fused
+    for M, ref_mat, nn in ((A, S, 5000), (Bd, B, n)):
+        full = M.new_full_vector(np.float64)
+        for rep in range(4):
+            xv = rng.standard_normal(nn)
+            lo_, hi_ = M.my_cols
+            full[lo_:hi_] = torch.from_numpy(xv[lo_:hi_]).cuda()
+            y = M.dot(full)
+            info = M._fused.get((id(M.local), full.data_ptr()))
+            assert info is not None and info["mode"] == ("blocks" if M is A else "halo"), info
+            rl, rh = M.row_plan.rows(rank)
+            assert np.allclose(y.cpu().numpy(), (ref_mat @ xv)[rl:rh], rtol=1e-12, atol=1e-10), (rep, info["mode"])
+        yg = torch.empty_like(y)
+        for rep in range(3):      # graph replay: device-side epochs, new x every time
+            xv = rng.standard_normal(nn)
+            full[lo_:hi_] = torch.from_numpy(xv[lo_:hi_]).cuda()
+            M.dot_graphed(full, yg)
+            assert np.allclose(yg.cpu().numpy(), (ref_mat @ xv)[rl:rh], rtol=1e-12, atol=1e-10), ("graph", rep)
+        M.check_peer()
+    # fp32 column blocks with long scattered rows (R32-like): deep-gather TMA shape per block
+    R = gallery.random_fixed(40000, 40000, 32, np.float32, seed=5).to_scipy_sparse_csr()
+    Rd = bd.dist_csr_array.from_global(R)
+    xr = rng.random(40000).astype(np.float32)
+    fullr = Rd.new_full_vector(np.float32)
+    lo_, hi_ = Rd.my_cols
+    fullr[lo_:hi_] = torch.from_numpy(xr[lo_:hi_]).cuda()
+    yr = Rd.dot_graphed(fullr, torch.empty(Rd.local.shape[0], dtype=torch.float32, device="cuda"))
+    assert Rd._fused[(id(Rd.local), fullr.data_ptr())]["mode"] == "blocks"
+    rl, rh = Rd.row_plan.rows(rank)
+    assert np.allclose(yr.cpu().numpy(), (R @ xr)[rl:rh], rtol=2e-4, atol=2e-4)
+    Rd.check_peer()
+    torch.cuda.synchronize(); dist.barrier()
+    A.close(); Bd.close(); Rd.close()
+
+    # 2./3. fused exchange (default), peer halo kernels, peer all-reduce only, plain NCCL
+    modes = [("1", "1", "0"), ("1", "0", "1"), ("1", "0", "0"), ("0", "0", "0")]
+    for peer, fused, halo in modes:
         os.environ["B2S_PEER"] = peer
+        os.environ["B2S_PEER_FUSED"] = fused
         os.environ["B2S_PEER_HALO"] = halo
         # 2. shards assembled directly (gallery row_lo/row_hi) equal the slices of the global operator
         n1, n2 = 300, 400 * world   # >= 64 tiles per shard so the plan is chunked
@@ -60,12 +96,11 @@ def main():
         Ls = local.to_scipy_sparse_csr()
         assert (Ls != G[lo:hi]).nnz == 0
         Ad = bd.dist_csr_array(local, (N, N))
-        assert Ad.use_peer == (peer == "1") and Ad.use_peer_halo == (halo in ("1", "fused"))
-        assert Ad.fused_halo == (halo == "fused")
+        assert Ad.use_peer == (peer == "1") and Ad.use_peer_halo == (halo == "1") and Ad.use_fused == (peer == "1" and fused == "1")
         assert Ad.exchange_mode == "p2p" and Ad.recv_elems <= 2 * n1
         for rep in range(3):  # repeated exchanges exercise the epoch / ack protocol
             xg = rng.standard_normal(N)
-            assert np.allclose(Ad.matvec_global(xg), G @ xg, rtol=1e-12, atol=1e-6), (peer, rep)
+            assert np.allclose(Ad.matvec_global(xg), G @ xg, rtol=1e-12, atol=1e-6), (peer, fused, halo, rep)
         # overlapped (halo exchange || interior tiles) and serialised schedules give identical results
         sched = Ad._overlap_schedule()
         assert sched and len(sched[0]) >= 1 and len(sched[1]) >= 1, sched
@@ -83,7 +118,7 @@ def main():
         xl, iters = bd.cg(Ad, b[lo:hi], tol=1e-8, maxiter=500)
         xs = bd.gather_vector(xl, Ad.row_plan, rank)
         xo, io = orc.cg(lambda v: orc.spmv(G.indptr, G.indices, G.data, v), b, tol=1e-8, maxiter=500)
-        assert iters == io, (peer, iters, io)
+        assert iters == io, (peer, fused, iters, io)
         assert np.allclose(xs, xo, rtol=1e-6, atol=1e-12)
         # scalars all-reduced through peer memory are bit-identical on every rank
         t = torch.tensor([float(rank + 1) * 0.1], dtype=torch.float64, device="cuda")
@@ -105,6 +140,7 @@ def main():
 
     # 4. row-sharded SpGEMM: B all-gathered, C row-sharded with exact structure
     os.environ["B2S_PEER"] = "1"
+    os.environ["B2S_PEER_FUSED"] = "1"
     os.environ["B2S_PEER_HALO"] = "0"
     SA = sp.random(900, 700, density=0.01, random_state=rng, format="csr", dtype=np.float64)
     SB = sp.random(700, 800, density=0.012, random_state=rng, format="csr", dtype=np.float64)

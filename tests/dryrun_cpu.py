@@ -46,9 +46,10 @@ def install():
 
     class FakePlan:
         chunks = []
-        config = rowgroup = uniform = scattered = tiles = 0
+        config = rowgroup = uniform = scattered = tiles = short_rows = tma = 0
+        kernel_name = "oracle"
 
-    def spmv_plan(indptr, indices, shape, nnz, vdtype):
+    def spmv_plan(indptr, indices, shape, nnz, vdtype, tma_only=False):
         return FakePlan()
 
     def spmv(indptr, indices, data, x, y, shape, plan=None):

@@ -464,3 +464,25 @@ def test_r32_full_size_vs_scipy_and_oracle(oracle):
     rhs = (A @ x) + (A @ z)
     scale = float(rhs.abs().max())
     assert float((lhs - rhs).abs().max()) <= 2e-5 * scale
+
+
+def test_inplace_data_edits_invalidate_derived_matrices():
+    """`.data` is a mutable device array (reference csr.py:264-287): after an in-place edit the cached promoted
+    copy (f32 matrix x f64 vector), the cached transpose (dense @ A) and the complex expansion must follow."""
+    S = sp.random(300, 300, density=0.05, random_state=np.random.default_rng(5), format="csr", dtype=np.float32)
+    A = sparse.csr_array(S)
+    x = np.random.default_rng(6).random(300)            # float64 operand -> promoted copy of A
+    X = np.random.default_rng(7).random((4, 300))
+    assert np.allclose(A @ x, S @ x) and np.allclose(X @ A, X @ S.toarray(), rtol=1e-5)
+    A.data *= 2                                          # same tensor, same pointer, new values
+    assert np.allclose(A @ x, 2 * (S @ x)), "stale promoted copy"
+    assert np.allclose(X @ A, 2 * (X @ S.toarray()), rtol=1e-5), "stale transpose"
+    A.data[:] = 1.0
+    ones = sp.csr_array((np.ones_like(S.data), S.indices, S.indptr), shape=S.shape)
+    assert np.allclose(A @ x, ones @ x)
+    C = sparse.csr_array(sp.csr_array((S.data.astype(np.complex128) * (1 + 2j), S.indices, S.indptr), shape=S.shape))
+    z = x + 1j * x[::-1]
+    ref = C.to_scipy_sparse_csr() @ z
+    assert np.allclose(C @ z, ref)
+    C.data *= 1j
+    assert np.allclose(C @ z, 1j * ref), "stale real expansion"

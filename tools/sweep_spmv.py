@@ -55,12 +55,19 @@ def run(name, A, cfgs, waves_list, out):
             _lib.check(_lib.lib.b2s_spmv_set_config(cfg, waves))
             plan = _ops.spmv_plan(A.indptr, A.indices, A.shape, A.nnz, A.dtype)
             plan.set_kernel(False)
-            t_med, t_min = time_spmv(A, x, y, plan)
-            scale = float(yref.abs().max()) + 1e-30
-            ok = bool(((y - yref).abs().max() / scale) < (1e-5 if A.dtype == np.float32 else 1e-12))
-            line = (f"{name:28s} cfg {cfg} waves {waves:2d}  med {t_med*1e6:8.1f} us  min {t_min*1e6:8.1f} us  "
-                    f"{2*A.nnz/t_med/1e9:8.1f} GF/s  {B/t_med/1e9:7.1f} GB/s  frac {B/t_med/1e9/PEAK:.3f}  ok={ok}")
-            print(line); out.write(line + "\n"); out.flush()
+            flavors = [None]
+            if plan.tma and os.environ.get("SWEEP_FLAVORS"):
+                flavors = [None] + [int(f) for f in os.environ["SWEEP_FLAVORS"].split(",")]
+            for fl in flavors:
+                if fl is not None:
+                    plan.set_flavor(fl)
+                t_med, t_min = time_spmv(A, x, y, plan)
+                scale = float(yref.abs().max()) + 1e-30
+                ok = bool(((y - yref).abs().max() / scale) < (1e-5 if A.dtype == np.float32 else 1e-12))
+                tag = "auto:" + ("short" if plan.short_rows else "uni" if plan.uniform else "gen") if fl is None else f"flavor{fl}"
+                line = (f"{name:28s} cfg {cfg} waves {waves:2d} {tag:10s} med {t_med*1e6:8.1f} us  min {t_min*1e6:8.1f} us  "
+                        f"{2*A.nnz/t_med/1e9:8.1f} GF/s  {B/t_med/1e9:7.1f} GB/s  frac {B/t_med/1e9/PEAK:.3f}  ok={ok}")
+                print(line); out.write(line + "\n"); out.flush()
     _lib.check(_lib.lib.b2s_spmv_set_config(-1, 0))
     auto = A._get_plan()
     t_med, t_min = time_spmv(A, x, y, auto)
