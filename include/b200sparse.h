@@ -267,6 +267,23 @@ int         b2s_peer_check(void* own_buf_dev, void* stream, int64_t* error_out_h
  * pointer; 128-bit loads when both are 16-byte aligned. */
 int         b2s_copy(int vt, int64_t n, void* dst, const void* src, void* stream);
 
+/* ---- multi-GPU: NCCL communicator owned by the library -----------------------------------------
+ * For hosts without torch.distributed (and for multi-node runs): the library binds NCCL at run time (dlopen of
+ * libnccl.so.2, the one already in the process if any) and owns the communicator.  The reference uses NCCL
+ * natively the same way (src/sparse/sort/sort.cu:163-322; communicator pre-initialised at sparse/runtime.py:84-87).
+ *   b2s_comm_unique_id    : rank 0 fills 128 bytes (ncclUniqueId); the host ships them to every rank
+ *   b2s_comm_init         : collective; communicator on the calling thread's current device
+ *   b2s_allgather_x       : x_full[q*n_local ..] = rank q's x_local (equal shards; in place allowed) -- the
+ *                           exchange before a row-sharded SpMV (sparse/csr.py:930-968)
+ *   b2s_allreduce_scalars : in-place fp64 sum of the CG scalars (sparse/linalg.py:540,550,561)
+ * Both collectives are enqueued on `stream` and do not synchronise. */
+int         b2s_comm_nccl_version(void);      /* e.g. 22703; 0 = libnccl could not be loaded */
+int         b2s_comm_unique_id(void* id128_host_out);
+int         b2s_comm_init(int rank, int nranks, const void* nccl_unique_id_128B, void** comm_out);
+int         b2s_comm_destroy(void* comm);
+int         b2s_allgather_x(void* comm, int vt, const void* x_local, int64_t n_local, void* x_full, void* stream);
+int         b2s_allreduce_scalars(void* comm, void* scalars_dev, int count, void* stream);
+
 /* ---- measurement probe -------------------------------------------------------------------------------------
  * ngathers independent reads x[hash(i) mod ncols] (16 in flight per thread, nothing else read or written): the gather
  * rate the memory system sustains for the access pattern of a uniformly random CSR SpMV (BASELINE config 4).  Timed

@@ -69,6 +69,12 @@ SIGNATURES = {
     "b2s_ipc_open": (c_i32, [c_vp, ctypes.POINTER(c_vp)]),
     "b2s_ipc_close": (c_i32, [c_vp]),
     "b2s_copy": (c_i32, [c_i32, c_i64, c_vp, c_vp, c_vp]),
+    "b2s_comm_nccl_version": (c_i32, []),
+    "b2s_comm_unique_id": (c_i32, [c_vp]),
+    "b2s_comm_init": (c_i32, [c_i32, c_i32, c_vp, ctypes.POINTER(c_vp)]),
+    "b2s_comm_destroy": (c_i32, [c_vp]),
+    "b2s_allgather_x": (c_i32, [c_i32, c_i32, c_vp, c_i64, c_vp, c_vp]),
+    "b2s_allreduce_scalars": (c_i32, [c_vp, c_vp, c_i32, c_vp]),
     "b2s_probe_gather": (c_i32, [c_i32, c_i64, c_i64, c_vp, c_vp, c_vp]),
     # tuning hooks (not in the public header)
     "b2s_spmv_set_config": (c_i32, [c_i32, c_i32]),
