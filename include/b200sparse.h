@@ -218,6 +218,11 @@ int         b2s_csr_diagonal(int vt, int it, int pt, int64_t nrows, const void* 
  * `dense_ws`: device buffer of b2s_spgemm_dense_bytes(vt, n, info_host[2]) bytes (may be
  *   NULL when that is 0) -- the parallel form of the reference's per-thread `workspace` /
  *   `already_set` arrays (spgemm_csr_csr_csr.cc:100-118, _omp.cc:92-167). */
+/* work_out[i] (int64, device) = A*B products of row i = upper bound of nnz(C[i,:]): lets a caller cut A into row chunks
+ * whose output fits its memory budget and run the two passes chunk by chunk (a row slice of a CSR matrix is again a
+ * CSR matrix: indptr slice rebased, contiguous indices/vals slice) -- how R-MAT scale 22 fits one GPU. */
+int         b2s_spgemm_row_work(int pt, int64_t m, const void* a_indptr, const int32_t* a_indices,
+                                const void* b_indptr, int64_t* work_out, void* stream);
 int64_t     b2s_spgemm_scratch_bytes(int64_t m, int64_t n);
 int64_t     b2s_spgemm_dense_bytes(int vt, int64_t n, int64_t dense_rows);
 int         b2s_spgemm_csr_symbolic(int pt, int64_t m, int64_t k, int64_t n,

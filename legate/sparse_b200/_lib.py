@@ -52,6 +52,7 @@ SIGNATURES = {
     "b2s_nrm2": (c_i32, [c_i32, c_i64, c_vp, c_vp, c_vp, c_vp]),
     "b2s_cg_update_xr": (c_i32, [c_i32, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "b2s_csr_diagonal": (c_i32, [c_i32, c_i32, c_i32, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "b2s_spgemm_row_work": (c_i32, [c_i32, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "b2s_spgemm_scratch_bytes": (c_i64, [c_i64, c_i64]),
     "b2s_spgemm_dense_bytes": (c_i64, [c_i32, c_i64, c_i64]),
     "b2s_spgemm_csr_symbolic": (c_i32, [c_i32, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),

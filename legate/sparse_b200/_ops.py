@@ -243,6 +243,17 @@ def spgemm(a_indptr, a_indices, a_data, b_indptr, b_indices, b_data, shape_a, sh
     return c_indptr, c_indices, c_data, {"nnz": nnz, "products": products, "dense_rows": dense_rows}
 
 
+def spgemm_row_work(a_indptr, a_indices, b_indptr) -> torch.Tensor:
+    """Products per row of A @ B (int64 device tensor of len m): the chunk planner's measure of work / output size."""
+    _chk_dev(a_indptr, a_indices, b_indptr)
+    assert a_indices.dtype == torch.int32 and a_indptr.dtype == b_indptr.dtype
+    m = a_indptr.shape[0] - 1
+    out = torch.empty(max(m, 1), dtype=torch.int64, device=a_indptr.device)
+    _lib.check(L.b2s_spgemm_row_work(idx_code(a_indptr.dtype), m, ptr(a_indptr), ptr(a_indices), ptr(b_indptr), ptr(out),
+                                     _stream()), "b2s_spgemm_row_work")
+    return out[:m]
+
+
 # ---- CUDA IPC / NVLink peer exchange -----------------------------------------------------------------------
 def ipc_alloc(nbytes: int) -> int:
     out = _lib.c_vp()

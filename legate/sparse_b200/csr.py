@@ -583,3 +583,64 @@ def spgemm_csr_csr_csr(A: csr_array, B: csr_array) -> csr_array:
     C = csr_array._from_parts(c_ptr, c_idx, c_val, (A.shape[0], B.shape[1]))
     C.spgemm_info = info
     return C
+
+
+def spgemm_chunked(A: csr_array, B: csr_array, max_products: int = 1 << 31, keep: bool = False, on_chunk=None):
+    """C = A @ B computed in ROW CHUNKS of A so that the output of one chunk fits a memory budget -- how BASELINE
+    config 5 (R-MAT scale 22 squared: nnz(C) is hundreds of GB) runs on one 180 GB GPU.
+
+    A cheap pass counts the products of every row (`b2s_spgemm_row_work`, an upper bound of the row's nnz); rows are
+    cut greedily into ranges of <= `max_products` products (a single heavier row is its own chunk); each range is a
+    CSR matrix in its own right (indptr slice rebased, contiguous indices / vals slice) and goes through the two-pass
+    SpGEMM of `spgemm_csr_csr_csr`.  A chunk of C is handed to `on_chunk(row_lo, row_hi, C_chunk)` and dropped, or
+    kept and concatenated when `keep` (only if everything fits).  The reference sizes its output with a blocking
+    `int(nnz)` and a single allocation (sparse/csr.py:1442); it cannot run this case on one GPU either.
+
+    Returns (C or None, stats) with stats = {chunks, products, nnz, rows_per_chunk, checksum (sum of all values,
+    fp64), max_chunk_nnz}."""
+    runtime.require_cuda("spgemm_chunked")
+    assert A.shape[1] == B.shape[0]
+    m = A.shape[0]
+    a_idx = A._indices if A._indices.dtype == torch.int32 else A._indices.to(torch.int32)
+    a_ptr, b_ptr = A._indptr, B._indptr
+    if a_ptr.dtype != b_ptr.dtype:
+        a_ptr, b_ptr = a_ptr.to(torch.int64), b_ptr.to(torch.int64)
+    work = _ops.spgemm_row_work(a_ptr, a_idx, b_ptr)
+    cum = torch.cumsum(work, 0).cpu().numpy() if m else np.zeros(0, dtype=np.int64)
+    cuts = [0]
+    while cuts[-1] < m:
+        base = int(cum[cuts[-1] - 1]) if cuts[-1] > 0 else 0
+        nxt = int(np.searchsorted(cum, base + int(max_products), side="right"))
+        cuts.append(min(max(nxt, cuts[-1] + 1), m))
+    del work
+    parts = []
+    stats = {"chunks": 0, "products": int(cum[-1]) if m else 0, "nnz": 0, "checksum": 0.0, "max_chunk_nnz": 0,
+             "rows_per_chunk": []}
+    ip_host = A._indptr.cpu().numpy() if m else np.zeros(1, dtype=np.int64)
+    for lo, hi in zip(cuts[:-1], cuts[1:]):
+        klo, khi = int(ip_host[lo]), int(ip_host[hi])
+        Ac = csr_array._from_parts((A._indptr[lo : hi + 1] - klo).contiguous(), A._indices[klo:khi], A._data[klo:khi],
+                                   (hi - lo, A.shape[1]))
+        Cc = spgemm_csr_csr_csr(Ac, B)
+        stats["chunks"] += 1
+        stats["nnz"] += Cc.nnz
+        stats["max_chunk_nnz"] = max(stats["max_chunk_nnz"], Cc.nnz)
+        stats["rows_per_chunk"].append(hi - lo)
+        stats["checksum"] += float(Cc._data.sum(dtype=torch.float64)) if Cc.nnz else 0.0
+        if on_chunk is not None:
+            on_chunk(lo, hi, Cc)
+        if keep:
+            parts.append(Cc)
+        del Cc, Ac
+    C = None
+    if keep:
+        ptrs, off = [torch.zeros(1, dtype=torch.int64, device=A.device)], 0
+        for P_ in parts:
+            ptrs.append(P_._indptr[1:].to(torch.int64) + off)
+            off += P_.nnz
+        indptr = torch.cat(ptrs)
+        if off <= _INT32_MAX and not _force_wide():
+            indptr = indptr.to(torch.int32)
+        C = csr_array._from_parts(indptr, torch.cat([P_._indices for P_ in parts]) if parts else A._indices[:0],
+                                  torch.cat([P_._data for P_ in parts]) if parts else A._data[:0], (m, B.shape[1]))
+    return C, stats

@@ -727,6 +727,24 @@ int64_t b2s_spgemm_dense_bytes(int vt, int64_t n, int64_t dense_rows) {
   return slots * per;
 }
 
+/* work_out[i] = number of A*B products of row i (= upper bound of its structural nnz), i < m; enqueued on `stream`.
+ * The row-chunked driver (csr.spgemm_chunked) cuts A into row ranges whose product count fits a memory budget. */
+int b2s_spgemm_row_work(int pt, int64_t m, const void* a_indptr, const int32_t* a_indices, const void* b_indptr,
+                        int64_t* work_out, void* stream) {
+  B2S_CHECK_ARG(pt == B2S_I32 || pt == B2S_I64, "bad indptr type code %d", pt);
+  B2S_CHECK_ARG(m >= 0 && a_indptr && b_indptr && (m == 0 || work_out), "bad arguments");
+  if (m == 0) return B2S_OK;
+  DeviceProps pr;
+  if (int rc = get_props(&pr)) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  int64_t want = (m * 32 + 255) / 256, cap = (int64_t)pr.sm_count * 32;
+  unsigned grid = (unsigned)(want < cap ? want : cap);
+  if (pt == B2S_I32) spgemm_ub_kernel<int32_t><<<grid, 256, 0, st>>>(m, (const int32_t*)a_indptr, a_indices, (const int32_t*)b_indptr, (long long*)work_out);
+  else               spgemm_ub_kernel<int64_t><<<grid, 256, 0, st>>>(m, (const int64_t*)a_indptr, a_indices, (const int64_t*)b_indptr, (long long*)work_out);
+  B2S_LAUNCH_CHECK();
+  return B2S_OK;
+}
+
 int b2s_spgemm_csr_symbolic(int pt, int64_t m, int64_t k, int64_t n, const void* a_indptr, const int32_t* a_indices,
                             const void* b_indptr, const int32_t* b_indices, int64_t* c_indptr, int64_t* info_host,
                             void* scratch, void* stream) {

@@ -133,3 +133,32 @@ def test_pde_example_problem():
     x, iters = linalg.cg(A, b, tol=1e-10)
     assert iters == 300
     assert np.allclose(A @ x, b)
+
+
+def test_pde4096_full_size_vs_scipy():
+    """BASELINE config 3 at full size: examples/pde.py -nx 4096 -ny 4096 (N = 16,760,836, nnz = 83,787,804), the fused
+    device CG against scipy's cg on the same matrix after the SAME 300 iterations (absolute tolerance 1e-10 is never
+    met, reference semantics rtol=0): true residual ||b - A x|| and x agree to 1e-6 relative (north-star bar)."""
+    import scipy.sparse.linalg as spla
+    import torch
+
+    from legate.sparse_b200 import gallery
+
+    g1 = 4094
+    A = gallery.laplacian_5pt(g1, g1, np.float64)
+    N = A.shape[0]
+    assert N == 16760836 and A.nnz == 83787804
+    b = torch.ones(N, dtype=torch.float64, device="cuda")
+    x, iters = linalg.cg(A, b, tol=1e-10, maxiter=300)
+    assert iters == 300
+    res_gpu = float(torch.linalg.vector_norm(b - (A @ x)))
+    S = sp.csr_array((A.data.cpu().numpy(), A.indices.cpu().numpy(), A.indptr.cpu().numpy()), shape=A.shape)
+    bh = np.ones(N)
+    xs, info = spla.cg(S, bh, rtol=0.0, atol=1e-10, maxiter=300)
+    assert info == 300                                   # scipy also ran out of iterations: same count
+    res_cpu = float(np.linalg.norm(bh - S @ xs))
+    xg = x.cpu().numpy()
+    assert abs(res_gpu - res_cpu) <= 1e-6 * res_cpu, (res_gpu, res_cpu)
+    assert np.linalg.norm(xg - xs) <= 1e-6 * np.linalg.norm(xs)
+    # the device product itself against scipy on the iterate (1e-6 of the row scale would be the bar; this is ~1e-15)
+    assert np.allclose((A @ x).cpu().numpy(), S @ xg, rtol=1e-12, atol=1e-12 * float(np.abs(S.data).max()))
