@@ -483,6 +483,49 @@ def _r32_case(torch, gallery, _ops, peak, dtype, reps=20):
     return out
 
 
+def _spgemm_rmat_case(torch, gallery, peak, args):
+    """BASELINE config 5: C = A @ A for an R-MAT graph (a,b,c,d = .57,.19,.19,.05), scale 22, edge factor 16, fp64.
+    nnz(C) is hundreds of GB, so the product runs through the row-chunked driver (csr.spgemm_chunked): chunks of
+    <= 1.5e9 products, each through the two-pass SpGEMM, reduced to (nnz, checksum) and dropped.  scipy on the host:
+    a BOUNDED SAMPLE -- 4096 random rows of A times A -- scaled by the share of products (scipy's full product would
+    take hours and ~1 TB).  B = nnz_A*12 + products*12 (B rows streamed per A entry) + nnz_C*12 + indptrs."""
+    from legate.sparse_b200.csr import spgemm_chunked
+
+    scale = int(os.environ.get("B2S_BENCH_RMAT_SCALE", "22"))
+    ef = 16
+    A = gallery.rmat(scale, ef, seed=42)
+    n = A.shape[0]
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    _, st = spgemm_chunked(A, A, max_products=int(1.5e9), keep=False)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    byts = A.nnz * 12 + st["products"] * 12 + st["nnz"] * 12 + 3 * 8 * (n + 1)
+    out = {"scale": scale, "edge_factor": ef, "rows": n, "nnz_a": A.nnz, "products": st["products"], "nnz_c": st["nnz"],
+           "chunks": st["chunks"], "max_chunk_nnz": st["max_chunk_nnz"], "ms": dt * 1e3,
+           "gflops": 2.0 * st["products"] / dt / 1e9, "model_bytes": byts, "B_over_t_frac": byts / dt / 1e9 / peak,
+           "checksum": st["checksum"], "c_bytes_if_kept": st["nnz"] * 12}
+    if not args.no_cpu:
+        import scipy.sparse as sp
+
+        S = sp.csr_array((A.data.cpu().numpy(), A.indices.cpu().numpy(), A.indptr.cpu().numpy()), shape=A.shape)
+        rows = np.sort(np.random.default_rng(3).choice(n, size=min(4096, n), replace=False))
+        lens = np.diff(S.indptr)
+        sample_products = int(lens[S.indices[np.concatenate([np.arange(S.indptr[r], S.indptr[r + 1]) for r in rows])]].sum())
+        Ssub = S[rows]
+        t0 = time.perf_counter()
+        Csub = Ssub @ S
+        ts = time.perf_counter() - t0
+        out.update({"scipy_sample_rows": int(rows.shape[0]), "scipy_sample_products": sample_products,
+                    "scipy_sample_ms": ts * 1e3, "scipy_sample_nnz_c": int(Csub.nnz),
+                    "scipy_ms_extrapolated_by_products": ts * 1e3 * st["products"] / max(sample_products, 1),
+                    "speedup_vs_scipy_extrapolated": (ts * st["products"] / max(sample_products, 1)) / dt})
+        del S, Ssub, Csub
+    del A
+    torch.cuda.empty_cache()
+    return out
+
+
 def other_rows_of_the_path(torch, gallery, peak, args):
     """The other hot-path rows of SURVEY 8 at N=1, so one bench line records them all (bounded: ~1 minute).
     R32: BASELINE config 4 (the north-star shape) fp32 and fp64 with the measured gather ceiling.
@@ -553,6 +596,10 @@ def other_rows_of_the_path(torch, gallery, peak, args):
         del B, C
     except Exception as exc:  # pragma: no cover
         out["spgemm_error"] = repr(exc)
+    try:
+        out["spgemm_rmat"] = _spgemm_rmat_case(torch, gallery, peak, args)
+    except Exception as exc:  # pragma: no cover
+        out["spgemm_rmat_error"] = repr(exc)
     try:
         # SpMM: examples/dot_microbenchmark.py -op spmm -k 32 shape at n = 4M, fp64
         n, k = 4_000_000, 32

@@ -272,6 +272,20 @@ int         b2s_peer_check(void* own_buf_dev, void* stream, int64_t* error_out_h
  * pointer; 128-bit loads when both are 16-byte aligned. */
 int         b2s_copy(int vt, int64_t n, void* dst, const void* src, void* stream);
 
+/* ---- assembly: COO triplets -> CSR, CSR -> CSR of the transpose ------------------------------
+ * Replaces the reference's sort-by-key assembly (sparse/coo.py:233-347 -> src/sparse/sort/sort.cu:124-379,
+ * sorted_coords_to_counts.cu:32, nnz_to_pos base.py:30-48) and its CSR->CSC->transpose route (sparse/csr.py:404-424)
+ * with a counting sort by row (L2 atomics), a scan and a per-row bitonic sort by column: no global sort.  Unique
+ * (row, col) pairs assumed, as in the reference (coo.py:73-76).  `scratch`: b2s_convert_scratch_bytes(nbuckets, pt)
+ * bytes with nbuckets = nrows of the OUTPUT matrix.  Both calls sync the stream once. */
+int64_t     b2s_convert_scratch_bytes(int64_t nbuckets, int pt);
+int         b2s_coo_to_csr(int vt, int it, int pt, int64_t nrows, int64_t nnz, const void* rows, const void* cols,
+                           const void* vals, void* indptr, void* indices, void* vals_out, void* scratch,
+                           int64_t* bad_host, void* stream);
+int         b2s_csr_transpose(int vt, int it, int pt, int64_t nrows, int64_t ncols, int64_t nnz,
+                              const void* indptr, const void* indices, const void* vals,
+                              void* t_indptr, void* t_indices, void* t_vals, void* scratch, void* stream);
+
 /* ---- multi-GPU: NCCL communicator owned by the library -----------------------------------------
  * For hosts without torch.distributed (and for multi-node runs): the library binds NCCL at run time (dlopen of
  * libnccl.so.2, the one already in the process if any) and owns the communicator.  The reference uses NCCL

@@ -70,6 +70,9 @@ SIGNATURES = {
     "b2s_ipc_open": (c_i32, [c_vp, ctypes.POINTER(c_vp)]),
     "b2s_ipc_close": (c_i32, [c_vp]),
     "b2s_copy": (c_i32, [c_i32, c_i64, c_vp, c_vp, c_vp]),
+    "b2s_convert_scratch_bytes": (c_i64, [c_i64, c_i32]),
+    "b2s_coo_to_csr": (c_i32, [c_i32, c_i32, c_i32, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "b2s_csr_transpose": (c_i32, [c_i32, c_i32, c_i32, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "b2s_comm_nccl_version": (c_i32, []),
     "b2s_comm_unique_id": (c_i32, [c_vp]),
     "b2s_comm_init": (c_i32, [c_i32, c_i32, c_vp, ctypes.POINTER(c_vp)]),

@@ -243,6 +243,45 @@ def spgemm(a_indptr, a_indices, a_data, b_indptr, b_indices, b_data, shape_a, sh
     return c_indptr, c_indices, c_data, {"nnz": nnz, "products": products, "dense_rows": dense_rows}
 
 
+# ---- assembly -------------------------------------------------------------------------------------------------
+def coo_to_csr(rows, cols, vals, nrows: int, ptr_dtype, idx_dtype):
+    """COO triplets (device tensors) -> canonical CSR arrays (indptr, indices, vals) through b2s_coo_to_csr."""
+    _chk_dev(rows, cols, vals)
+    nnz = int(vals.shape[0])
+    rows, cols = rows.to(idx_dtype).contiguous(), cols.to(idx_dtype).contiguous()
+    vals = vals.contiguous()
+    dev = vals.device
+    indptr = torch.empty(nrows + 1, dtype=ptr_dtype, device=dev)
+    indices = torch.empty(nnz, dtype=idx_dtype, device=dev)
+    out_vals = torch.empty(nnz, dtype=vals.dtype, device=dev)
+    pt = idx_code(ptr_dtype)
+    scratch = torch.empty(int(L.b2s_convert_scratch_bytes(nrows, pt)), dtype=torch.uint8, device=dev)
+    bad = _lib.c_i64(0)
+    _lib.check(L.b2s_coo_to_csr(vt_code(vals.dtype), idx_code(idx_dtype), pt, nrows, nnz, ptr(rows), ptr(cols), ptr(vals),
+                                ptr(indptr), ptr(indices), ptr(out_vals), ptr(scratch), ctypes.byref(bad), _stream()),
+               "b2s_coo_to_csr")
+    if bad.value:
+        raise ValueError(f"{bad.value} triplets have a row index outside [0, {nrows})")
+    return indptr, indices, out_vals
+
+
+def csr_transpose(indptr, indices, data, shape):
+    """CSR arrays of the transpose (same index widths) through b2s_csr_transpose."""
+    _chk_dev(indptr, indices, data)
+    nrows, ncols = shape
+    nnz = int(data.shape[0])
+    dev = data.device
+    t_indptr = torch.empty(ncols + 1, dtype=indptr.dtype, device=dev)
+    t_indices = torch.empty(nnz, dtype=indices.dtype, device=dev)
+    t_vals = torch.empty(nnz, dtype=data.dtype, device=dev)
+    pt = idx_code(indptr.dtype)
+    scratch = torch.empty(int(L.b2s_convert_scratch_bytes(ncols, pt)), dtype=torch.uint8, device=dev)
+    _lib.check(L.b2s_csr_transpose(vt_code(data.dtype), idx_code(indices.dtype), pt, nrows, ncols, nnz, ptr(indptr),
+                                   ptr(indices.contiguous()), ptr(data.contiguous()), ptr(t_indptr), ptr(t_indices),
+                                   ptr(t_vals), ptr(scratch), _stream()), "b2s_csr_transpose")
+    return t_indptr, t_indices, t_vals
+
+
 def spgemm_row_work(a_indptr, a_indices, b_indptr) -> torch.Tensor:
     """Products per row of A @ B (int64 device tensor of len m): the chunk planner's measure of work / output size."""
     _chk_dev(a_indptr, a_indices, b_indptr)

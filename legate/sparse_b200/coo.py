@@ -93,11 +93,21 @@ class coo_array:
         return self
 
     def _tocsr_device(self):
-        """Sort-by-key assembly on the GPU: stable sort of row * ncols + col, per-row counts, prefix sum."""
+        """Assembly on the GPU by the library's own kernels (b2s_coo_to_csr, csrc/convert.cu): counting sort of the
+        triplets by row, scan of the row counts (nnz_to_pos, reference base.py:30-48), per-row bitonic sort by column.
+        Real float32/float64 values; other dtypes (complex) take the tensor-op route below."""
         from .csr import _INT32_MAX, _force_wide, csr_array
 
         vals, rows, cols = self._dev
         m, n = self.shape
+        wide = _force_wide()
+        ptr_dt = torch.int64 if (wide or vals.shape[0] > _INT32_MAX) else torch.int32
+        idx_dt = torch.int64 if (wide or max(m, n) > _INT32_MAX) else torch.int32
+        if vals.dtype in (torch.float32, torch.float64) and vals.is_cuda:
+            from . import _ops
+
+            indptr, indices, data = _ops.coo_to_csr(rows, cols, vals, m, ptr_dt, idx_dt)
+            return csr_array._from_parts(indptr, indices, data, self.shape)
         if m * n < 2 ** 62:
             order = torch.sort(rows * n + cols, stable=True).indices
         else:  # the fused key would overflow: two stable passes, minor key first
@@ -106,9 +116,6 @@ class coo_array:
         rows, cols, vals = rows[order], cols[order], vals[order]
         indptr = torch.zeros(m + 1, dtype=torch.int64, device=vals.device)
         torch.cumsum(torch.bincount(rows, minlength=m), 0, out=indptr[1:])  # nnz_to_pos, reference base.py:30-48
-        wide = _force_wide()
-        ptr_dt = torch.int64 if (wide or vals.shape[0] > _INT32_MAX) else torch.int32
-        idx_dt = torch.int64 if (wide or n > _INT32_MAX) else torch.int32
         return csr_array._from_parts(indptr.to(ptr_dt), cols.to(idx_dt), vals.contiguous(), self.shape)
 
     def tocsr(self, copy=False):

@@ -238,6 +238,11 @@ class csr_array:
         csc.py:317-324).  Counting sort by column with plain tensor ops on the device."""
         nrows, ncols = self.shape
         dev = self.device
+        if (self._data.is_cuda and self._data.dtype in (torch.float32, torch.float64)
+                and (self._indices.dtype == torch.int64 or nrows <= _INT32_MAX)):
+            # the library's own kernels (b2s_csr_transpose, csrc/convert.cu): counting sort by column + per-row sort
+            t_ptr, t_idx, t_val = _ops.csr_transpose(self._indptr, self._indices, self._data, self.shape)
+            return csr_array._from_parts(t_ptr, t_idx, t_val, (ncols, nrows))
         counts = (self._indptr[1:] - self._indptr[:-1]).to(torch.int64)
         rows = torch.repeat_interleave(torch.arange(nrows, dtype=torch.int64, device=dev), counts)
         cols = self._indices.to(torch.int64)

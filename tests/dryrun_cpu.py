@@ -96,6 +96,27 @@ def install():
         return (torch.from_numpy(cp), torch.from_numpy(ci.astype(np.int32)), torch.from_numpy(cv),
                 {"nnz": int(cp[-1]), "products": 0, "dense_rows": 0})
 
+    def coo_to_csr(rows, cols, vals, nrows, ptr_dtype, idx_dtype):
+        import scipy.sparse as sp
+
+        r, c = rows.numpy().astype(np.int64), cols.numpy().astype(np.int64)
+        if r.size and (r.min() < 0 or r.max() >= nrows):
+            raise ValueError(f"{int(((r < 0) | (r >= nrows)).sum())} triplets have a row index outside [0, {nrows})")
+        ncols = int(c.max()) + 1 if c.size else 1
+        S = sp.coo_array((vals.numpy(), (r, c)), shape=(nrows, ncols)).tocsr()
+        S.sort_indices()
+        return (torch.from_numpy(S.indptr.astype(np.int64)).to(ptr_dtype), torch.from_numpy(S.indices.astype(np.int64)).to(idx_dtype),
+                torch.from_numpy(S.data))
+
+    def csr_transpose(indptr, indices, data, shape):
+        import scipy.sparse as sp
+
+        S = sp.csr_array((data.numpy(), indices.numpy(), indptr.numpy()), shape=shape).T.tocsr()
+        S.sort_indices()
+        return (torch.from_numpy(S.indptr.astype(np.int64)).to(indptr.dtype),
+                torch.from_numpy(S.indices.astype(np.int64)).to(indices.dtype), torch.from_numpy(S.data))
+
+    _ops.coo_to_csr, _ops.csr_transpose = coo_to_csr, csr_transpose
     _ops.spmv_plan, _ops.spmv, _ops.spmm, _ops.dot, _ops.nrm2 = spmv_plan, spmv, spmm, dot, nrm2
     _ops.axpby, _ops.spmv_dot, _ops.cg_update_xr, _ops.csr_diagonal, _ops.spgemm = (axpby, spmv_dot, cg_update_xr,
                                                                                       csr_diagonal, spgemm)

@@ -111,3 +111,47 @@ def test_coo_products_go_through_csr(name):
     x = np.random.default_rng(0).random(arr.shape[1])
     assert np.allclose(arr @ x, s @ x)
     assert np.array_equal(arr.T.todense(), s.T.toarray())
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("wide", [False, True])
+def test_library_assembly_kernels_row_shapes(dtype, wide, monkeypatch):
+    """b2s_coo_to_csr / b2s_csr_transpose (csrc/convert.cu) on every row-sort path: empty rows, rows of <= 32 entries
+    (warp network), rows of hundreds / thousands (shared-memory network) and one row beyond 4096 entries (in-place
+    global network); int32 and int64 index instantiations.  Bit-exact against scipy's canonical CSR."""
+    import scipy.sparse as sp
+    import torch
+
+    import legate.sparse_b200 as sparse
+
+    if wide:
+        monkeypatch.setenv("B2S_INDEX_WIDTH", "64")
+    rng = np.random.default_rng(3)
+    m, n = 3000, 9000
+    lens = rng.integers(0, 20, m)
+    lens[7] = 33; lens[100] = 700; lens[101] = 4096; lens[1500] = 6000; lens[2999] = 1
+    lens[200:260] = 0
+    rows = np.repeat(np.arange(m), lens)
+    cols = np.concatenate([rng.choice(n, size=int(k), replace=False) for k in lens]) if lens.sum() else np.zeros(0, int)
+    vals = rng.standard_normal(rows.shape[0]).astype(dtype)
+    perm = rng.permutation(rows.shape[0])            # triplets in random order
+    rows, cols, vals = rows[perm], cols[perm], vals[perm]
+    ref = sp.coo_array((vals, (rows, cols)), shape=(m, n)).tocsr()
+    ref.sort_indices()
+    A = sparse.coo_array((torch.from_numpy(vals).cuda(), (torch.from_numpy(rows).cuda(), torch.from_numpy(cols).cuda())),
+                         shape=(m, n)).tocsr()
+    assert A.indices.dtype == (torch.int64 if wide else torch.int32)
+    assert np.array_equal(A.indptr.cpu().numpy(), ref.indptr)
+    assert np.array_equal(A.indices.cpu().numpy(), ref.indices)
+    assert np.array_equal(A.data.cpu().numpy(), ref.data)
+    T = A.transpose()
+    rt = ref.T.tocsr()
+    rt.sort_indices()
+    assert T.shape == (n, m)
+    assert np.array_equal(T.indptr.cpu().numpy(), rt.indptr)
+    assert np.array_equal(T.indices.cpu().numpy(), rt.indices)
+    assert np.array_equal(T.data.cpu().numpy(), rt.data)
+    # out-of-range rows are reported, not written
+    with pytest.raises(ValueError, match="outside"):
+        sparse.coo_array((torch.ones(2, dtype=torch.float64, device="cuda"),
+                          (torch.tensor([0, 5], device="cuda"), torch.tensor([0, 1], device="cuda"))), shape=(3, 3)).tocsr()
