@@ -152,6 +152,18 @@ def main():
     assert np.allclose(Gc.data, ref.data, rtol=1e-12)
     assert Ca.global_nnz == ref.nnz
 
+    # 5. distributed assembly over NCCL: every rank holds an arbitrary subset of the triplets; they are routed to the
+    # owner of their row block (grouped send/recv) and assembled there by the library's COO->CSR kernels
+    St = sp.random(3000, 3000, density=0.004, random_state=np.random.default_rng(23), format="coo", dtype=np.float64)
+    mine = np.arange(St.nnz) % world == rank
+    At = bd.dist_csr_array.from_triplets(torch.from_numpy(St.data[mine]).cuda(), torch.from_numpy(St.row[mine]).cuda(),
+                                         torch.from_numpy(St.col[mine]).cuda(), St.shape)
+    Gt = bd.gather_matrix(At).to_scipy_sparse_csr()
+    Rt = St.tocsr(); Rt.sort_indices()
+    assert np.array_equal(Gt.indptr, Rt.indptr) and np.array_equal(Gt.indices, Rt.indices) and np.array_equal(Gt.data, Rt.data)
+    xt = rng.standard_normal(3000)
+    assert np.allclose(At.matvec_global(xt), Rt @ xt, rtol=1e-12, atol=1e-12)
+
     torch.cuda.synchronize()
     dist.barrier()
     if rank == 0:
