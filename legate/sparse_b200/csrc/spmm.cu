@@ -33,6 +33,7 @@
 // Algorithmic bytes: nnz*(sv+si) + (nrows+1)*sp + ncols*k*sv (X once) + nrows*k*sv (Y once); the
 // X-row gathers (nnz*k*sv) are served by L1/L2 when neighbouring rows share columns.
 #include "common.cuh"
+#include <limits.h>
 
 namespace b2s {
 
@@ -133,6 +134,9 @@ constexpr int SPMM_MAX_TILE_ROWS = 1024;     // indptr staging: R + 1 entries
 
 template <typename V, typename I> struct SpmmStage {
   static constexpr int CAP = (SPMM_STAGE_BYTES / (int)(sizeof(V) + sizeof(I))) / 256 * 256;
+  // the X-window variant keeps its tiles small (R rows with room for a band in the window), so a 12 KB staging
+  // buffer is enough and three CTAs (20 KB static + 48 KB window each) fit one SM
+  static constexpr int CAP_WIN = (12 * 1024 / (int)(sizeof(V) + sizeof(I))) / 256 * 256;
 };
 
 // One row of A for one lane group out of the staged copies: slots [qs, qe) of idx_s / val_s.
@@ -167,6 +171,42 @@ __device__ __forceinline__ void spmm_walk_staged(int qs, int qe, const I* __rest
   }
 }
 
+// The same row with the X rows of the tile's column window already in shared memory (`win`: window row w at
+// win + w * row_elems, this pass's column panel only): every nonzero is a 16-byte LDS per owned pack instead of a
+// global gather.  U independent loads in flight per lane.
+template <typename V, typename I, int VEC, int CH, int U>
+__device__ __forceinline__ void spmm_walk_window(int qs, int qe, const I* __restrict__ idx_s, const V* __restrict__ val_s,
+                                                 const V* __restrict__ win, int64_t cmin, int row_elems, int sub_off,
+                                                 int jstep, const bool (&on)[CH], Pack<V, VEC> (&acc)[CH]) {
+  for (int q = qs; q < qe; q += U) {
+    Pack<V, VEC> xv[U][CH];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      if (q + u < qe) {
+        const V* xr = win + (int64_t)((int64_t)idx_s[q + u] - cmin) * row_elems + sub_off;
+#pragma unroll
+        for (int c = 0; c < CH; c++)
+          if (on[c]) {
+#pragma unroll
+            for (int e = 0; e < VEC; e++) xv[u][c].v[e] = xr[c * jstep + e];
+          }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      if (q + u < qe) {
+        const V a = val_s[q + u];
+#pragma unroll
+        for (int c = 0; c < CH; c++)
+          if (on[c]) {
+#pragma unroll
+            for (int e = 0; e < VEC; e++) acc[c].v[e] = fma(a, xv[u][c].v[e], acc[c].v[e]);
+          }
+      }
+    }
+  }
+}
+
 // The same row straight from global memory, one nonzero at a time: only for tiles whose nonzeros
 // exceed the staging buffer (rows thousands of entries long).
 template <typename V, typename I, int VEC, int CH>
@@ -187,16 +227,23 @@ __device__ __forceinline__ void spmm_walk_direct(int64_t ps, int64_t pe, const I
   }
 }
 
-template <typename V, typename I, typename P, int VEC, int CH>
+// WIN: when the columns of a tile span a window of at most `win_rows` rows of X (banded / stencil matrices: a tile of R
+// consecutive rows touches ~R + bandwidth distinct X rows, each ~nnz-per-row times), the CTA first copies that window
+// of X (this pass's column panel) into dynamic shared memory with coalesced 16-byte loads and the products read X from
+// there: L2->SM traffic drops from one X row per NONZERO to one per DISTINCT column of the tile, and the per-nonzero
+// cost is a shared-memory read (one wavefront per 128 bytes, no tag lookup, no replay) instead of a global gather.
+template <typename V, typename I, typename P, int VEC, int CH, bool WIN>
 __global__ void __launch_bounds__(SPMM_THREADS, (CH == 1) ? 3 : 2)
 spmm_tile_kernel(int64_t nrows, int64_t k, const P* __restrict__ indptr, const I* __restrict__ indices,
                  const V* __restrict__ vals, const V* __restrict__ X, int64_t ldx, V* __restrict__ Y, int64_t ldy,
-                 int lpr_shift, int rows_per_group) {
-  constexpr int CAP = SpmmStage<V, I>::CAP;
+                 int lpr_shift, int rows_per_group, int win_rows) {
+  constexpr int CAP = WIN ? SpmmStage<V, I>::CAP_WIN : SpmmStage<V, I>::CAP;
   constexpr int U = (CH == 1) ? 12 : 2;  // X-row gathers in flight per group (see the header comment)
   __shared__ __align__(16) V val_s[CAP];
   __shared__ __align__(16) I idx_s[CAP];
   __shared__ int64_t rowptr_s[SPMM_MAX_TILE_ROWS + 1];
+  extern __shared__ __align__(16) unsigned char spmm_dyn[];   // WIN: the X window
+  __shared__ long long s_mn[SPMM_THREADS / 32], s_mx[SPMM_THREADS / 32];
 
   const int lpr = 1 << lpr_shift;
   const int groups = SPMM_THREADS >> lpr_shift;
@@ -217,10 +264,52 @@ spmm_tile_kernel(int64_t nrows, int64_t k, const P* __restrict__ indptr, const I
   const int g = threadIdx.x >> lpr_shift;
   const int sub = threadIdx.x & (lpr - 1);
   const int64_t jstep = (int64_t)lpr * VEC;
-  const int64_t j0 = (int64_t)blockIdx.y * (CH * jstep) + (int64_t)sub * VEC;
+  const int64_t jpass = (int64_t)blockIdx.y * (CH * jstep);   // first dense column of this pass
+  const int64_t j0 = jpass + (int64_t)sub * VEC;
   bool on[CH];
 #pragma unroll
   for (int c = 0; c < CH; c++) on[c] = (j0 + c * jstep) < k;
+  // ---- X window (block-uniform decision) ------------------------------------------------------------------
+  bool use_win = false;
+  long long cmin = 0;
+  const int row_elems = (int)(CH * jstep);                     // window row = this pass's column panel
+  V* win = reinterpret_cast<V*>(spmm_dyn);
+  if (WIN && staged && p_hi > p_lo) {
+    long long mn = LLONG_MAX, mx = -1;
+    for (int64_t i = threadIdx.x; i < p_hi - p_lo; i += SPMM_THREADS) {
+      const long long c = (long long)idx_s[i];
+      mn = c < mn ? c : mn;
+      mx = c > mx ? c : mx;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const long long a = __shfl_xor_sync(0xffffffffu, mn, o), b = __shfl_xor_sync(0xffffffffu, mx, o);
+      mn = a < mn ? a : mn;
+      mx = b > mx ? b : mx;
+    }
+    if ((threadIdx.x & 31) == 0) { s_mn[threadIdx.x >> 5] = mn; s_mx[threadIdx.x >> 5] = mx; }
+    __syncthreads();
+    mn = s_mn[0]; mx = s_mx[0];
+#pragma unroll
+    for (int w = 1; w < SPMM_THREADS / 32; w++) { mn = s_mn[w] < mn ? s_mn[w] : mn; mx = s_mx[w] > mx ? s_mx[w] : mx; }
+    const long long wrows = mx - mn + 1;
+    use_win = wrows <= (long long)win_rows;
+    cmin = mn;
+    if (use_win) {
+      const int packs_row = row_elems / VEC;
+      const long long total = wrows * packs_row;
+      for (long long i = threadIdx.x; i < total; i += SPMM_THREADS) {
+        const long long r = i / packs_row;
+        const int pk = (int)(i - r * packs_row);
+        if (jpass + (int64_t)pk * VEC < k) {
+          Pack<V, VEC> t;
+          t.load(X + (mn + r) * ldx + jpass + (int64_t)pk * VEC);
+          t.store(win + r * row_elems + pk * VEC);
+        }
+      }
+      __syncthreads();
+    }
+  }
   for (int j = 0; j < rows_per_group; j++) {
     const int lr = j * groups + g;  // neighbouring groups walk neighbouring rows: shared X rows hit in L1
     if (lr >= Rn) break;
@@ -231,7 +320,10 @@ spmm_tile_kernel(int64_t nrows, int64_t k, const P* __restrict__ indptr, const I
       for (int e = 0; e < VEC; e++) acc[c].v[e] = (V)0;
     }
     const int64_t ps = rowptr_s[lr], pe = rowptr_s[lr + 1];
-    if (staged)
+    if (WIN && use_win)
+      spmm_walk_window<V, I, VEC, CH, (CH == 1) ? 8 : 2>((int)(ps - p_lo), (int)(pe - p_lo), idx_s, val_s, win, cmin,
+                                                         row_elems, sub * VEC, (int)jstep, on, acc);
+    else if (staged)
       spmm_walk_staged<V, I, VEC, CH, U>((int)(ps - p_lo), (int)(pe - p_lo), idx_s, val_s, X + j0, ldx, jstep, on, acc);
     else
       spmm_walk_direct<V, I, VEC, CH>(ps, pe, indices, vals, X + j0, ldx, jstep, on, acc);
@@ -242,7 +334,8 @@ spmm_tile_kernel(int64_t nrows, int64_t k, const P* __restrict__ indptr, const I
   }
 }
 
-static int g_spmm_kernel = 0;  // 0 = by value type (measured: fp64 -> tile, fp32 -> row), 1 = row kernel, 2 = tile kernel
+static int g_spmm_kernel = 0;  // 0 = automatic, 1 = row kernel, 2 = tile kernel (global gathers), 3 = tile kernel with the X window
+constexpr int SPMM_WIN_BYTES = 48 * 1024;
 
 template <typename V, typename I, typename P, int VEC>
 static int launch_spmm(int64_t nrows, int64_t nnz, int64_t k, const void* indptr, const void* indices, const void* vals,
@@ -264,18 +357,44 @@ static int launch_spmm(int64_t nrows, int64_t nnz, int64_t k, const void* indptr
   const double avg_row = nrows > 0 ? (double)nnz / (double)nrows : 0.0;
   const double fit = (double)SpmmStage<V, I>::CAP / ((avg_row > 1.0 ? avg_row : 1.0) * groups);
   const int rpg = fit >= 4.0 ? 4 : (fit >= 1.0 ? (int)fit : 1);
-  const bool tile = (g_spmm_kernel == 2) || (g_spmm_kernel == 0 && sizeof(V) == 8 && fit >= 1.0);
+  // X window: rows of the panel that fit the dynamic shared memory; worth it when a tile's rows (R) leave room for a
+  // band around them.  Vector path only (16-byte copies).
+  const int64_t row_bytes = per_pass * (int64_t)sizeof(V);
+  const int win_rows = (int)(SPMM_WIN_BYTES / row_bytes);
+  const bool win_ok = VEC > 1 && fit >= 1.0 && win_rows >= 2 * groups;
+  const bool window = (g_spmm_kernel == 3 && win_ok) || (g_spmm_kernel == 0 && win_ok);
+  const bool tile = window || (g_spmm_kernel == 2) || (g_spmm_kernel == 0 && sizeof(V) == 8 && fit >= 1.0);
   if (tile) {
-    const int64_t R = (int64_t)groups * rpg;
+    int rpg_eff = rpg;
+    if (window) {   // keep R <= win_rows / 2 so that half of the window is left for the band around the tile's rows,
+                    // and an average tile's nonzeros inside the (smaller) staging buffer of this variant
+      const double fit_w = (double)SpmmStage<V, I>::CAP_WIN / ((avg_row > 1.0 ? avg_row : 1.0) * groups);
+      if ((double)rpg_eff > fit_w) rpg_eff = fit_w >= 1.0 ? (int)fit_w : 1;
+      while (rpg_eff > 1 && (int64_t)groups * rpg_eff * 2 > win_rows) rpg_eff--;
+    }
+    const int64_t R = (int64_t)groups * rpg_eff;
     const int64_t gx = (nrows + R - 1) / R;
     B2S_CHECK_ARG(gx < 2147483647LL, "SpMM grid too large");
     dim3 grid((unsigned)gx, (unsigned)gy, 1);
-    if (!multi)
-      spmm_tile_kernel<V, I, P, VEC, 1><<<grid, SPMM_THREADS, 0, st>>>(
-          nrows, k, (const P*)indptr, (const I*)indices, (const V*)vals, (const V*)X, ldx, (V*)Y, ldy, shift, rpg);
+    if (window) {
+      const size_t dyn = (size_t)win_rows * (size_t)row_bytes;
+      if (!multi) {
+        auto kern = spmm_tile_kernel<V, I, P, VEC, 1, true>;
+        B2S_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SPMM_WIN_BYTES));
+        kern<<<grid, SPMM_THREADS, dyn, st>>>(nrows, k, (const P*)indptr, (const I*)indices, (const V*)vals, (const V*)X, ldx,
+                                              (V*)Y, ldy, shift, rpg_eff, win_rows);
+      } else {
+        auto kern = spmm_tile_kernel<V, I, P, VEC, CH, true>;
+        B2S_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SPMM_WIN_BYTES));
+        kern<<<grid, SPMM_THREADS, dyn, st>>>(nrows, k, (const P*)indptr, (const I*)indices, (const V*)vals, (const V*)X, ldx,
+                                              (V*)Y, ldy, shift, rpg_eff, win_rows);
+      }
+    } else if (!multi)
+      spmm_tile_kernel<V, I, P, VEC, 1, false><<<grid, SPMM_THREADS, 0, st>>>(
+          nrows, k, (const P*)indptr, (const I*)indices, (const V*)vals, (const V*)X, ldx, (V*)Y, ldy, shift, rpg, 0);
     else
-      spmm_tile_kernel<V, I, P, VEC, CH><<<grid, SPMM_THREADS, 0, st>>>(
-          nrows, k, (const P*)indptr, (const I*)indices, (const V*)vals, (const V*)X, ldx, (V*)Y, ldy, shift, rpg);
+      spmm_tile_kernel<V, I, P, VEC, CH, false><<<grid, SPMM_THREADS, 0, st>>>(
+          nrows, k, (const P*)indptr, (const I*)indices, (const V*)vals, (const V*)X, ldx, (V*)Y, ldy, shift, rpg, 0);
   } else {
     const int64_t gx = (nrows * lpr + SPMM_THREADS - 1) / SPMM_THREADS;
     B2S_CHECK_ARG(gx < 2147483647LL, "SpMM grid too large");
@@ -315,9 +434,10 @@ using namespace b2s;
 
 extern "C" {
 
-/* tools / tests: 0 = choose by value type (default), 1 = row kernel, 2 = staged tile kernel */
+/* tools / tests: 0 = automatic (default), 1 = row kernel, 2 = staged tile kernel (global X gathers), 3 = staged tile
+ * kernel with the X window in shared memory */
 int b2s_spmm_set_kernel(int kernel) {
-  B2S_CHECK_ARG(kernel >= 0 && kernel <= 2, "unknown SpMM kernel %d", kernel);
+  B2S_CHECK_ARG(kernel >= 0 && kernel <= 3, "unknown SpMM kernel %d", kernel);
   g_spmm_kernel = kernel;
   return B2S_OK;
 }

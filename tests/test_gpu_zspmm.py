@@ -18,10 +18,11 @@ pytestmark = pytest.mark.gpu
 TYPES = [np.float32, np.float64]
 
 
-@pytest.fixture(params=[2, 1], ids=["tile", "row"])
+@pytest.fixture(params=[2, 1, 3], ids=["tile", "row", "window"])
 def kernel(request):
-    """Both SpMM kernels forced in turn (the default picks one per value type): the staged tile kernel and the
-    one-row-per-group kernel."""
+    """All SpMM kernels forced in turn (the default picks one per launch): the staged tile kernel with global X
+    gathers, the one-row-per-group kernel, and the staged tile kernel with the X window in shared memory (which
+    itself falls back to gathers, tile by tile, when the columns of a tile span more rows than the window holds)."""
     from legate.sparse_b200 import _lib
     assert _lib.lib.b2s_spmm_set_kernel(request.param) == 0
     yield request.param
