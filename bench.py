@@ -597,6 +597,24 @@ def other_rows_of_the_path(torch, gallery, peak, args):
     except Exception as exc:  # pragma: no cover
         out["spgemm_error"] = repr(exc)
     try:
+        # GMG-preconditioned CG: the reference's own benchmark shape (results/summit/legate_gpu_gmg.out:
+        # examples/gmg.py -n 4500 -m 200, defaults 2 levels / injection / weighted Jacobi; 37.5 it/s on one V100)
+        import re
+        import subprocess
+
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "examples", "gmg.py"), "-n", "4500", "-l", "2", "-g",
+                            "injection", "-m", "200"], capture_output=True, text=True, timeout=300, cwd=os.path.join(ROOT, "examples"))
+        m = re.search(r"Iterations / sec: ([0-9.]+)", r.stdout)
+        it = re.search(r"after (\d+) iterations, \|b - Ax\| = ([0-9.eE+-]+)", r.stdout)
+        if m:
+            out["gmg_n4500"] = {"it_per_s": float(m.group(1)), "iters": int(it.group(1)) if it else None,
+                                "final_residual": float(it.group(2)) if it else None, "levels": 2, "gridop": "injection",
+                                "reference_v100_it_per_s": 37.5}
+        else:
+            out["gmg_error"] = (r.stdout + r.stderr)[-400:]
+    except Exception as exc:  # pragma: no cover
+        out["gmg_error"] = repr(exc)
+    try:
         out["spgemm_rmat"] = _spgemm_rmat_case(torch, gallery, peak, args)
     except Exception as exc:  # pragma: no cover
         out["spgemm_rmat_error"] = repr(exc)
