@@ -5,6 +5,7 @@
 // the partition helpers behind it (sparse/partition.py:56-208, src/sparse/partition/*.cu).
 #include "spmv_common.cuh"
 #include <atomic>
+#include <stdlib.h>
 
 namespace b2s {
 
@@ -47,7 +48,7 @@ __global__ void spmv_plan_kernel(int64_t nrows, const P* __restrict__ indptr, in
 
 // Second plan pass: the row-shape code of every tile (PlanEntry::pad).  L > 0: every row has the same length L
 // (ELL-like tiles: fixed-degree graphs, interior rows of banded matrices) -- reducible straight from registers;
-// -M: rows differ, none longer than M <= 16 -- one lane per row; 0: anything else.
+// -M: rows differ, none longer than M <= 32 -- one lane per row; 0: anything else.
 // stats[0] += tiles the uniform register path can take, stats[1] += tiles the one-lane-per-row path can take.
 template <typename P>
 __global__ void spmv_plan_shape_kernel(const P* __restrict__ indptr, int64_t ntiles, PlanEntry* __restrict__ plan,
@@ -66,7 +67,7 @@ __global__ void spmv_plan_shape_kernel(const P* __restrict__ indptr, int64_t nti
       same = same && len == len0;
       mx = len > mx ? len : mx;
     }
-    is_short = mx <= 16;
+    is_short = mx <= kShortRowMax;
     if (same && len0 > 0 && len0 < 32768) code = (int)len0;
     else if (is_short) code = -(int)(mx > 0 ? mx : 1);
   }
@@ -227,7 +228,7 @@ static int plan_create_impl(int vt, int it, int pt, int64_t nrows, int64_t ncols
   const bool scattered = lines > 16.0;
   // the deep-gather tile shapes are for scattered LONG rows; scattered short rows (e.g. one column block of a
   // column-blocked random shard, ~4 entries per row) take the one-lane-per-row path of the default shape
-  const bool likely_short = nnz <= 8 * nrows;
+  const bool likely_short = nnz <= 20 * nrows;
   int cfg = resolve_cfg(vt, scattered && !likely_short);
   // B2S_PLAN_TMA_ONLY: the caller needs the TMA tile kernel (y += A x, fused exchange): swap an LDG-kind choice
   // for the deep-gather TMA shape
@@ -258,8 +259,9 @@ static int plan_create_impl(int vt, int it, int pt, int64_t nrows, int64_t ncols
   h->use_rowgroup = 0;
   h->scattered = scattered ? 1 : 0;
   // kernel flavour.  1: >= 25% of the tiles are ELL-like, or rows are long (>= 12) / of even mean length (the
-  // generic reduce then wants the bank-skewed walk); 2: at least half of the tiles hold only short rows (<= 16
-  // entries: stencils, narrow bands, column blocks) and the uniform path does not already cover them;
+  // generic reduce then wants the bank-skewed walk); 2: at least half of the tiles hold only short rows (<= 32
+  // entries: stencils up to 27 points, narrow bands, column blocks of random shards) and the uniform path does
+  // not already cover them;
   // 0: everything else (irregular long rows).
   const int64_t meanL = nrows > 0 ? (nnz + nrows / 2) / nrows : 0;
   int flavor = 0;
@@ -529,6 +531,15 @@ int b2s_spmv_csr_host(int vt, int it, int pt, int64_t nrows, int64_t ncols, int6
       P.ok = true;
     }
   }
+  // B2S_PIPE_TRACE=1: print when each chunk's H2D / tiles / D2H started and ended (debugging the overlap)
+  static const bool trace = getenv("B2S_PIPE_TRACE") != nullptr && getenv("B2S_PIPE_TRACE")[0] == '1';
+  cudaEvent_t tr[kPlanChunks][6];
+  cudaEvent_t tr0 = nullptr;
+  if (trace) {
+    B2S_CUDA(cudaEventCreate(&tr0));
+    for (int c = 0; c < h->nchunks; c++) for (int q = 0; q < 6; q++) B2S_CUDA(cudaEventCreate(&tr[c][q]));
+    B2S_CUDA(cudaEventRecord(tr0, st));
+  }
   // the copy streams start after everything already queued on the compute stream
   B2S_CUDA(cudaEventRecord(P.ev0, st));
   B2S_CUDA(cudaStreamWaitEvent(P.s_in, P.ev0, 0));
@@ -537,24 +548,42 @@ int b2s_spmv_csr_host(int vt, int it, int pt, int64_t nrows, int64_t ncols, int6
   for (int c = 0; c < h->nchunks; c++) {
     const int64_t need = h->ccol_hi[c];
     if (need > copied) {
+      if (trace) B2S_CUDA(cudaEventRecord(tr[c][0], P.s_in));
       B2S_CUDA(cudaMemcpyAsync((char*)x_dev + sv * copied, (const char*)x_host + sv * copied, sv * (size_t)(need - copied),
                                cudaMemcpyHostToDevice, P.s_in));
+      if (trace) B2S_CUDA(cudaEventRecord(tr[c][1], P.s_in));
       copied = need;
       B2S_CUDA(cudaEventRecord(P.ev_in[c], P.s_in));
       B2S_CUDA(cudaStreamWaitEvent(st, P.ev_in[c], 0));
     }
+    if (trace) B2S_CUDA(cudaEventRecord(tr[c][2], st));
     if (int rc = b2s_spmv_csr_tiles(vt, it, pt, nrows, ncols, nnz, indptr, indices, vals, x_dev, y_dev, plan,
                                     h->ctile[c], h->ctile[c + 1], stream)) return rc;
+    if (trace) B2S_CUDA(cudaEventRecord(tr[c][3], st));
     const int64_t r0 = h->crow[c], r1 = h->crow[c + 1];
     if (r1 > r0) {
       B2S_CUDA(cudaEventRecord(P.ev_k[c], st));
       B2S_CUDA(cudaStreamWaitEvent(P.s_out, P.ev_k[c], 0));
+      if (trace) B2S_CUDA(cudaEventRecord(tr[c][4], P.s_out));
       B2S_CUDA(cudaMemcpyAsync((char*)y_host + sv * r0, (const char*)y_dev + sv * r0, sv * (size_t)(r1 - r0),
                                cudaMemcpyDeviceToHost, P.s_out));
+      if (trace) B2S_CUDA(cudaEventRecord(tr[c][5], P.s_out));
     }
   }
   B2S_CUDA(cudaStreamSynchronize(P.s_out));
+  B2S_CUDA(cudaStreamSynchronize(P.s_in));
   B2S_CUDA(cudaStreamSynchronize(st));
+  if (trace) {
+    for (int c = 0; c < h->nchunks; c++) {
+      float t[6] = {-1, -1, -1, -1, -1, -1};
+      for (int q = 0; q < 6; q++) if (cudaEventQuery(tr[c][q]) == cudaSuccess) cudaEventElapsedTime(&t[q], tr0, tr[c][q]);
+      fprintf(stderr, "[b2s pipe] chunk %2d  h2d %7.3f..%7.3f  tiles %7.3f..%7.3f  d2h %7.3f..%7.3f ms\n", c, t[0], t[1], t[2],
+              t[3], t[4], t[5]);
+      for (int q = 0; q < 6; q++) cudaEventDestroy(tr[c][q]);
+    }
+    cudaEventDestroy(tr0);
+    cudaGetLastError();   // events never recorded report an error on query: clear it
+  }
   return B2S_OK;
 }
 

@@ -9,9 +9,10 @@
 namespace b2s {
 
 constexpr int kMaxDevices = 64;
+constexpr int kShortRowMax = 32;   // longest row the one-lane-per-row path takes
 
 // pad: row-shape code of the tile written by the plan: L > 0 = every row has exactly L entries;
-//      -M < 0 = rows differ but none is longer than M <= 16 (one-lane-per-row path); 0 = anything else.
+//      -M < 0 = rows differ but none is longer than M <= kShortRowMax (one-lane-per-row path); 0 = anything else.
 struct __align__(16) PlanEntry {
   long long k;   // first nonzero of the tile's first row
   int row;       // first row of the tile

@@ -13,7 +13,7 @@
 //            indptr slices into a ring of shared-memory stages with cp.async.bulk (TMA, evict-first L2
 //            hint) completing on mbarriers, running STAGES tiles ahead of the consumer warps.  The consumers
 //            pick one of three per-tile paths (chosen by the plan from the tile's row shape):
-//              short   : every row has <= 16 entries -> ONE LANE PER ROW walks its row straight out of shared
+//              short   : every row has <= 32 entries -> ONE LANE PER ROW walks its row straight out of shared
 //                        memory (conflict-free for odd strides), gathers x, FMAs in the reference's
 //                        left-to-right order (spmv.cc:36-44) and stores y: no product round trip, no barrier;
 //              uniform : every row has the same length L = EPT*2^s -> 2^s lanes per row, register sums +
@@ -509,9 +509,12 @@ spmv_tma_kernel(TileOrder order, int64_t nrows, int64_t nnz, const P* __restrict
     // next push may overwrite it; (2) CTA b copies slice b of the local x into its neighbour's x buffer with
     // remote stores over NVLink and raises the arrival flag there.  The matrix stream of this CTA's first
     // tiles is already in flight meanwhile (producer warp), and every other CTA is computing.
+    // The pushing CTAs are the LAST ones of the grid: with tiles dealt round-robin they are the CTAs that get one tile
+    // fewer whenever the tile count is not a multiple of the grid, so part of the push hides in that slack.
     if (exchanging) {
-      if (blockIdx.x == 0 && ctid < order.n_acks) st_release_sys(order.ack_out[ctid], epoch - 1);
-      for (int b = blockIdx.x; b < order.n_sends; b += gridDim.x) {
+      const int rb = (int)(gridDim.x - 1 - blockIdx.x);
+      if (rb == 0 && ctid < order.n_acks) st_release_sys(order.ack_out[ctid], epoch - 1);
+      for (int b = rb; b < order.n_sends; b += gridDim.x) {
         if (ctid == 0 && !spin_ge(order.send_ack[b], epoch - 1)) *order.error = 1ull;
         named_bar_sync(3, CT);
         const V* src = reinterpret_cast<const V*>(order.send_src[b]);
@@ -550,8 +553,8 @@ spmv_tma_kernel(TileOrder order, int64_t nrows, int64_t nnz, const P* __restrict
       const int lo = off, hi = (int)(kce - kb);  // valid slots [lo, hi)
 
       // ---- short-row path: one lane per row (plan code pad = -(longest row of the tile), or the common
-      // length of a uniform tile; <= 16 either way) -----------------------------------------------------------
-      const int shortlen = m.pad < 0 ? -m.pad : (m.pad <= 16 ? m.pad : 0);
+      // length of a uniform tile; <= kShortRowMax either way) ---------------------------------------------------
+      const int shortlen = m.pad < 0 ? -m.pad : (m.pad <= kShortRowMax ? m.pad : 0);
       if (FLAVOR == 2 && shortlen > 0) {
         const int maxlen = shortlen;
         for (int j = ctid; j < nr; j += CT) {

@@ -529,8 +529,14 @@ class dist_csr_array:
                     ranges, n_free = [tuple(r) for r in sched[0] + sched[1]], len(sched[0])
                 sends = [(x_full.data_ptr() + a * item, pc.x_remote(q, a), b - a, pc.flag_remote(q), pc.ack_local(q))
                          for q, a, b in self.sends]
-                desc = _ops.fuse_desc(ranges, n_free, flags=[pc.flag_local(q) for q, _, _ in self.recvs], sends=sends,
-                                      acks=[pc.ack_remote(q) for q, _, _ in self.recvs], epoch_ctr=pc.epoch_ctr,
+                flags = [pc.flag_local(q) for q, _, _ in self.recvs]
+                acks = [pc.ack_remote(q) for q, _, _ in self.recvs]
+                dbg = os.environ.get("B2S_FUSE_DEBUG", "")   # timing experiments only (results are then WRONG)
+                if dbg == "order-only":      # same tile order, no exchange at all
+                    sends, flags, acks = [], [], []
+                elif dbg == "no-wait":       # push + acks, but nobody waits for arrival
+                    flags = []
+                desc = _ops.fuse_desc(ranges, n_free, flags=flags, sends=sends, acks=acks, epoch_ctr=pc.epoch_ctr,
                                       ticket=pc.ticket, epoch_add=1, epoch_bump=1, error=pc.error_word)
                 info = {"mode": "halo", "desc": desc, "plan": plan, "pc": pc}
         elif self.exchange_mode == "allgather":

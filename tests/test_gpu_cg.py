@@ -137,8 +137,9 @@ def test_pde_example_problem():
 
 def test_pde4096_full_size_vs_scipy():
     """BASELINE config 3 at full size: examples/pde.py -nx 4096 -ny 4096 (N = 16,760,836, nnz = 83,787,804), the fused
-    device CG against scipy's cg on the same matrix after the SAME 300 iterations (absolute tolerance 1e-10 is never
-    met, reference semantics rtol=0): true residual ||b - A x|| and x agree to 1e-6 relative (north-star bar)."""
+    device CG against scipy's cg on the same matrix after the SAME 150 iterations (absolute tolerance 1e-10 is never
+    met, reference semantics rtol=0; 150 instead of the benchmark's 300 keeps scipy's single-threaded side near a
+    minute): true residual ||b - A x|| and x agree to 1e-6 relative (north-star bar)."""
     import scipy.sparse.linalg as spla
     import torch
 
@@ -149,13 +150,14 @@ def test_pde4096_full_size_vs_scipy():
     N = A.shape[0]
     assert N == 16760836 and A.nnz == 83787804
     b = torch.ones(N, dtype=torch.float64, device="cuda")
-    x, iters = linalg.cg(A, b, tol=1e-10, maxiter=300)
-    assert iters == 300
+    K = 150
+    x, iters = linalg.cg(A, b, tol=1e-10, maxiter=K)
+    assert iters == K
     res_gpu = float(torch.linalg.vector_norm(b - (A @ x)))
     S = sp.csr_array((A.data.cpu().numpy(), A.indices.cpu().numpy(), A.indptr.cpu().numpy()), shape=A.shape)
     bh = np.ones(N)
-    xs, info = spla.cg(S, bh, rtol=0.0, atol=1e-10, maxiter=300)
-    assert info == 300                                   # scipy also ran out of iterations: same count
+    xs, info = spla.cg(S, bh, rtol=0.0, atol=1e-10, maxiter=K)
+    assert info == K                                     # scipy also ran out of iterations: same count
     res_cpu = float(np.linalg.norm(bh - S @ xs))
     xg = x.cpu().numpy()
     assert abs(res_gpu - res_cpu) <= 1e-6 * res_cpu, (res_gpu, res_cpu)

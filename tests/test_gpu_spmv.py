@@ -372,7 +372,7 @@ def test_host_vectors_pipelined_path(kind, pinned, monkeypatch):
 def test_plan_entries_follow_the_tile_rule():
     """White-box check of b2s_spmv_plan_create: tile t starts at the first row r with indptr[r] + r >= t*T,
     its entry holds that row, indptr[row] and the row-shape code of the tile (common row length L, or -longest when the
-    rows differ but none exceeds 16, else 0); so every
+    rows differ but none exceeds 32, else 0); so every
     tile has <= T rows and all rows but the last fit in T + 4 nonzeros."""
     rng = np.random.default_rng(77)
     nrows = 30011
@@ -407,7 +407,7 @@ def test_plan_entries_follow_the_tile_rule():
         ls = lens[r0:r1]
         if r1 > r0 and ls[0] > 0 and (ls == ls[0]).all():
             want = int(ls[0])                                # uniform tile: the common row length
-        elif r1 > r0 and ls.max() <= 16:
+        elif r1 > r0 and ls.max() <= 32:
             want = -max(int(ls.max()), 1)                    # short rows: minus the longest
         else:
             want = 0
