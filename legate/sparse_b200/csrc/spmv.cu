@@ -532,7 +532,8 @@ int b2s_spmv_csr_host(int vt, int it, int pt, int64_t nrows, int64_t ncols, int6
     }
   }
   // B2S_PIPE_TRACE=1: print when each chunk's H2D / tiles / D2H started and ended (debugging the overlap)
-  static const bool trace = getenv("B2S_PIPE_TRACE") != nullptr && getenv("B2S_PIPE_TRACE")[0] == '1';
+  const char* trace_env = getenv("B2S_PIPE_TRACE");
+  const bool trace = trace_env != nullptr && trace_env[0] == '1';
   cudaEvent_t tr[kPlanChunks][6];
   cudaEvent_t tr0 = nullptr;
   if (trace) {

@@ -313,46 +313,49 @@ def _cg_fused_loop(Ad: csr_array, comm, b, x, tol, maxiter, callback, conv_test_
     p.copy_(x)
     comm.spmv_dot(Ad, p_full, q, p, torch.empty(1, dtype=b.dtype, device=b.device))   # q = A x (the dot is discarded)
     r = b - q
-    rho = _ops.dot(r, r)
-    comm.allreduce(rho)
-    rho_prev = torch.ones_like(rho)
-    rr = torch.empty_like(rho)
-    pq = torch.empty_like(rho)
+    # rho_k = r_k . r_k lives in slot k % 3 of `scal`: iteration k reads rho_k and rho_{k-1} and writes rho_{k+1}, so the
+    # roles rotate with period 3 and no scalar is ever copied (three captured graphs, one per k % 3, instead of one
+    # graph plus two one-element copy kernels per iteration)
+    scal = torch.zeros(3, dtype=b.dtype, device=b.device)
+    slot = [scal[i : i + 1] for i in range(3)]
+    _ops.dot(r, r, out=slot[0])
+    comm.allreduce(slot[0])
+    pq = torch.empty(1, dtype=b.dtype, device=b.device)
 
-    def tail_of_iteration():
+    def tail_of_iteration(k):
         comm.spmv_dot(Ad, p_full, q, p, pq)      # exchange of p (fused into the launch when sharded) + product + p.q
-        _ops.cg_update_xr(x, r, p, q, rho, pq, rr)
-        comm.allreduce(rr)
-        rho_prev.copy_(rho)
-        rho.copy_(rr)
+        _ops.cg_update_xr(x, r, p, q, slot[k % 3], pq, slot[(k + 1) % 3])
+        comm.allreduce(slot[(k + 1) % 3])
 
-    def generic_iteration():
-        cg_axpby(p, r, rho, rho_prev, isalpha=False, negate=False)
-        tail_of_iteration()
+    def generic_iteration(k):
+        cg_axpby(p, r, slot[k % 3], slot[(k - 1) % 3], isalpha=False, negate=False)
+        tail_of_iteration(k)
 
     def converged(iters):
-        return (iters % conv_test_iters == 0 or iters == (maxiter - 1)) and float(rho[0]) ** 0.5 < tol
+        return (iters % conv_test_iters == 0 or iters == (maxiter - 1)) and float(slot[iters % 3][0]) ** 0.5 < tol
 
     iters = 0
     if maxiter <= 0:
         return x, iters
     # iteration 0: p = r (no alias: p is updated in place later, reference linalg.py:541-544)
     p.copy_(r)
-    tail_of_iteration()
+    tail_of_iteration(0)
     iters = 1
     if callback is not None:
         callback(x if on_device else to_host(x))
     if converged(iters):
         return x, iters
 
-    graph = None
-    if os.environ.get("B2S_CG_GRAPH", "1") != "0" and maxiter - iters >= 4 and b.is_cuda:
-        graph = _try_capture(generic_iteration)
+    graphs = None
+    if os.environ.get("B2S_CG_GRAPH", "1") != "0" and maxiter - iters >= 6 and b.is_cuda:
+        graphs = [_try_capture(lambda k=k: generic_iteration(k)) for k in (3, 1, 2)]   # index = k % 3
+        if any(g is None for g in graphs):
+            graphs = None
     while iters < maxiter:
-        if graph is not None:
-            graph.replay()
+        if graphs is not None:
+            graphs[iters % 3].replay()
         else:
-            generic_iteration()
+            generic_iteration(iters)
         iters += 1
         if callback is not None:
             callback(x if on_device else to_host(x))

@@ -61,7 +61,11 @@ def install():
         return Y
 
     def dot(x, y, out=None):
-        return torch.from_numpy(orc.dot(x.numpy(), y.numpy()))
+        r = torch.from_numpy(orc.dot(x.numpy(), y.numpy()))
+        if out is not None:
+            out[:] = r
+            return out
+        return r
 
     def nrm2(x, out=None):
         return torch.from_numpy(orc.nrm2(x.numpy()))
