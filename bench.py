@@ -640,12 +640,14 @@ def sharded_rows_of_the_path(torch, dist, bd, gallery, peak, rank, world, args):
     r32_strong: BASELINE config 4 / the north-star scaling test -- ONE 10M x 10M, 32-per-row random matrix row-sharded
         over the N GPUs; x all-gathered by b2s_peer_push (NVLink remote stores) while the own-column block is
         multiplied, one accumulating launch per source rank waiting in-kernel for its slice.
+    r32_weak: the same with 10M rows PER GPU (10M*N columns): config 4 as literally written ("weak-scale 1/2/4/8").
     cg_pde4096_strong: BASELINE config 3 -- pde.py 4096^2 CG (300 iterations) row-sharded over the N GPUs, halo fused
         into the SpMV launch, scalars all-reduced by the NVLink peer kernel, iteration replayed from a CUDA graph."""
     out = {}
     barrier = lambda: (dist.barrier(), torch.cuda.synchronize())
-    try:
-        n = 10_000_000
+
+    def r32_case(weak):
+        n = 10_000_000 * (world if weak else 1)
         rp = bd.RowBlockPlan(n, world)
         lo, hi = rp.rows(rank)
         local = gallery.random_fixed(hi - lo, n, 32, np.float32, seed=1234 + rank)
@@ -679,19 +681,29 @@ def sharded_rows_of_the_path(torch, dist, bd, gallery, peak, rank, world, args):
         ms = float(t[0])
         info = R._fused.get((id(R.local), xf.data_ptr()))
         nnz = 32 * n
-        out["r32_strong"] = {"global_rows": n, "global_nnz": nnz, "n_gpus": world, "ms_per_step": ms,
-                             "gflops": 2.0 * nnz / (ms * 1e-3) / 1e9, "verified_vs_nccl_allgather": bool(int(ok[0])),
-                             "max_rel_err": err, "exchange_path": f"fused-{info['mode']}" if info else f"nccl-{R.exchange_mode}",
-                             "collective": "all-gather of x by remote stores (b2s_peer_push), one in-kernel wait per source block",
-                             "nvlink_bytes_in_per_gpu_per_step": int((n - (hi - lo)) * 4),
-                             "nvlink_ms_at_770GBs": (n - (hi - lo)) * 4 / 770e9 * 1e3,
-                             "frac_of_hbm_peak_aggregate": alg_bytes(n, n, nnz, sv=4) / (ms * 1e-3) / 1e9 / (peak * world)}
+        blocks = None
+        if info and info["mode"] == "blocks":
+            blocks = {"count": sum(1 for b in info["blocks"].values() if b is not None),
+                      "kernel": next(b._get_plan().kernel_name for b in info["blocks"].values() if b is not None)}
+        res = {"global_rows": n, "global_nnz": nnz, "n_gpus": world, "ms_per_step": ms,
+               "gflops": 2.0 * nnz / (ms * 1e-3) / 1e9, "verified_vs_nccl_allgather": bool(int(ok[0])),
+               "max_rel_err": err, "exchange_path": f"fused-{info['mode']}" if info else f"nccl-{R.exchange_mode}",
+               "column_blocks": blocks,
+               "collective": "all-gather of x by remote stores (b2s_peer_push), one in-kernel wait per source block",
+               "nvlink_bytes_in_per_gpu_per_step": int((n - (hi - lo)) * 4),
+               "nvlink_ms_at_770GBs": (n - (hi - lo)) * 4 / 770e9 * 1e3,
+               "frac_of_hbm_peak_aggregate": alg_bytes(n, n, nnz, sv=4) / (ms * 1e-3) / 1e9 / (peak * world)}
         barrier()
         R.close()
         del R, local, xf, yl, yref
         torch.cuda.empty_cache()
-    except Exception as exc:  # pragma: no cover
-        out["r32_strong_error"] = repr(exc)
+        return res
+
+    for key, weak in (("r32_strong", False), ("r32_weak", True)):
+        try:
+            out[key] = r32_case(weak)
+        except Exception as exc:  # pragma: no cover
+            out[key + "_error"] = repr(exc)
     try:
         g1 = 4094
         N = g1 * g1
