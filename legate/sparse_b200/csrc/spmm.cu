@@ -362,7 +362,9 @@ static int launch_spmm(int64_t nrows, int64_t nnz, int64_t k, const void* indptr
   const int64_t row_bytes = per_pass * (int64_t)sizeof(V);
   const int win_rows = (int)(SPMM_WIN_BYTES / row_bytes);
   const bool win_ok = VEC > 1 && fit >= 1.0 && win_rows >= 2 * groups;
-  const bool window = (g_spmm_kernel == 3 && win_ok) || (g_spmm_kernel == 0 && win_ok);
+  // opt-in for now: measured SLOWER than the gather kernels (banded 11/row fp64 k=32: 3301 us vs 1078 us,
+  // profiles/r02_spmm_bench.json) -- the synchronous stage / window-load / compute phases of a CTA do not overlap
+  const bool window = g_spmm_kernel == 3 && win_ok;
   const bool tile = window || (g_spmm_kernel == 2) || (g_spmm_kernel == 0 && sizeof(V) == 8 && fit >= 1.0);
   if (tile) {
     int rpg_eff = rpg;

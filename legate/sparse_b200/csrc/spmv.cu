@@ -140,6 +140,7 @@ spmv_col_window_kernel(const I* __restrict__ indices, const long long* __restric
 }
 
 constexpr int kPlanChunks = 16;
+constexpr int kDefaultPipeStages = 16;   // host-vector pipeline stages (see b2s_spmv_csr_host)
 
 struct PlanHandle {
   uint32_t magic;
@@ -545,9 +546,16 @@ int b2s_spmv_csr_host(int vt, int it, int pt, int64_t nrows, int64_t ncols, int6
   B2S_CUDA(cudaEventRecord(P.ev0, st));
   B2S_CUDA(cudaStreamWaitEvent(P.s_in, P.ev0, 0));
   B2S_CUDA(cudaStreamWaitEvent(P.s_out, P.ev0, 0));
+  // pipeline granularity: the plan's 16 chunks are processed in groups of `grp` (B2S_PIPE_CHUNKS = 16 / 8 / 4 / 2
+  // stages; fewer, larger copies run closer to the duplex PCIe rate, more stages shorten the fill / drain)
+  int stages = kDefaultPipeStages;
+  if (const char* e = getenv("B2S_PIPE_CHUNKS")) { const int v = atoi(e); if (v >= 1 && v <= kPlanChunks) stages = v; }
+  const int grp = (h->nchunks + stages - 1) / stages;
   int64_t copied = 0;
-  for (int c = 0; c < h->nchunks; c++) {
-    const int64_t need = h->ccol_hi[c];
+  for (int c = 0; c < h->nchunks; c += grp) {
+    const int ce = c + grp < h->nchunks ? c + grp : h->nchunks;   // chunks [c, ce)
+    int64_t need = 0;
+    for (int q = c; q < ce; q++) need = h->ccol_hi[q] > need ? h->ccol_hi[q] : need;
     if (need > copied) {
       if (trace) B2S_CUDA(cudaEventRecord(tr[c][0], P.s_in));
       B2S_CUDA(cudaMemcpyAsync((char*)x_dev + sv * copied, (const char*)x_host + sv * copied, sv * (size_t)(need - copied),
@@ -559,9 +567,9 @@ int b2s_spmv_csr_host(int vt, int it, int pt, int64_t nrows, int64_t ncols, int6
     }
     if (trace) B2S_CUDA(cudaEventRecord(tr[c][2], st));
     if (int rc = b2s_spmv_csr_tiles(vt, it, pt, nrows, ncols, nnz, indptr, indices, vals, x_dev, y_dev, plan,
-                                    h->ctile[c], h->ctile[c + 1], stream)) return rc;
+                                    h->ctile[c], h->ctile[ce], stream)) return rc;
     if (trace) B2S_CUDA(cudaEventRecord(tr[c][3], st));
-    const int64_t r0 = h->crow[c], r1 = h->crow[c + 1];
+    const int64_t r0 = h->crow[c], r1 = h->crow[ce];
     if (r1 > r0) {
       B2S_CUDA(cudaEventRecord(P.ev_k[c], st));
       B2S_CUDA(cudaStreamWaitEvent(P.s_out, P.ev_k[c], 0));

@@ -76,6 +76,7 @@ static inline int cfg_T(int c, int vt) { return cfg_cap(c, vt) - 4; }
 struct TileOrder {
   int nranges, n_free, n_flags, n_sends;
   int n_acks, accumulate, epoch_add, epoch_bump;
+  int n_push, pad0;          // dedicated pusher CTAs (set by the launcher: min(n_sends, grid - 1); they take no tiles)
   long long lo[6], hi[6];
   const unsigned long long* flag[8];
   const void* send_src[4];

@@ -411,6 +411,14 @@ spmv_tma_kernel(TileOrder order, int64_t nrows, int64_t nnz, const P* __restrict
   // exchange epoch of this launch: device-side counter (graph-replayable) or host-numbered
   unsigned long long epoch = order.expect;
   const bool exchanging = (order.n_flags | order.n_sends | order.n_acks) != 0;
+  // Dedicated pusher CTAs: the first n_push CTAs of the grid take NO tiles -- they only push this rank's x slices to
+  // the neighbours (waiting, if they must, for the neighbour's acknowledgement) and exit, so neither the push latency
+  // nor the skew between ranks ever sits on the critical path of a CTA that still has tiles to multiply.  The other
+  // (gridDim - n_push) CTAs share the tiles; 2 of 888 slots for a few microseconds is the whole cost.
+  const int n_push = order.n_push;
+  const bool pusher = (int)blockIdx.x < n_push;
+  const long long wid = (long long)blockIdx.x - n_push;        // worker index
+  const long long nworkers = (long long)gridDim.x - n_push;
   if (exchanging && order.epoch_ctr)
     epoch = *reinterpret_cast<volatile unsigned long long*>(order.epoch_ctr) + (unsigned long long)order.epoch_add;
 
@@ -428,7 +436,7 @@ spmv_tma_kernel(TileOrder order, int64_t nrows, int64_t nnz, const P* __restrict
       if (r < order.n_free) free_total = total;
     }
     bool halo_ready = order.n_flags == 0;
-    for (long long v = blockIdx.x; v < total; v += gridDim.x) {
+    for (long long v = pusher ? total : wid; v < total; v += nworkers) {
       long long off = v;
       int r = 0;
       while (off >= order.hi[r] - order.lo[r]) { off -= order.hi[r] - order.lo[r]; r++; }
@@ -488,7 +496,7 @@ spmv_tma_kernel(TileOrder order, int64_t nrows, int64_t nnz, const P* __restrict
       __syncwarp();
       it++;
     }
-    if (lane == 0) {
+    if (lane == 0 && !pusher) {
       // sentinel: tells the consumers there is no more work
       const int s = it % STAGES;
       const uint32_t par = (uint32_t)((it / STAGES) & 1);
@@ -509,35 +517,42 @@ spmv_tma_kernel(TileOrder order, int64_t nrows, int64_t nnz, const P* __restrict
     // next push may overwrite it; (2) CTA b copies slice b of the local x into its neighbour's x buffer with
     // remote stores over NVLink and raises the arrival flag there.  The matrix stream of this CTA's first
     // tiles is already in flight meanwhile (producer warp), and every other CTA is computing.
-    // The pushing CTAs are the LAST ones of the grid: with tiles dealt round-robin they are the CTAs that get one tile
-    // fewer whenever the tile count is not a multiple of the grid, so part of the push hides in that slack.
     if (exchanging) {
-      const int rb = (int)(gridDim.x - 1 - blockIdx.x);
-      if (rb == 0 && ctid < order.n_acks) st_release_sys(order.ack_out[ctid], epoch - 1);
-      for (int b = rb; b < order.n_sends; b += gridDim.x) {
-        if (ctid == 0 && !spin_ge(order.send_ack[b], epoch - 1)) *order.error = 1ull;
-        named_bar_sync(3, CT);
-        const V* src = reinterpret_cast<const V*>(order.send_src[b]);
-        V* dst = reinterpret_cast<V*>(order.send_dst[b]);
-        const long long cnt = order.send_count[b];
-        for (long long i = ctid; i < cnt; i += CT) dst[i] = src[i];
-        __threadfence_system();
-        named_bar_sync(3, CT);
-        if (ctid == 0) st_release_sys(order.send_flag[b], epoch);
+      // acknowledgements never wait: first thing CTA 0 does
+      if (blockIdx.x == 0 && ctid < order.n_acks) st_release_sys(order.ack_out[ctid], epoch - 1);
+      const bool sends_here = n_push > 0 ? pusher : true;      // no dedicated pushers (tiny grid): workers push
+      const int first = n_push > 0 ? (int)blockIdx.x : (int)blockIdx.x;
+      const int stride = n_push > 0 ? n_push : (int)gridDim.x;
+      if (sends_here) {
+        for (int b = first; b < order.n_sends; b += stride) {
+          if (ctid == 0 && !spin_ge(order.send_ack[b], epoch - 1)) *order.error = 1ull;
+          named_bar_sync(3, CT);
+          const V* src = reinterpret_cast<const V*>(order.send_src[b]);
+          V* dst = reinterpret_cast<V*>(order.send_dst[b]);
+          const long long cnt = order.send_count[b];
+          for (long long i = ctid; i < cnt; i += CT) dst[i] = src[i];
+          __threadfence_system();
+          named_bar_sync(3, CT);
+          if (ctid == 0) st_release_sys(order.send_flag[b], epoch);
+        }
       }
     }
 
     bool fenced = false;
     int it = 0;
-    while (true) {
+    while (!pusher) {
       const int s = it % STAGES;
       const uint32_t par = (uint32_t)((it / STAGES) & 1);
       mbar_wait(&full[s], par);
       const TileMeta m = metas[s];
       if (m.nr < 0) break;
-      if ((m.flags & 1) && !fenced) {
-        // first tile that reads pushed x entries: drop whatever this SM's L1 holds of those lines (a sector that
-        // straddles the owned / pushed boundary may have been read before the push landed)
+      const bool remote_tile = (m.flags & 1) != 0;
+      const int shape_code = m.pad;
+      const bool short_tile = FLAVOR == 2 && (shape_code < 0 ? true : (shape_code > 0 && shape_code <= kShortRowMax));
+      if (remote_tile && !fenced && !short_tile) {
+        // first tile that reads pushed x entries through the L1-allocating path: drop whatever this SM's L1 holds of
+        // those lines (a sector that straddles the owned / pushed boundary may have been read before the push
+        // landed).  Short-row tiles do not need it: they gather remote columns with ld.global.cg (L2 is coherent).
         __threadfence_system();
         fenced = true;
       }
@@ -560,7 +575,11 @@ spmv_tma_kernel(TileOrder order, int64_t nrows, int64_t nnz, const P* __restrict
         for (int j = ctid; j < nr; j += CT) {
           const int sidx = (int)((int64_t)srp[j] - kb), eidx = (int)((int64_t)srp[j + 1] - kb);
           V sum;
-          if (maxlen <= 4)      sum = short_row_sum<4, XL>(scols, svals, x, sidx, eidx, 4);
+          if (remote_tile) {   // columns other GPUs push: L2-coherent gathers (tile-uniform branch)
+            if (maxlen <= 5) sum = short_row_sum<5, 2>(scols, svals, x, sidx, eidx, 5);
+            else             sum = short_row_sum<8, 2>(scols, svals, x, sidx, eidx, maxlen);
+          }
+          else if (maxlen <= 4) sum = short_row_sum<4, XL>(scols, svals, x, sidx, eidx, 4);
           else if (maxlen <= 5) sum = short_row_sum<5, XL>(scols, svals, x, sidx, eidx, 5);
           else if (maxlen <= 6) sum = short_row_sum<6, XL>(scols, svals, x, sidx, eidx, 6);
           else if (maxlen <= 7) sum = short_row_sum<7, XL>(scols, svals, x, sidx, eidx, 7);
@@ -830,10 +849,14 @@ static int launch_tma_f(const SpmvArgs& a) {
   order.accumulate = a.accumulate;
   int64_t ntl = 0;
   for (int r = 0; r < order.nranges; r++) ntl += order.hi[r] - order.lo[r];
-  int64_t grid = (int64_t)pr.sm_count * per_sm;
-  if (grid > ntl) grid = ntl;
-  if (DOT && grid > WS_MAX_PARTIALS) grid = WS_MAX_PARTIALS;
-  if (grid < 1) grid = 1;
+  int64_t slots = (int64_t)pr.sm_count * per_sm;          // CTAs resident at once: the whole grid is one wave
+  if (DOT && slots > WS_MAX_PARTIALS) slots = WS_MAX_PARTIALS;
+  // dedicated pusher CTAs come first in the grid (scheduled first) and take no tiles
+  order.n_push = (order.n_sends > 0 && slots > order.n_sends) ? order.n_sends : 0;
+  int64_t workers = slots - order.n_push;
+  if (workers > ntl) workers = ntl;
+  if (workers < 1) workers = 1;
+  const int64_t grid = workers + order.n_push;
   kern<<<(unsigned)grid, THREADS, smem, a.st>>>(order, a.nrows, a.nnz, (const P*)a.indptr, (const I*)a.indices,
                                                 (const V*)a.vals, (const V*)a.x, (V*)a.y, a.plan, (const V*)a.w,
                                                 (V*)a.dot_out, a.ws);

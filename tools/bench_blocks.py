@@ -1,0 +1,75 @@
+"""1-GPU experiment behind the column-blocked all-gather SpMV (dist._fused_setup 'blocks'): the R32 shard of rank 0 of a
+P-rank run (10M/P rows x 10M columns, 32 per row), split into P column blocks; per-block accumulating SpMV under each
+kernel flavour / tile config vs the unsplit shard.  Says which path the blocks should take.
+    python tools/bench_blocks.py [P ...]"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from legate.sparse_b200 import _lib, _ops, gallery  # noqa: E402
+from legate.sparse_b200.csr import csr_array  # noqa: E402
+
+
+def time_fn(fn, reps=20, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+    for s, e in ev:
+        s.record(); fn(); e.record()
+    torch.cuda.synchronize()
+    ts = sorted(s.elapsed_time(e) for s, e in ev)
+    return ts[len(ts) // 2] * 1e3
+
+
+def blocks_of(A, P):
+    n = A.shape[1]
+    T = (n + P - 1) // P
+    idx = A.indices
+    nrows = A.shape[0]
+    counts = (A.indptr[1:] - A.indptr[:-1]).to(torch.int64)
+    rows = torch.repeat_interleave(torch.arange(nrows, device=idx.device, dtype=torch.int64), counts)
+    out = []
+    for q in range(P):
+        mask = (idx >= q * T) & (idx < min((q + 1) * T, n))
+        cnt = torch.bincount(rows[mask], minlength=nrows)
+        ip = torch.zeros(nrows + 1, dtype=torch.int64, device=idx.device)
+        torch.cumsum(cnt, 0, out=ip[1:])
+        out.append(csr_array._from_parts(ip.to(torch.int32), idx[mask].contiguous(), A.data[mask].contiguous(), A.shape))
+    return out
+
+
+def main():
+    Ps = [int(a) for a in sys.argv[1:]] or [2, 4, 8]
+    n = 10_000_000
+    for P in Ps:
+        rows = n // P
+        A = gallery.random_fixed(rows, n, 32, np.float32, seed=1234)
+        x = torch.rand(n, dtype=torch.float32, device="cuda")
+        y = torch.zeros(rows, dtype=torch.float32, device="cuda")
+        plan = A._get_plan()
+        t_unsplit = time_fn(lambda: _ops.spmv(A.indptr, A.indices, A.data, x, y, A.shape, plan=plan))
+        print(f"P={P} shard {rows} rows: unsplit {plan.kernel_name}: {t_unsplit:8.1f} us", flush=True)
+        blocks = blocks_of(A, P)
+        for cfg in (-1, 5, 8, 3, 0):
+            _lib.check(_lib.lib.b2s_spmv_set_config(cfg, 0))
+            for flavor in (None, 0, 1, 2):
+                tot, names = 0.0, set()
+                for B in blocks:
+                    B._plan = None
+                    pl = B._get_plan(tma_only=True)
+                    if flavor is not None:
+                        pl.set_flavor(flavor)
+                    names.add(pl.kernel_name)
+                    tot += time_fn(lambda: _ops.spmv_add(B.indptr, B.indices, B.data, x, y, B.shape, pl), reps=10)
+                print(f"   cfg {cfg:2d} flavor {str(flavor):4s}: sum over {P} blocks {tot:8.1f} us   ({sorted(names)[0]})", flush=True)
+        _lib.check(_lib.lib.b2s_spmv_set_config(-1, 0))
+        del A, blocks, x, y
+        torch.cuda.empty_cache()
+
+
+if __name__ == "__main__":
+    main()
