@@ -689,7 +689,11 @@ def sharded_rows_of_the_path(torch, dist, bd, gallery, peak, rank, world, args):
                "gflops": 2.0 * nnz / (ms * 1e-3) / 1e9, "verified_vs_nccl_allgather": bool(int(ok[0])),
                "max_rel_err": err, "exchange_path": f"fused-{info['mode']}" if info else f"nccl-{R.exchange_mode}",
                "column_blocks": blocks,
-               "collective": "all-gather of x by remote stores (b2s_peer_push), one in-kernel wait per source block",
+               "collective": ("all-gather of x by remote stores (b2s_peer_push, many CTAs per destination), one accumulating "
+                              "launch per source-rank column block, each waiting in-kernel for its own slice"
+                              if info and info["mode"] == "blocks" else
+                              "all-gather of x by remote stores (b2s_peer_push, many CTAs per destination) + arrival wait, "
+                              "then the product of the unsplit shard" if info else "NCCL all-gather"),
                "nvlink_bytes_in_per_gpu_per_step": int((n - (hi - lo)) * 4),
                "nvlink_ms_at_770GBs": (n - (hi - lo)) * 4 / 770e9 * 1e3,
                "frac_of_hbm_peak_aggregate": alg_bytes(n, n, nnz, sv=4) / (ms * 1e-3) / 1e9 / (peak * world)}

@@ -264,6 +264,10 @@ int         b2s_peer_halo_exchange(int vt, int rank, int nranks, void* const* pe
 int         b2s_peer_push(int vt, int rank, int nranks, void* const* peers_host, const void* x_local_dev,
                           int nsends, const int64_t* send_desc_host, int nrecvs,
                           const int32_t* recv_peers_host, int ctas_per_send, void* stream);
+/* wait on `stream` for the slices the listed source ranks pushed with b2s_peer_push (stream-ordered after this rank's
+ * own push of the same exchange): for consumers that need ALL of x before their first tile */
+int         b2s_peer_push_wait(int rank, int nranks, void* const* peers_host, int nrecvs,
+                               const int32_t* recv_peers_host, void* stream);
 /* byte offset inside the peer header (fused protocol): which = 0 arrival flag of source rank idx, 1 error word,
  * 2 acknowledgement word of destination rank idx, 3 epoch counter, 4 ticket word */
 int64_t     b2s_peer_header_offset(int which, int idx);

@@ -64,6 +64,7 @@ SIGNATURES = {
     "b2s_peer_allreduce": (c_i32, [c_i32, c_i32, c_i32, c_vp, c_vp, c_i32, c_vp]),
     "b2s_peer_halo_exchange": (c_i32, [c_i32, c_i32, c_i32, c_vp, c_vp, c_i32, c_vp, c_i32, c_vp, c_vp]),
     "b2s_peer_push": (c_i32, [c_i32, c_i32, c_i32, c_vp, c_vp, c_i32, c_vp, c_i32, c_vp, c_i32, c_vp]),
+    "b2s_peer_push_wait": (c_i32, [c_i32, c_i32, c_vp, c_i32, c_vp, c_vp]),
     "b2s_peer_header_offset": (c_i64, [c_i32, c_i32]),
     "b2s_peer_check": (c_i32, [c_vp, c_vp, c_vp]),
     "b2s_ipc_export": (c_i32, [c_vp, c_vp]),

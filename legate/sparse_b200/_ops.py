@@ -346,6 +346,14 @@ def peer_push(x_local: torch.Tensor, rank: int, peers, sends, recv_peers, ctas_p
                                len(recv_peers), rp, int(ctas_per_send), _stream()), "b2s_peer_push")
 
 
+def peer_push_wait(rank: int, peers, recv_peers) -> None:
+    """Wait on the current stream for the slices `recv_peers` pushed (b2s_peer_push) in the current exchange."""
+    n = len(peers)
+    arr = (_lib.c_vp * n)(*peers)
+    rp = (ctypes.c_int32 * max(len(recv_peers), 1))(*recv_peers)
+    _lib.check(L.b2s_peer_push_wait(rank, n, arr, len(recv_peers), rp, _stream()), "b2s_peer_push_wait")
+
+
 def fuse_desc(ranges, n_free=None, flags=(), sends=(), acks=(), epoch_ctr=0, ticket=0, epoch_add=1, epoch_bump=1,
               expect=0, error=0, accumulate=False) -> "_lib.FuseDesc":
     """Build a b2s_fuse_desc.  ranges: [(tile_lo, tile_hi)]; flags: local arrival-word addresses;

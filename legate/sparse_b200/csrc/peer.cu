@@ -220,6 +220,17 @@ peer_halo_wait_kernel(PeerPtrs peers, int rank, HaloRecvs recvs) {
   if (threadIdx.x == 0) { __threadfence_system(); me->halo_epoch = e; }
 }
 
+// wait side of b2s_peer_push for consumers that are not b2s_spmv_csr_fused launches: one warp polls the arrival flag of
+// every listed source until it reaches the epoch the preceding push advanced to.
+__global__ void __launch_bounds__(32)
+peer_push_wait_kernel(PeerPtrs peers, int rank, HaloRecvs recvs) {
+  PeerHeader* me = reinterpret_cast<PeerHeader*>(peers.p[rank]);
+  const unsigned long long e = *reinterpret_cast<volatile unsigned long long*>(&me->fuse_epoch);
+  if ((int)threadIdx.x < recvs.n) spin_until_ge(&me->fuse_flag[recvs.peer[threadIdx.x]], e, me);
+  __syncwarp();
+  if (threadIdx.x == 0) __threadfence_system();
+}
+
 static int fill_peers(PeerPtrs* pp, int rank, int nranks, void* const* peers_host) {
   B2S_CHECK_ARG(nranks >= 1 && nranks <= PEER_MAX, "nranks %d out of range [1,%d]", nranks, PEER_MAX);
   B2S_CHECK_ARG(rank >= 0 && rank < nranks, "rank %d out of range", rank);
@@ -334,6 +345,21 @@ int b2s_peer_push(int vt, int rank, int nranks, void* const* peers_host, const v
   const int blocks = nsends > 0 ? nsends * ctas_per_send : 1;
   if (vt == B2S_F32) peer_push_kernel<float><<<blocks, 256, 0, st>>>(pp, rank, (const float*)x_local_dev, s, r, PEER_DATA_OFF, ctas_per_send);
   else               peer_push_kernel<double><<<blocks, 256, 0, st>>>(pp, rank, (const double*)x_local_dev, s, r, PEER_DATA_OFF, ctas_per_send);
+  B2S_LAUNCH_CHECK();
+  return B2S_OK;
+}
+
+/* Wait (on `stream`) until the slices of the listed source ranks pushed with b2s_peer_push have landed -- for
+ * consumers that read ALL of x (an unsplit shard of a random matrix: every tile needs every slice, so there is nothing
+ * to overlap inside the kernel).  Must be stream-ordered after this rank's own b2s_peer_push of the same exchange. */
+int b2s_peer_push_wait(int rank, int nranks, void* const* peers_host, int nrecvs, const int32_t* recv_peers_host,
+                       void* stream) {
+  PeerPtrs pp;
+  if (int rc = fill_peers(&pp, rank, nranks, peers_host)) return rc;
+  HaloSends s;
+  HaloRecvs r;
+  if (int rc = parse_halo(rank, nranks, 0, nullptr, nrecvs, recv_peers_host, &s, &r)) return rc;
+  peer_push_wait_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(pp, rank, r);
   B2S_LAUNCH_CHECK();
   return B2S_OK;
 }

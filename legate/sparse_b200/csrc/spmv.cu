@@ -13,9 +13,10 @@ namespace b2s {
 static std::atomic<int> g_cfg{-1};
 static std::atomic<int> g_waves{0};
 
-static inline int resolve_cfg(int vt, bool scattered) {
+static inline int resolve_cfg(int vt, bool scattered, bool likely_short) {
   const int forced = g_cfg.load();
   if (forced >= 0) return forced;
+  if (scattered && likely_short) return vt == B2S_F32 ? kScatterShortCfgF32 : kScatterShortCfgF64;
   if (scattered) return vt == B2S_F32 ? kScatterCfgF32 : kScatterCfgF64;
   return vt == B2S_F32 ? kDefaultCfgF32 : kDefaultCfgF64;
 }
@@ -140,7 +141,6 @@ spmv_col_window_kernel(const I* __restrict__ indices, const long long* __restric
 }
 
 constexpr int kPlanChunks = 16;
-constexpr int kDefaultPipeStages = 16;   // host-vector pipeline stages (see b2s_spmv_csr_host)
 
 struct PlanHandle {
   uint32_t magic;
@@ -187,9 +187,9 @@ int64_t b2s_spmv_plan_tiles(int vt, int64_t nrows, int64_t nnz) {
   // upper bound over the configurations plan_create may pick (it decides after sampling the matrix)
   int64_t m = 0;
   const int forced = g_cfg.load();
-  const int cands[4] = {forced >= 0 ? forced : (vt == B2S_F32 ? kDefaultCfgF32 : kDefaultCfgF64),
+  const int cands[5] = {forced >= 0 ? forced : (vt == B2S_F32 ? kDefaultCfgF32 : kDefaultCfgF64),
                         vt == B2S_F32 ? kScatterCfgF32 : kScatterCfgF64, vt == B2S_F32 ? kDefaultCfgF32 : kDefaultCfgF64,
-                        kScatterCfgF32};
+                        kScatterCfgF32, vt == B2S_F32 ? kScatterShortCfgF32 : kScatterShortCfgF64};
   for (int c : cands) { const int64_t t = tiles_for(c, vt, nrows, nnz); m = t > m ? t : m; }
   return m;
 }
@@ -230,7 +230,7 @@ static int plan_create_impl(int vt, int it, int pt, int64_t nrows, int64_t ncols
   // the deep-gather tile shapes are for scattered LONG rows; scattered short rows (e.g. one column block of a
   // column-blocked random shard, ~4 entries per row) take the one-lane-per-row path of the default shape
   const bool likely_short = nnz <= 20 * nrows;
-  int cfg = resolve_cfg(vt, scattered && !likely_short);
+  int cfg = resolve_cfg(vt, scattered, likely_short);
   // B2S_PLAN_TMA_ONLY: the caller needs the TMA tile kernel (y += A x, fused exchange): swap an LDG-kind choice
   // for the deep-gather TMA shape
   if ((flags & B2S_PLAN_TMA_ONLY) && kCfgs[cfg].kind != 1) cfg = kScatterCfgF32;
@@ -546,14 +546,30 @@ int b2s_spmv_csr_host(int vt, int it, int pt, int64_t nrows, int64_t ncols, int6
   B2S_CUDA(cudaEventRecord(P.ev0, st));
   B2S_CUDA(cudaStreamWaitEvent(P.s_in, P.ev0, 0));
   B2S_CUDA(cudaStreamWaitEvent(P.s_out, P.ev0, 0));
-  // pipeline granularity: the plan's 16 chunks are processed in groups of `grp` (B2S_PIPE_CHUNKS = 16 / 8 / 4 / 2
-  // stages; fewer, larger copies run closer to the duplex PCIe rate, more stages shorten the fill / drain)
-  int stages = kDefaultPipeStages;
-  if (const char* e = getenv("B2S_PIPE_CHUNKS")) { const int v = atoi(e); if (v >= 1 && v <= kPlanChunks) stages = v; }
-  const int grp = (h->nchunks + stages - 1) / stages;
+  // pipeline schedule over the plan's 16 chunks.  Small copies run well below the duplex PCIe rate (5 MB stages: ~75
+  // GB/s aggregate, 256 MB copies: 99 GB/s) but long first / last stages leave one direction idle while the pipeline
+  // fills and drains, so the default is GRADED: 1, 3, 4, 4, 3, 1 chunks per stage.  B2S_PIPE_CHUNKS = n (1..16) asks
+  // for n equal stages instead.
+  int bounds[kPlanChunks + 2];
+  int nst = 0;
+  bounds[0] = 0;
+  {
+    int stages = 0;
+    if (const char* e = getenv("B2S_PIPE_CHUNKS")) { const int v = atoi(e); if (v >= 1 && v <= kPlanChunks) stages = v; }
+    if (stages > 0 || h->nchunks != kPlanChunks) {
+      if (stages <= 0) stages = h->nchunks;
+      const int grp = (h->nchunks + stages - 1) / stages;
+      for (int c = grp; c < h->nchunks; c += grp) bounds[++nst] = c;
+      bounds[++nst] = h->nchunks;
+    } else {
+      static const int graded[6] = {1, 3, 4, 4, 3, 1};
+      int c = 0;
+      for (int i = 0; i < 6; i++) { c += graded[i]; bounds[++nst] = c; }
+    }
+  }
   int64_t copied = 0;
-  for (int c = 0; c < h->nchunks; c += grp) {
-    const int ce = c + grp < h->nchunks ? c + grp : h->nchunks;   // chunks [c, ce)
+  for (int sidx = 0; sidx < nst; sidx++) {
+    const int c = bounds[sidx], ce = bounds[sidx + 1];            // chunks [c, ce)
     int64_t need = 0;
     for (int q = c; q < ce; q++) need = h->ccol_hi[q] > need ? h->ccol_hi[q] : need;
     if (need > copied) {

@@ -37,9 +37,9 @@ struct __align__(16) PlanEntry {
   X(4, 1, 4, 8, 2, 3, 0)    \
   X(5, 1, 4, 3, 2, 8, 0)    \
   X(6, 1, 8, 4, 2, 2, 0)    \
-  X(7, 1, 4, 8, 2, 3, 1)    \
+  X(7, 1, 4, 3, 2, 8, 2)    \
   X(8, 1, 4, 8, 2, 3, 2)    \
-  X(9, 1, 4, 16, 2, 1, 2)   \
+  X(9, 1, 4, 4, 2, 6, 2)    \
   X(10, 1, 4, 2, 3, 8, 0)   \
   X(11, 1, 8, 4, 2, 3, 0)
 struct TileCfgRt { int kind, a, b, c, d, xl; };
@@ -55,6 +55,10 @@ static constexpr int kDefaultCfgF32 = 5;   // 4 consumer warps x 3 groups, 2 sta
 static constexpr int kScatterCfgF64 = 2;   // LDG tiles, 128 threads x 8 nnz, scalar mapping
 static constexpr int kScatterCfgF32 = 8;   // TMA tiles, 4 warps x 8 groups = 32 gathers/thread, x through ld.global.cg
                                            // (R32 fp32 on B200: .cg 1265 us, .nc 1355 us, .nc.L1::no_allocate 2744 us)
+// scattered SHORT rows (one lane per row): the default tile shapes, but x through ld.global.cg -- the L1-allocating
+// path thrashes on random columns (column blocks of an R32 shard, 16 per row: 1194 us with .nc vs 706 us with .cg)
+static constexpr int kScatterShortCfgF32 = 7;
+static constexpr int kScatterShortCfgF64 = 9;
 
 static inline int cfg_cap(int c, int vt) {
   const TileCfgRt& k = kCfgs[c];

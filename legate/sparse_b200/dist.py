@@ -383,6 +383,7 @@ class dist_csr_array:
         self.use_peer = peer_ok and os.environ.get("B2S_PEER", "1") != "0"
         self.use_peer_halo = self.use_peer and os.environ.get("B2S_PEER_HALO", "0") == "1"
         self.use_fused = self.use_peer and os.environ.get("B2S_PEER_FUSED", "1") != "0"
+        self._blocks_min = int(os.environ.get("B2S_BLOCKS_MIN_BYTES", str(96 << 20)))   # read once, at construction
 
     def _comm_device(self):
         return runtime.device
@@ -541,9 +542,22 @@ class dist_csr_array:
                 info = {"mode": "halo", "desc": desc, "plan": plan, "pc": pc}
         elif self.exchange_mode == "allgather":
             ok = bool(usable and self.col_plan.uniform)
-            if self._agree(ok):
+            # Column blocks pay per-block launch / row-pointer / y read-modify-write overheads (measured on an R32
+            # shard with x L2-resident: 8 blocks 396 us vs 177 us unsplit, tools/bench_blocks.py), so they are used only
+            # when the gathered x would NOT stay L2-resident (each block then gathers from one L2-sized slice).
+            # Otherwise ("gather"): push, wait for every slice, one product of the unsplit shard.
+            want_blocks = self.shape[1] * item > self._blocks_min
+            lo, hi = self.my_cols
+            if ok and not want_blocks:
+                ok = self._agree(True)
+                if ok:
+                    sends = [(q, lo, pc.peer_x_off[q] + lo, hi - lo) for q in range(self.nranks) if q != self.rank and hi > lo]
+                    slice_bytes = (hi - lo) * item
+                    info = {"mode": "gather", "sends": sends, "pc": pc, "plan": A._get_plan(),
+                            "recv_peers": [q for q in range(self.nranks) if q != self.rank],
+                            "cps": 16 if slice_bytes >= (1 << 22) else (4 if slice_bytes >= (1 << 18) else 1)}
+            elif self._agree(ok):
                 blocks = self._column_blocks(A)
-                lo, hi = self.my_cols
                 sends = [(q, lo, pc.peer_x_off[q] + lo, hi - lo) for q in range(self.nranks) if q != self.rank and hi > lo]
                 recv_peers = [q for q in range(self.nranks) if q != self.rank]
                 descs = {}
@@ -590,6 +604,15 @@ class dist_csr_array:
             _ops.spmv_fused(A.indptr, A.indices, A.data, xin, out, A.shape, info["plan"], info["desc"], w=w, dot_out=dot_out)
             return out
         pc = info["pc"]
+        if info["mode"] == "gather":
+            # every tile of an unsplit shard needs every slice: push, wait for all arrivals, multiply
+            _ops.peer_push(x_full, self.rank, pc.peers, info["sends"], info["recv_peers"], info["cps"])
+            _ops.peer_push_wait(self.rank, pc.peers, info["recv_peers"])
+            if w is not None:
+                _ops.spmv_dot(A.indptr, A.indices, A.data, xin, out, w, dot_out, A.shape, info["plan"])
+            else:
+                _ops.spmv(A.indptr, A.indices, A.data, xin, out, A.shape, plan=info["plan"])
+            return out
         cur = torch.cuda.current_stream()
         if getattr(self, "_comm_stream", None) is None:
             self._comm_stream = torch.cuda.Stream()

@@ -43,11 +43,16 @@ def main():
         assert np.allclose(Bm.matvec_global(xb), B @ xb, rtol=1e-12, atol=1e-12), mode
     os.environ["B2S_EXCHANGE"] = "auto"
 
-    # 1b. the same two matrices through the FUSED exchange (default on one box): the random one becomes one column
-    # block per source rank (b2s_peer_push + in-kernel arrival waits), the banded one pushes / awaits its halo
-    # inside the SpMV launch.  Vectors change between products, so stale halo data would be caught.
+    # 1b. the same two matrices through the peer-memory exchange (default on one box): the random one all-gathers x
+    # with b2s_peer_push ("gather": wait for every slice, unsplit product; "blocks" when forced: one column block
+    # per source rank with in-kernel arrival waits), the banded one pushes / awaits its halo inside the SpMV launch.
+    # Vectors change between products, so stale halo data would be caught.
     assert A.use_fused and Bd.use_fused
-    for M, ref_mat, nn in ((A, S, 5000), (Bd, B, n)):
+    os.environ["B2S_BLOCKS_MIN_BYTES"] = "0"
+    Ablk = bd.dist_csr_array.from_global(S)          # same matrix, column-blocked
+    os.environ.pop("B2S_BLOCKS_MIN_BYTES")
+    expect = {id(A): "gather", id(Ablk): "blocks", id(Bd): "halo"}
+    for M, ref_mat, nn in ((A, S, 5000), (Ablk, S, 5000), (Bd, B, n)):
         full = M.new_full_vector(np.float64)
         for rep in range(4):
             xv = rng.standard_normal(nn)
@@ -55,7 +60,7 @@ def main():
             full[lo_:hi_] = torch.from_numpy(xv[lo_:hi_]).cuda()
             y = M.dot(full)
             info = M._fused.get((id(M.local), full.data_ptr()))
-            assert info is not None and info["mode"] == ("blocks" if M is A else "halo"), info
+            assert info is not None and info["mode"] == expect[id(M)], (info and info["mode"], expect[id(M)])
             rl, rh = M.row_plan.rows(rank)
             assert np.allclose(y.cpu().numpy(), (ref_mat @ xv)[rl:rh], rtol=1e-12, atol=1e-10), (rep, info["mode"])
         yg = torch.empty_like(y)
@@ -67,6 +72,7 @@ def main():
         M.check_peer()
     # fp32 column blocks with long scattered rows (R32-like): deep-gather TMA shape per block
     R = gallery.random_fixed(40000, 40000, 32, np.float32, seed=5).to_scipy_sparse_csr()
+    os.environ["B2S_BLOCKS_MIN_BYTES"] = "0"
     Rd = bd.dist_csr_array.from_global(R)
     xr = rng.random(40000).astype(np.float32)
     fullr = Rd.new_full_vector(np.float32)
@@ -74,11 +80,12 @@ def main():
     fullr[lo_:hi_] = torch.from_numpy(xr[lo_:hi_]).cuda()
     yr = Rd.dot_graphed(fullr, torch.empty(Rd.local.shape[0], dtype=torch.float32, device="cuda"))
     assert Rd._fused[(id(Rd.local), fullr.data_ptr())]["mode"] == "blocks"
+    os.environ.pop("B2S_BLOCKS_MIN_BYTES")
     rl, rh = Rd.row_plan.rows(rank)
     assert np.allclose(yr.cpu().numpy(), (R @ xr)[rl:rh], rtol=2e-4, atol=2e-4)
     Rd.check_peer()
     torch.cuda.synchronize(); dist.barrier()
-    A.close(); Bd.close(); Rd.close()
+    A.close(); Ablk.close(); Bd.close(); Rd.close()
 
     # 2./3. fused exchange (default), peer halo kernels, peer all-reduce only, plain NCCL
     modes = [("1", "1", "0"), ("1", "0", "1"), ("1", "0", "0"), ("0", "0", "0")]

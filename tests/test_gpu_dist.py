@@ -22,7 +22,7 @@ def _free_port():
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
-@pytest.mark.parametrize("world", [2])
+@pytest.mark.parametrize("world", [2, 4, 8])
 def test_sharded_spmv_and_cg_nccl(world):
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
