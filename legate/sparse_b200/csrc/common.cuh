@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
+#include <mutex>
 #include "../../../include/b200sparse.h"
 
 namespace b2s {
@@ -132,5 +133,22 @@ template <> struct VecTraits<float>  { static constexpr int vt = B2S_F32; };
 template <> struct VecTraits<double> { static constexpr int vt = B2S_F64; };
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel instantiation, device), thread-safe: the library may
+// be entered from one host thread per GPU.  `Tag` makes the static state unique per call site / instantiation.
+template <typename Tag, typename K>
+inline int ensure_dyn_smem(K kern, int bytes) {
+  static std::mutex mu;
+  static int done[64] = {0};
+  int dev = 0;
+  B2S_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) { set_error("device ordinal %d out of range", dev); return B2S_EINVAL; }
+  std::lock_guard<std::mutex> g(mu);
+  if (done[dev] < bytes) {
+    B2S_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    done[dev] = bytes;
+  }
+  return B2S_OK;
+}
 
 }  // namespace b2s

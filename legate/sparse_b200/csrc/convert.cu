@@ -290,7 +290,8 @@ static int cv_run(int64_t nbuckets, int64_t nnz, const I* rows, const I* cols, c
     constexpr int CAP = 4096;
     auto kern = cv_sort_cta_kernel<V, I, P, CAP>;
     const size_t smem = (sizeof(I) + sizeof(V)) * CAP;
-    B2S_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    struct TagSort {};
+    if (int rc = ensure_dyn_smem<TagSort>(kern, (int)smem)) return rc;
     const unsigned gl = (unsigned)std::min<int64_t>((int64_t)host_counters[1], (int64_t)pr.sm_count * 4);
     kern<<<gl, 256, smem, st>>>((int64_t)host_counters[1], list, indptr, out_idx, out_val);
     B2S_LAUNCH_CHECK();

@@ -682,7 +682,8 @@ static int run_classes(int sm_count, const unsigned long long counts[8], const C
   if (counts[4]) {
     auto kern = spgemm_cta_kernel<V, P, TBL3, 14, 256, NUMERIC>;
     const size_t smem = sizeof(int32_t) * TBL3 + (NUMERIC ? sizeof(V) * TBL3 : 0);
-    B2S_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    struct Tag4 {};
+    if (int rc = ensure_dyn_smem<Tag4>(kern, (int)smem)) return rc;
     int64_t cap = (int64_t)sm_count * (NUMERIC ? 2 : 6);
     unsigned grid = (unsigned)((int64_t)counts[4] < cap ? (int64_t)counts[4] : cap);
     kern<<<grid, 256, smem, st>>>((int64_t)counts[4], perm + offs.off[4], ap, a_idx, av, bp, b_idx, bv, c_ptr, c_idx, cv);

@@ -34,6 +34,7 @@
 // X-row gathers (nnz*k*sv) are served by L1/L2 when neighbouring rows share columns.
 #include "common.cuh"
 #include <limits.h>
+#include <atomic>
 
 namespace b2s {
 
@@ -334,7 +335,7 @@ spmm_tile_kernel(int64_t nrows, int64_t k, const P* __restrict__ indptr, const I
   }
 }
 
-static int g_spmm_kernel = 0;  // 0 = automatic, 1 = row kernel, 2 = tile kernel (global gathers), 3 = tile kernel with the X window
+static std::atomic<int> g_spmm_kernel{0};  // 0 = automatic, 1 = row kernel, 2 = tile kernel (global gathers), 3 = tile kernel with the X window
 constexpr int SPMM_WIN_BYTES = 48 * 1024;
 
 template <typename V, typename I, typename P, int VEC>
@@ -382,12 +383,14 @@ static int launch_spmm(int64_t nrows, int64_t nnz, int64_t k, const void* indptr
       const size_t dyn = (size_t)win_rows * (size_t)row_bytes;
       if (!multi) {
         auto kern = spmm_tile_kernel<V, I, P, VEC, 1, true>;
-        B2S_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SPMM_WIN_BYTES));
+        struct TagW1 {};
+        if (int rc = ensure_dyn_smem<TagW1>(kern, SPMM_WIN_BYTES)) return rc;
         kern<<<grid, SPMM_THREADS, dyn, st>>>(nrows, k, (const P*)indptr, (const I*)indices, (const V*)vals, (const V*)X, ldx,
                                               (V*)Y, ldy, shift, rpg_eff, win_rows);
       } else {
         auto kern = spmm_tile_kernel<V, I, P, VEC, CH, true>;
-        B2S_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SPMM_WIN_BYTES));
+        struct TagW4 {};
+        if (int rc = ensure_dyn_smem<TagW4>(kern, SPMM_WIN_BYTES)) return rc;
         kern<<<grid, SPMM_THREADS, dyn, st>>>(nrows, k, (const P*)indptr, (const I*)indices, (const V*)vals, (const V*)X, ldx,
                                               (V*)Y, ldy, shift, rpg_eff, win_rows);
       }
@@ -440,7 +443,7 @@ extern "C" {
  * kernel with the X window in shared memory */
 int b2s_spmm_set_kernel(int kernel) {
   B2S_CHECK_ARG(kernel >= 0 && kernel <= 3, "unknown SpMM kernel %d", kernel);
-  g_spmm_kernel = kernel;
+  g_spmm_kernel.store(kernel);
   return B2S_OK;
 }
 

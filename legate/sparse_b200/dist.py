@@ -383,7 +383,7 @@ class dist_csr_array:
         self.use_peer = peer_ok and os.environ.get("B2S_PEER", "1") != "0"
         self.use_peer_halo = self.use_peer and os.environ.get("B2S_PEER_HALO", "0") == "1"
         self.use_fused = self.use_peer and os.environ.get("B2S_PEER_FUSED", "1") != "0"
-        self._blocks_min = int(os.environ.get("B2S_BLOCKS_MIN_BYTES", str(96 << 20)))   # read once, at construction
+        self._blocks_min = int(os.environ.get("B2S_BLOCKS_MIN_BYTES", str(48 << 20)))   # read once, at construction
 
     def _comm_device(self):
         return runtime.device
@@ -544,7 +544,8 @@ class dist_csr_array:
             ok = bool(usable and self.col_plan.uniform)
             # Column blocks pay per-block launch / row-pointer / y read-modify-write overheads (measured on an R32
             # shard with x L2-resident: 8 blocks 396 us vs 177 us unsplit, tools/bench_blocks.py), so they are used only
-            # when the gathered x would NOT stay L2-resident (each block then gathers from one L2-sized slice).
+            # when the gathered x would NOT stay L2-resident next to the matrix stream (> 48 MB: an 80 MB x costs the
+            # unsplit R32 product 3.0 ms instead of 1.3; each block then gathers from one L2-sized slice).
             # Otherwise ("gather"): push, wait for every slice, one product of the unsplit shard.
             want_blocks = self.shape[1] * item > self._blocks_min
             lo, hi = self.my_cols

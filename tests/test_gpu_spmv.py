@@ -283,14 +283,14 @@ def test_plan_kernel_choice_by_column_locality():
     assert pl.short_rows and pb.short_rows and pl.tma
     assert gallery.banded(100000, 32, np.float32)._get_plan().uniform
     assert pr.scattered and pr.lines_per_warp > 28 and pr.config == 8   # deep-MLP tile shape for scattered fp32, x via ld.global.cg
-    # scattered SHORT rows (a column block of a random shard) keep the default shape and go one lane per row
+    # scattered SHORT rows (a column block of a random shard): default tile shape, one lane per row, x via ld.global.cg
     rng = np.random.default_rng(9)
     ip, ix, dv = _random_csr(rng, 100000, 100000, rng.integers(1, 8, 100000), np.float32)
     R4 = sparse.csr_array((dv, ix, ip), shape=(100000, 100000))._get_plan()
-    assert R4.scattered and R4.short_rows and R4.tma and R4.config == 5
+    assert R4.scattered and R4.short_rows and R4.tma and R4.config == 7
     # ... and uniform short rows (exactly 4 per row = one 16-byte group per lane) take the register path
     U4 = gallery.random_fixed(100000, 100000, 4, np.float32)._get_plan()
-    assert U4.scattered and U4.uniform and U4.tma and U4.config == 5
+    assert U4.scattered and U4.uniform and U4.tma and U4.config == 7
     # both kernel families give the same answer on the same plan
     x = torch.rand(100000, dtype=torch.float32, device="cuda")
     y1 = R @ x
