@@ -239,7 +239,7 @@ spmm_tile_kernel(int64_t nrows, int64_t k, const P* __restrict__ indptr, const I
                  const V* __restrict__ vals, const V* __restrict__ X, int64_t ldx, V* __restrict__ Y, int64_t ldy,
                  int lpr_shift, int rows_per_group, int win_rows) {
   constexpr int CAP = WIN ? SpmmStage<V, I>::CAP_WIN : SpmmStage<V, I>::CAP;
-  constexpr int U = (CH == 1) ? 12 : 2;  // X-row gathers in flight per group (see the header comment)
+  constexpr int U = (CH == 1) ? (WIN ? 6 : 12) : 2;  // X-row gathers in flight per group (see the header comment)
   __shared__ __align__(16) V val_s[CAP];
   __shared__ __align__(16) I idx_s[CAP];
   __shared__ int64_t rowptr_s[SPMM_MAX_TILE_ROWS + 1];
@@ -297,15 +297,16 @@ spmm_tile_kernel(int64_t nrows, int64_t k, const P* __restrict__ indptr, const I
     use_win = wrows <= (long long)win_rows;
     cmin = mn;
     if (use_win) {
-      const int packs_row = row_elems / VEC;
-      const long long total = wrows * packs_row;
-      for (long long i = threadIdx.x; i < total; i += SPMM_THREADS) {
-        const long long r = i / packs_row;
-        const int pk = (int)(i - r * packs_row);
+      const int packs_row = row_elems / VEC;                 // CH * lpr: a power of two
+      const int pr_shift = 31 - __clz(packs_row);
+      const int total = (int)wrows * packs_row;
+      for (int i = threadIdx.x; i < total; i += SPMM_THREADS) {
+        const int r = i >> pr_shift;
+        const int pk = i & (packs_row - 1);
         if (jpass + (int64_t)pk * VEC < k) {
           Pack<V, VEC> t;
-          t.load(X + (mn + r) * ldx + jpass + (int64_t)pk * VEC);
-          t.store(win + r * row_elems + pk * VEC);
+          t.load(X + (mn + (long long)r) * ldx + jpass + (int64_t)pk * VEC);
+          t.store(win + (size_t)r * row_elems + pk * VEC);
         }
       }
       __syncthreads();
@@ -322,7 +323,7 @@ spmm_tile_kernel(int64_t nrows, int64_t k, const P* __restrict__ indptr, const I
     }
     const int64_t ps = rowptr_s[lr], pe = rowptr_s[lr + 1];
     if (WIN && use_win)
-      spmm_walk_window<V, I, VEC, CH, (CH == 1) ? 8 : 2>((int)(ps - p_lo), (int)(pe - p_lo), idx_s, val_s, win, cmin,
+      spmm_walk_window<V, I, VEC, CH, (CH == 1) ? 4 : 2>((int)(ps - p_lo), (int)(pe - p_lo), idx_s, val_s, win, cmin,
                                                          row_elems, sub * VEC, (int)jstep, on, acc);
     else if (staged)
       spmm_walk_staged<V, I, VEC, CH, U>((int)(ps - p_lo), (int)(pe - p_lo), idx_s, val_s, X + j0, ldx, jstep, on, acc);
