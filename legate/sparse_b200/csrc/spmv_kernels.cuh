@@ -574,6 +574,9 @@ spmv_tma_kernel(TileOrder order, int64_t nrows, int64_t nnz, const P* __restrict
         const int maxlen = shortlen;
         for (int j = ctid; j < nr; j += CT) {
           const int sidx = (int)((int64_t)srp[j] - kb), eidx = (int)((int64_t)srp[j + 1] - kb);
+          const int row = r0 + j;
+          // y += A x: fetch the old y BEFORE the gathers so the two global round trips overlap
+          const V yold = acc_y ? __ldcg(y + row) : (V)0;
           V sum;
           if (remote_tile) {   // columns other GPUs push: L2-coherent gathers (tile-uniform branch)
             if (maxlen <= 5) sum = short_row_sum<5, 2>(scols, svals, x, sidx, eidx, 5);
@@ -584,8 +587,7 @@ spmv_tma_kernel(TileOrder order, int64_t nrows, int64_t nnz, const P* __restrict
           else if (maxlen <= 6) sum = short_row_sum<6, XL>(scols, svals, x, sidx, eidx, 6);
           else if (maxlen <= 7) sum = short_row_sum<7, XL>(scols, svals, x, sidx, eidx, 7);
           else                  sum = short_row_sum<8, XL>(scols, svals, x, sidx, eidx, maxlen);
-          const int row = r0 + j;
-          if (acc_y) sum += y[row];
+          sum += yold;
           y[row] = sum;
           if (DOT) dot_acc += (double)sum * (double)w[row];
         }
