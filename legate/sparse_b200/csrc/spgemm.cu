@@ -500,119 +500,139 @@ spgemm_cta_kernel(int64_t count, const int32_t* __restrict__ perm, const P* __re
 }
 
 // ---- class 4: global two-level bitmap (+ dense value accumulator in the numeric pass) ----------------------------
+// Rows whose output does not fit the largest shared-memory table.  They are processed in ROUNDS of `slots` rows (one
+// bitmap + accumulator slot each); within a round a row is expanded by G CTAs at once -- CTA (slot s, part g) takes the
+// A-entries alo + g*THREADS, + G*THREADS, ... -- because the hub rows of a power-law matrix carry tens of millions of
+// products each and one CTA per row left most of the GPU idle behind them (R-MAT scale 22: 43.8 s in round 2 call 1).
+// All parts accumulate into the slot's global bitmap / dense accumulator with atomics; a second kernel then counts
+// (symbolic) or emits the row in column order (numeric) and clears the slot for the next round.
 template <typename V, typename P, int THREADS, bool NUMERIC>
 __global__ void __launch_bounds__(THREADS)
-spgemm_dense_kernel(int64_t count, const int32_t* __restrict__ perm, const P* __restrict__ a_ptr,
-                    const int32_t* __restrict__ a_idx, const V* __restrict__ a_val, const P* __restrict__ b_ptr,
-                    const int32_t* __restrict__ b_idx, const V* __restrict__ b_val, long long* __restrict__ c_ptr,
-                    int32_t* __restrict__ c_idx, V* __restrict__ c_val, unsigned char* __restrict__ bitmaps,
-                    int64_t slot_bytes, int64_t words0, int64_t words1, V* __restrict__ dense, int64_t n) {
-  __shared__ double red[32];
-  __shared__ int s_scan[THREADS / 32];
-  __shared__ long long s_base;
+spgemm_dense_acc_kernel(int64_t count, int64_t round_base, int G, const int32_t* __restrict__ perm,
+                        const P* __restrict__ a_ptr, const int32_t* __restrict__ a_idx, const V* __restrict__ a_val,
+                        const P* __restrict__ b_ptr, const int32_t* __restrict__ b_idx, const V* __restrict__ b_val,
+                        unsigned char* __restrict__ bitmaps, int64_t slot_bytes, int64_t words0,
+                        V* __restrict__ dense, int64_t n) {
   __shared__ int s_excl[THREADS];
   __shared__ int s_wsum[THREADS / 32];
   __shared__ long long s_blo[THREADS];
   __shared__ V s_av[NUMERIC ? THREADS : 1];
+  const int tid = threadIdx.x;
+  const int slot = (int)(blockIdx.x / (unsigned)G), part = (int)(blockIdx.x % (unsigned)G);
+  const int64_t it = round_base + slot;
+  if (it >= count) return;
+  unsigned int* bm0 = reinterpret_cast<unsigned int*>(bitmaps + slot_bytes * slot);
+  unsigned int* bm1 = bm0 + words0;
+  V* acc = NUMERIC ? dense + n * (int64_t)slot : nullptr;
+  const int32_t row = perm[it];
+  const int64_t alo = (int64_t)a_ptr[row], ahi = (int64_t)a_ptr[row + 1];
+  // flattened expansion, THREADS A-entries per step (see spgemm_warp_kernel)
+  for (int64_t base = alo + (int64_t)part * THREADS; base < ahi; base += (int64_t)G * THREADS) {
+    const int64_t ka = base + tid;
+    int len = 0;
+    if (ka < ahi) {
+      const int32_t kk = a_idx[ka];
+      const long long blo = (long long)b_ptr[kk];
+      len = (int)((long long)b_ptr[kk + 1] - blo);
+      s_blo[tid] = blo;
+      if (NUMERIC) s_av[tid] = a_val[ka];
+    }
+    const int total = block_exclusive_scan<THREADS>(len, s_excl, s_wsum);
+    for (int p = tid; p < total; p += THREADS) {
+      int lo = 0, hi = THREADS - 1;
+      while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (s_excl[mid] <= p) lo = mid; else hi = mid - 1;
+      }
+      const long long jb = s_blo[lo] + (p - s_excl[lo]);
+      const int32_t j = b_idx[jb];
+      const unsigned int bit = 1u << (j & 31);
+      const unsigned int old = atomicOr(&bm0[j >> 5], bit);
+      if (old == 0) atomicOr(&bm1[j >> 10], 1u << ((j >> 5) & 31));
+      if (NUMERIC) atomicAdd(&acc[j], s_av[lo] * b_val[jb]);
+    }
+    __syncthreads();
+  }
+}
+
+template <typename V, int THREADS, bool NUMERIC>
+__global__ void __launch_bounds__(THREADS)
+spgemm_dense_emit_kernel(int64_t count, int64_t round_base, const int32_t* __restrict__ perm,
+                         long long* __restrict__ c_ptr, int32_t* __restrict__ c_idx, V* __restrict__ c_val,
+                         unsigned char* __restrict__ bitmaps, int64_t slot_bytes, int64_t words0, int64_t words1,
+                         V* __restrict__ dense, int64_t n) {
+  __shared__ double red[32];
+  __shared__ int s_scan[THREADS / 32];
+  __shared__ long long s_base;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   constexpr int NWARPS = THREADS / 32;
-  unsigned int* bm0 = reinterpret_cast<unsigned int*>(bitmaps + slot_bytes * blockIdx.x);
+  const int slot = (int)blockIdx.x;
+  const int64_t it = round_base + slot;
+  if (it >= count) return;
+  unsigned int* bm0 = reinterpret_cast<unsigned int*>(bitmaps + slot_bytes * slot);
   unsigned int* bm1 = bm0 + words0;
-  V* acc = NUMERIC ? dense + n * (int64_t)blockIdx.x : nullptr;
-  for (int64_t it = blockIdx.x; it < count; it += gridDim.x) {
-    const int32_t row = perm[it];
-    const int64_t alo = (int64_t)a_ptr[row], ahi = (int64_t)a_ptr[row + 1];
-    // flattened expansion, THREADS A-entries per round (see spgemm_warp_kernel)
-    for (int64_t base = alo; base < ahi; base += THREADS) {
-      const int64_t ka = base + tid;
-      int len = 0;
-      if (ka < ahi) {
-        const int32_t kk = a_idx[ka];
-        const long long blo = (long long)b_ptr[kk];
-        len = (int)((long long)b_ptr[kk + 1] - blo);
-        s_blo[tid] = blo;
-        if (NUMERIC) s_av[tid] = a_val[ka];
+  V* acc = NUMERIC ? dense + n * (int64_t)slot : nullptr;
+  const int32_t row = perm[it];
+  if (!NUMERIC) {
+    // count set bits, clearing as we go (only level-0 words flagged in level 1 are visited)
+    long long cnt = 0;
+    for (int64_t w1 = tid; w1 < words1; w1 += THREADS) {
+      unsigned int m1 = bm1[w1];
+      if (!m1) continue;
+      bm1[w1] = 0;
+      while (m1) {
+        const int b = __ffs(m1) - 1;
+        m1 &= m1 - 1;
+        const int64_t w0 = w1 * 32 + b;
+        cnt += __popc(bm0[w0]);
+        bm0[w0] = 0;
       }
-      const int total = block_exclusive_scan<THREADS>(len, s_excl, s_wsum);
-      for (int p = tid; p < total; p += THREADS) {
-        int lo = 0, hi = THREADS - 1;
-        while (lo < hi) {
-          const int mid = (lo + hi + 1) >> 1;
-          if (s_excl[mid] <= p) lo = mid; else hi = mid - 1;
-        }
-        const long long jb = s_blo[lo] + (p - s_excl[lo]);
-        const int32_t j = b_idx[jb];
-        const unsigned int bit = 1u << (j & 31);
-        const unsigned int old = atomicOr(&bm0[j >> 5], bit);
-        if (old == 0) atomicOr(&bm1[j >> 10], 1u << ((j >> 5) & 31));
-        if (NUMERIC) atomicAdd(&acc[j], s_av[lo] * b_val[jb]);
-      }
-      __syncthreads();
     }
-    __threadfence_block();
+    double tot = block_sum<THREADS>((double)cnt, red);
+    if (tid == 0) c_ptr[row] = (long long)(tot + 0.5);
+  } else {
+    // ordered emission: walk level-1 words in chunks of THREADS, block-scan the popcounts
+    if (tid == 0) s_base = c_ptr[row];
     __syncthreads();
-    if (!NUMERIC) {
-      // count set bits, clearing as we go (only level-0 words flagged in level 1 are visited)
-      long long cnt = 0;
-      for (int64_t w1 = tid; w1 < words1; w1 += THREADS) {
-        unsigned int m1 = bm1[w1];
-        if (!m1) continue;
+    for (int64_t c0 = 0; c0 < words1; c0 += THREADS) {
+      const int64_t w1 = c0 + tid;
+      unsigned int m1 = (w1 < words1) ? bm1[w1] : 0u;
+      int mine = 0;
+      {
+        unsigned int t1 = m1;
+        while (t1) { const int b = __ffs(t1) - 1; t1 &= t1 - 1; mine += __popc(bm0[w1 * 32 + b]); }
+      }
+      // block exclusive scan of `mine`
+      int inc = mine;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+      if (lane == 31) s_scan[wid] = inc;
+      __syncthreads();
+      int woff = 0, total = 0;
+      for (int w = 0; w < NWARPS; w++) { if (w < wid) woff += s_scan[w]; total += s_scan[w]; }
+      long long pos = s_base + woff + inc - mine;
+      if (m1) {
         bm1[w1] = 0;
         while (m1) {
           const int b = __ffs(m1) - 1;
           m1 &= m1 - 1;
           const int64_t w0 = w1 * 32 + b;
-          cnt += __popc(bm0[w0]);
+          unsigned int m0 = bm0[w0];
           bm0[w0] = 0;
-        }
-      }
-      double tot = block_sum<THREADS>((double)cnt, red);
-      if (tid == 0) c_ptr[row] = (long long)(tot + 0.5);
-      __syncthreads();
-    } else {
-      // ordered emission: walk level-1 words in chunks of THREADS, block-scan the popcounts
-      if (tid == 0) s_base = c_ptr[row];
-      __syncthreads();
-      for (int64_t c0 = 0; c0 < words1; c0 += THREADS) {
-        const int64_t w1 = c0 + tid;
-        unsigned int m1 = (w1 < words1) ? bm1[w1] : 0u;
-        int mine = 0;
-        {
-          unsigned int t1 = m1;
-          while (t1) { const int b = __ffs(t1) - 1; t1 &= t1 - 1; mine += __popc(bm0[w1 * 32 + b]); }
-        }
-        // block exclusive scan of `mine`
-        int inc = mine;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
-        if (lane == 31) s_scan[wid] = inc;
-        __syncthreads();
-        int woff = 0, total = 0;
-        for (int w = 0; w < NWARPS; w++) { if (w < wid) woff += s_scan[w]; total += s_scan[w]; }
-        long long pos = s_base + woff + inc - mine;
-        if (m1) {
-          bm1[w1] = 0;
-          while (m1) {
-            const int b = __ffs(m1) - 1;
-            m1 &= m1 - 1;
-            const int64_t w0 = w1 * 32 + b;
-            unsigned int m0 = bm0[w0];
-            bm0[w0] = 0;
-            while (m0) {
-              const int bb = __ffs(m0) - 1;
-              m0 &= m0 - 1;
-              const int64_t j = w0 * 32 + bb;
-              c_idx[pos] = (int32_t)j;
-              c_val[pos] = acc[j];
-              acc[j] = (V)0;
-              pos++;
-            }
+          while (m0) {
+            const int bb = __ffs(m0) - 1;
+            m0 &= m0 - 1;
+            const int64_t j = w0 * 32 + bb;
+            c_idx[pos] = (int32_t)j;
+            c_val[pos] = acc[j];
+            acc[j] = (V)0;
+            pos++;
           }
         }
-        __syncthreads();
-        if (tid == 0) s_base += total;
-        __syncthreads();
       }
+      __syncthreads();
+      if (tid == 0) s_base += total;
+      __syncthreads();
     }
   }
 }
@@ -694,10 +714,21 @@ static int run_classes(int sm_count, const unsigned long long counts[8], const C
     if (NUMERIC && dense_slots < slots) slots = dense_slots;
     if ((int64_t)counts[5] < slots) slots = (int64_t)counts[5];
     if (slots < 1) { set_error("dense accumulator workspace too small"); return B2S_ENOMEM; }
-    spgemm_dense_kernel<V, P, 256, NUMERIC><<<(unsigned)slots, 256, 0, st>>>(
-        (int64_t)counts[5], perm + offs.off[5], ap, a_idx, av, bp, b_idx, bv, c_ptr, c_idx, cv, bitmaps,
-        L.bitmap_slot_bytes, L.bitmap_words0, L.bitmap_words1, (V*)dense, n);
-    B2S_LAUNCH_CHECK();
+    const int64_t cta_budget = (int64_t)sm_count * 8;        // 256-thread CTAs resident at once
+    for (int64_t rb = 0; rb < (int64_t)counts[5]; rb += slots) {
+      const int64_t nthis = ((int64_t)counts[5] - rb) < slots ? ((int64_t)counts[5] - rb) : slots;
+      int64_t G = cta_budget / nthis;
+      if (G < 1) G = 1;
+      if (G > 64) G = 64;
+      spgemm_dense_acc_kernel<V, P, 256, NUMERIC><<<(unsigned)(nthis * G), 256, 0, st>>>(
+          (int64_t)counts[5], rb, (int)G, perm + offs.off[5], ap, a_idx, av, bp, b_idx, bv, bitmaps, L.bitmap_slot_bytes,
+          L.bitmap_words0, (V*)dense, n);
+      B2S_LAUNCH_CHECK();
+      spgemm_dense_emit_kernel<V, 256, NUMERIC><<<(unsigned)nthis, 256, 0, st>>>(
+          (int64_t)counts[5], rb, perm + offs.off[5], c_ptr, c_idx, cv, bitmaps, L.bitmap_slot_bytes, L.bitmap_words0,
+          L.bitmap_words1, (V*)dense, n);
+      B2S_LAUNCH_CHECK();
+    }
   }
   return B2S_OK;
 }
