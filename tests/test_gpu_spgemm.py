@@ -163,6 +163,31 @@ def test_forced_dense_bin():
     _check_vs_scipy(C, S, 1e-12)
 
 
+def test_hub_rows_many_ctas_per_row():
+    """Rows with > 4 M products (symbolic) / > 256 K distinct columns (numeric) -- the hubs of power-law matrices -- are
+    expanded by MANY CTAs per row into the global accumulator (class 6), next to ordinary dense rows (class 5): two hub
+    rows and a few dense ones, structure bit-exact against scipy, values 1e-9 (the accumulation order is atomic)."""
+    rng = np.random.default_rng(11)
+    k, n = 3200, 420_000
+    rows_b = np.repeat(np.arange(k), 2000)
+    cols_b = rng.integers(0, n, rows_b.shape[0])
+    B = sp.coo_array((rng.standard_normal(rows_b.shape[0]), (rows_b, cols_b)), shape=(k, n)).tocsr()
+    B.sum_duplicates()
+    A = sp.lil_array((40, k))
+    A[3, rng.choice(k, 3000, replace=False)] = rng.standard_normal(3000)      # 6 M products, ~ all columns: hub
+    A[17, rng.choice(k, 2500, replace=False)] = rng.standard_normal(2500)     # 5 M products: hub
+    A[5, rng.choice(k, 40, replace=False)] = 1.0                              # 80 K products: ordinary dense row
+    A[9, rng.choice(k, 6, replace=False)] = 2.0                               # 12 K: dense row (> 8192 columns)
+    A[30, rng.choice(k, 2, replace=False)] = -1.0                             # 4 K: shared-memory table
+    A = A.tocsr()
+    S = (A @ B).tocsr()
+    lens = np.diff(S.indptr)
+    assert lens[3] > 256 * 1024 and lens[17] > 256 * 1024 and 8192 < lens[5] < 256 * 1024
+    C = sparse.csr_array(A) @ sparse.csr_array(B)
+    assert C.spgemm_info["dense_rows"] >= 4 and C.spgemm_info["products"] == int(np.diff(B.indptr)[A.indices].sum())
+    _check_vs_scipy(C, S, 1e-9)
+
+
 @pytest.mark.parametrize("scale,ef,budget", [(13, 16, 1 << 18), (16, 16, 1 << 24), (16, 8, 1 << 40)])
 def test_row_chunked_spgemm_matches_scipy(scale, ef, budget):
     """csr.spgemm_chunked (the driver that makes BASELINE config 5 fit one GPU): rows of A cut by product count, the
