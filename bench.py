@@ -533,13 +533,19 @@ def other_rows_of_the_path(torch, gallery, peak, args):
     SpGEMM: examples/spgemm_microbenchmark.py shape (banded, 11 nnz/row) at n = 1M.  SpMM: dot_microbenchmark -op spmm."""
     from legate.sparse_b200 import _ops, linalg
 
+    only = [v for v in os.environ.get("B2S_BENCH_EXTRAS", "").split(",") if v]   # development: run a subset
+    want = lambda name: not only or name in only
     out = {}
     for key, dt in (("r32_fp32", np.float32), ("r32_fp64", np.float64)):
+        if not want("r32"):
+            continue
         try:
             out[key] = _r32_case(torch, gallery, _ops, peak, dt)
         except Exception as exc:  # pragma: no cover
             out[key + "_error"] = repr(exc)
     try:
+        if not want("cg"):
+            raise KeyError("skipped")
         A = gallery.laplacian_5pt(4094, 4094, np.float64)
         b = torch.ones(A.shape[0], dtype=torch.float64, device="cuda")
         linalg.cg(A, b, tol=1e-10, maxiter=30)
@@ -578,9 +584,13 @@ def other_rows_of_the_path(torch, gallery, peak, args):
             del S
         del A, b, x
         torch.cuda.empty_cache()
+    except KeyError:
+        pass
     except Exception as exc:  # pragma: no cover
         out["cg_error"] = repr(exc)
     try:
+        if not want("spgemm_banded"):
+            raise KeyError("skipped")
         B = gallery.banded(1_000_000, 11, np.float64)
         C = B @ B
         torch.cuda.synchronize()
@@ -594,9 +604,13 @@ def other_rows_of_the_path(torch, gallery, peak, args):
         out["spgemm_banded1m"] = {"ms": min(ts) * 1e3, "products": info["products"], "nnz_c": info["nnz"],
                                   "gflops": 2 * info["products"] / min(ts) / 1e9}
         del B, C
+    except KeyError:
+        pass
     except Exception as exc:  # pragma: no cover
         out["spgemm_error"] = repr(exc)
     try:
+        if not want("gmg"):
+            raise KeyError("skipped")
         # GMG-preconditioned CG: the reference's own benchmark shape (results/summit/legate_gpu_gmg.out:
         # examples/gmg.py -n 4500 -m 200, defaults 2 levels / injection / weighted Jacobi; 37.5 it/s on one V100)
         import re
@@ -612,13 +626,21 @@ def other_rows_of_the_path(torch, gallery, peak, args):
                                 "reference_v100_it_per_s": 37.5}
         else:
             out["gmg_error"] = (r.stdout + r.stderr)[-400:]
+    except KeyError:
+        pass
     except Exception as exc:  # pragma: no cover
         out["gmg_error"] = repr(exc)
     try:
+        if not want("spgemm_rmat"):
+            raise KeyError("skipped")
         out["spgemm_rmat"] = _spgemm_rmat_case(torch, gallery, peak, args)
+    except KeyError:
+        pass
     except Exception as exc:  # pragma: no cover
         out["spgemm_rmat_error"] = repr(exc)
     try:
+        if not want("spmm"):
+            raise KeyError("skipped")
         # SpMM: examples/dot_microbenchmark.py -op spmm -k 32 shape at n = 4M, fp64
         n, k = 4_000_000, 32
         B = gallery.banded(n, 11, np.float64)
@@ -630,6 +652,8 @@ def other_rows_of_the_path(torch, gallery, peak, args):
         out["spmm_banded4m_k32"] = {"us": t * 1e6, "gflops": 2 * B.nnz * k / t / 1e9, "algorithmic_bytes": byts,
                                     "frac_of_hbm_peak": byts / t / 1e9 / peak}
         del B, X, Y
+    except KeyError:
+        pass
     except Exception as exc:  # pragma: no cover
         out["spmm_error"] = repr(exc)
     return out
