@@ -176,8 +176,9 @@ int         b2s_spmm_csr(int vt, int it, int pt, int64_t nrows, int64_t ncols, i
                          const void* indptr, const void* indices, const void* vals,
                          const void* X, int64_t ldx, void* Y, int64_t ldy, void* stream);
 
-/* tools / tests: 0 = choose by value type (default: fp64 -> staged tile kernel, fp32 -> row kernel),
- * 1 = one-row-per-lane-group kernel, 2 = staged tile kernel */
+/* tools / tests: 0 = automatic (persistent TMA X-window kernel when the matrix has column locality, else fp64 ->
+ * staged tile kernel, fp32 -> row kernel), 1 = one-row-per-lane-group kernel, 2 = staged tile kernel, 3 = staged tile
+ * kernel with a synchronously loaded X window, 4 = TMA X-window kernel whenever the operand shape is eligible */
 int         b2s_spmm_set_kernel(int kernel);
 
 /* ---- CG vector kernels ---------------------------------------------------------------

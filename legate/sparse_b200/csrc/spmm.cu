@@ -416,11 +416,23 @@ static int launch_spmm(int64_t nrows, int64_t nnz, int64_t k, const void* indptr
   return B2S_OK;
 }
 
+// spmm_tma.cu: persistent kernel with TMA-staged X windows for matrices with column locality
+template <typename V, typename I, typename P>
+int spmm_window_try(int64_t nrows, int64_t nnz, int64_t k, const void* indptr, const void* indices, const void* vals,
+                    const void* X, int64_t ldx, void* Y, int64_t ldy, cudaStream_t st, int force, int* used);
+
 template <typename V, typename I, typename P>
 static int spmm_vec(int64_t nrows, int64_t nnz, int64_t k, const void* indptr, const void* indices, const void* vals, const void* X,
                     int64_t ldx, void* Y, int64_t ldy, cudaStream_t st) {
   constexpr int VEC = 16 / sizeof(V);
   const bool vec_ok = (k % VEC == 0) && (ldx % VEC == 0) && (ldy % VEC == 0) && aligned16(X) && aligned16(Y);
+  const int mode = g_spmm_kernel.load();
+  if (vec_ok && (mode == 0 || mode == 4)) {
+    int used = 0;
+    if (int rc = spmm_window_try<V, I, P>(nrows, nnz, k, indptr, indices, vals, X, ldx, Y, ldy, st, mode == 4, &used)) return rc;
+    if (used) return B2S_OK;
+    // mode 4 on an operand the window kernel cannot take (k, alignment): the gather kernels below run instead
+  }
   if (vec_ok) return launch_spmm<V, I, P, VEC>(nrows, nnz, k, indptr, indices, vals, X, ldx, Y, ldy, st);
   return launch_spmm<V, I, P, 1>(nrows, nnz, k, indptr, indices, vals, X, ldx, Y, ldy, st);
 }
@@ -440,10 +452,11 @@ using namespace b2s;
 
 extern "C" {
 
-/* tools / tests: 0 = automatic (default), 1 = row kernel, 2 = staged tile kernel (global X gathers), 3 = staged tile
- * kernel with the X window in shared memory */
+/* tools / tests: 0 = automatic (default: the TMA window kernel when the matrix has column locality, else by value
+ * type), 1 = row kernel, 2 = staged tile kernel (global X gathers), 3 = staged tile kernel with a synchronously loaded
+ * X window, 4 = persistent TMA-staged X-window kernel whenever the operand is eligible, whatever the column locality */
 int b2s_spmm_set_kernel(int kernel) {
-  B2S_CHECK_ARG(kernel >= 0 && kernel <= 3, "unknown SpMM kernel %d", kernel);
+  B2S_CHECK_ARG(kernel >= 0 && kernel <= 4, "unknown SpMM kernel %d", kernel);
   g_spmm_kernel.store(kernel);
   return B2S_OK;
 }

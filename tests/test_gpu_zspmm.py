@@ -18,11 +18,12 @@ pytestmark = pytest.mark.gpu
 TYPES = [np.float32, np.float64]
 
 
-@pytest.fixture(params=[2, 1, 3], ids=["tile", "row", "window"])
+@pytest.fixture(params=[2, 1, 3, 4], ids=["tile", "row", "window", "tma-window"])
 def kernel(request):
     """All SpMM kernels forced in turn (the default picks one per launch): the staged tile kernel with global X
-    gathers, the one-row-per-group kernel, and the staged tile kernel with the X window in shared memory (which
-    itself falls back to gathers, tile by tile, when the columns of a tile span more rows than the window holds)."""
+    gathers, the one-row-per-group kernel, the staged tile kernel with a synchronously loaded X window, and the
+    persistent TMA-staged X-window kernel (both window kernels fall back to gathers, tile by tile, when the columns
+    of a tile span more rows than a stage holds; the TMA one hands ineligible operand shapes to the gather kernels)."""
     from legate.sparse_b200 import _lib
     assert _lib.lib.b2s_spmm_set_kernel(request.param) == 0
     yield request.param
@@ -190,7 +191,7 @@ def test_bad_arguments():
     assert rc != 0 and b"value type" in L.b2s_last_error()
     rc = L.b2s_spmm_csr(1, 0, 0, 4, 4, 0, 8, None, None, None, None, 4, None, 8, None)
     assert rc != 0 and b"leading" in L.b2s_last_error()
-    assert L.b2s_spmm_set_kernel(7) != 0 and b"unknown SpMM kernel" in L.b2s_last_error()
+    assert L.b2s_spmm_set_kernel(9) != 0 and b"unknown SpMM kernel" in L.b2s_last_error()
 
 
 def test_laplacian_k32_matches_spmv_columns():

@@ -24,7 +24,7 @@ for name, make in (("banded11", lambda dt: gallery.banded(n, 11, dtype=dt)),
             X = torch.rand((A.shape[1], k), dtype=A._data.dtype, device="cuda")
             Y = torch.empty((m, k), dtype=A._data.dtype, device="cuda")
             times = {}
-            for kern, kname in ((1, "row"), (2, "tile"), (3, "window")):
+            for kern, kname in ((1, "row"), (2, "tile"), (3, "window"), (4, "tma")):
                 _lib.lib.b2s_spmm_set_kernel(kern)
                 for _ in range(3):
                     _ops.spmm(A._indptr, A._indices, A._data, X, Y, A.shape)
@@ -43,7 +43,7 @@ for name, make in (("banded11", lambda dt: gallery.banded(n, 11, dtype=dt)),
             err = float((Y[:, j] - y).abs().max() / (y.abs().max() + 1e-30))
             sv = A.dtype.itemsize
             byts = A.nnz * (sv + 4) + 4 * (m + 1) + 2 * m * k * sv
-            rows.append(dict(matrix=name, dtype=str(np.dtype(dt)), n=m, nnz=A.nnz, k=k, us=round(t * 1e6, 1), row_kernel_us=round(times['row'] * 1e6, 1), tile_kernel_us=round(times['tile'] * 1e6, 1), window_kernel_us=round(times['window'] * 1e6, 1),
+            rows.append(dict(matrix=name, dtype=str(np.dtype(dt)), n=m, nnz=A.nnz, k=k, us=round(t * 1e6, 1), row_kernel_us=round(times['row'] * 1e6, 1), tile_kernel_us=round(times['tile'] * 1e6, 1), window_kernel_us=round(times['window'] * 1e6, 1), tma_window_kernel_us=round(times['tma'] * 1e6, 1),
                              gflops=round(2 * A.nnz * k / t / 1e9, 1), alg_gbs=round(byts / t / 1e9, 1),
                              col_err=err))
             print("SPMM", json.dumps(rows[-1]), flush=True)
