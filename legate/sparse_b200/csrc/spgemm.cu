@@ -20,12 +20,8 @@
 namespace b2s {
 
 // row bins: 0 empty | 1: <=32 (warp, 64-slot table) | 2: <=128 (warp, 256) | 3: <=1024 (CTA, 2048) |
-//           4: <=8192 (CTA, 16384) | 5: larger (global bitmap + dense accumulator, one CTA per row) |
-//           6: hub rows (same accumulator, MANY CTAs per row): > 4 M products (symbolic binning by products) or
-//              > 256 K distinct columns (numeric binning by nnz) -- the handful of rows of a power-law matrix that
-//              one CTA would chew on for hundreds of milliseconds while the rest of the GPU idles
-constexpr int NCLS = 7;
-constexpr long long HUB_MIN_PRODUCTS = 4LL << 20, HUB_MIN_NNZ = 256LL << 10;
+//           4: <=8192 (CTA, 16384) | 5: larger (global bitmap + dense accumulator)
+constexpr int NCLS = 6;
 constexpr int64_t CLS0_MAX = 32, CLS1_MAX = 128, CLS2_MAX = 1024, CLS3_MAX = 8192;
 constexpr int TBL0 = 64, TBL1 = 256, TBL2 = 2048, TBL3 = 16384;
 constexpr int SCAN_BLOCK = 1024;        // elements per scan block (256 threads x 4)
@@ -61,8 +57,8 @@ static ScratchLayout scratch_layout(int64_t m, int64_t n, int sm_count) {
   return L;
 }
 
-__host__ __device__ __forceinline__ int classify(long long v, long long hub_min) {
-  return v == 0 ? 0 : (v <= CLS0_MAX ? 1 : (v <= CLS1_MAX ? 2 : (v <= CLS2_MAX ? 3 : (v <= CLS3_MAX ? 4 : (v <= hub_min ? 5 : 6)))));
+__host__ __device__ __forceinline__ int classify(long long v) {
+  return v == 0 ? 0 : (v <= CLS0_MAX ? 1 : (v <= CLS1_MAX ? 2 : (v <= CLS2_MAX ? 3 : (v <= CLS3_MAX ? 4 : 5))));
 }
 
 __device__ __forceinline__ unsigned hash_col(int32_t c, int bits) {
@@ -118,7 +114,7 @@ bin_count_kernel(int64_t m, const long long* __restrict__ src, Header* hdr, int 
   int c = -1;
   if (i < m) {
     v = FROM_INDPTR ? (src[i + 1] - src[i]) : src[i];
-    c = classify(v, FROM_INDPTR ? HUB_MIN_NNZ : HUB_MIN_PRODUCTS);
+    c = classify(v);
   }
   // warp-aggregated: one shared-memory atomic per (warp, class) instead of one per row
 #pragma unroll
@@ -152,7 +148,7 @@ bin_scatter_kernel(int64_t m, const long long* __restrict__ src, Header* hdr, Cl
   unsigned int local = 0;
   if (i < m) {
     const long long v = FROM_INDPTR ? (src[i + 1] - src[i]) : src[i];
-    c = classify(v, FROM_INDPTR ? HUB_MIN_NNZ : HUB_MIN_PRODUCTS);
+    c = classify(v);
     local = atomicAdd(&s_cnt[c], 1u);
   }
   __syncthreads();
@@ -503,7 +499,10 @@ spgemm_cta_kernel(int64_t count, const int32_t* __restrict__ perm, const P* __re
   }
 }
 
-// ---- class 5: global two-level bitmap (+ dense value accumulator in the numeric pass), one CTA per row ----------------------------
+// ---- class 4: global two-level bitmap (+ dense value accumulator in the numeric pass) ----------------------------
+// One CTA per row, CTAs loop over the rows of the class.  Two alternatives were measured on R-MAT scale 22 (round 2,
+// profiles/README.md) and lost: rounds of rows with G CTAs per row (79 s vs 44 s: a round lasts as long as its
+// heaviest row / G while the other slots idle) and a separate many-CTA class for hub rows only (103 s).
 template <typename V, typename P, int THREADS, bool NUMERIC>
 __global__ void __launch_bounds__(THREADS)
 spgemm_dense_kernel(int64_t count, const int32_t* __restrict__ perm, const P* __restrict__ a_ptr,
@@ -621,144 +620,6 @@ spgemm_dense_kernel(int64_t count, const int32_t* __restrict__ perm, const P* __
   }
 }
 
-// ---- class 6: hub rows -------------------------------------------------------------------------------------------
-// The heaviest rows of the dense class.  They are processed in ROUNDS of `slots` rows (one
-// bitmap + accumulator slot each); within a round a row is expanded by G CTAs at once -- CTA (slot s, part g) takes the
-// A-entries alo + g*THREADS, + G*THREADS, ... -- because the hub rows of a power-law matrix carry tens of millions of
-// products each and one CTA per row left most of the GPU idle behind them (R-MAT scale 22: 43.8 s in round 2 call 1).
-// All parts accumulate into the slot's global bitmap / dense accumulator with atomics; a second kernel then counts
-// (symbolic) or emits the row in column order (numeric) and clears the slot for the next round.
-template <typename V, typename P, int THREADS, bool NUMERIC>
-__global__ void __launch_bounds__(THREADS)
-spgemm_dense_acc_kernel(int64_t count, int64_t round_base, int G, const int32_t* __restrict__ perm,
-                        const P* __restrict__ a_ptr, const int32_t* __restrict__ a_idx, const V* __restrict__ a_val,
-                        const P* __restrict__ b_ptr, const int32_t* __restrict__ b_idx, const V* __restrict__ b_val,
-                        unsigned char* __restrict__ bitmaps, int64_t slot_bytes, int64_t words0,
-                        V* __restrict__ dense, int64_t n) {
-  __shared__ int s_excl[THREADS];
-  __shared__ int s_wsum[THREADS / 32];
-  __shared__ long long s_blo[THREADS];
-  __shared__ V s_av[NUMERIC ? THREADS : 1];
-  const int tid = threadIdx.x;
-  const int slot = (int)(blockIdx.x / (unsigned)G), part = (int)(blockIdx.x % (unsigned)G);
-  const int64_t it = round_base + slot;
-  if (it >= count) return;
-  unsigned int* bm0 = reinterpret_cast<unsigned int*>(bitmaps + slot_bytes * slot);
-  unsigned int* bm1 = bm0 + words0;
-  V* acc = NUMERIC ? dense + n * (int64_t)slot : nullptr;
-  const int32_t row = perm[it];
-  const int64_t alo = (int64_t)a_ptr[row], ahi = (int64_t)a_ptr[row + 1];
-  // flattened expansion, THREADS A-entries per step (see spgemm_warp_kernel)
-  for (int64_t base = alo + (int64_t)part * THREADS; base < ahi; base += (int64_t)G * THREADS) {
-    const int64_t ka = base + tid;
-    int len = 0;
-    if (ka < ahi) {
-      const int32_t kk = a_idx[ka];
-      const long long blo = (long long)b_ptr[kk];
-      len = (int)((long long)b_ptr[kk + 1] - blo);
-      s_blo[tid] = blo;
-      if (NUMERIC) s_av[tid] = a_val[ka];
-    }
-    const int total = block_exclusive_scan<THREADS>(len, s_excl, s_wsum);
-    for (int p = tid; p < total; p += THREADS) {
-      int lo = 0, hi = THREADS - 1;
-      while (lo < hi) {
-        const int mid = (lo + hi + 1) >> 1;
-        if (s_excl[mid] <= p) lo = mid; else hi = mid - 1;
-      }
-      const long long jb = s_blo[lo] + (p - s_excl[lo]);
-      const int32_t j = b_idx[jb];
-      const unsigned int bit = 1u << (j & 31);
-      const unsigned int old = atomicOr(&bm0[j >> 5], bit);
-      if (old == 0) atomicOr(&bm1[j >> 10], 1u << ((j >> 5) & 31));
-      if (NUMERIC) atomicAdd(&acc[j], s_av[lo] * b_val[jb]);
-    }
-    __syncthreads();
-  }
-}
-
-template <typename V, int THREADS, bool NUMERIC>
-__global__ void __launch_bounds__(THREADS)
-spgemm_dense_emit_kernel(int64_t count, int64_t round_base, const int32_t* __restrict__ perm,
-                         long long* __restrict__ c_ptr, int32_t* __restrict__ c_idx, V* __restrict__ c_val,
-                         unsigned char* __restrict__ bitmaps, int64_t slot_bytes, int64_t words0, int64_t words1,
-                         V* __restrict__ dense, int64_t n) {
-  __shared__ double red[32];
-  __shared__ int s_scan[THREADS / 32];
-  __shared__ long long s_base;
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  constexpr int NWARPS = THREADS / 32;
-  const int slot = (int)blockIdx.x;
-  const int64_t it = round_base + slot;
-  if (it >= count) return;
-  unsigned int* bm0 = reinterpret_cast<unsigned int*>(bitmaps + slot_bytes * slot);
-  unsigned int* bm1 = bm0 + words0;
-  V* acc = NUMERIC ? dense + n * (int64_t)slot : nullptr;
-  const int32_t row = perm[it];
-  if (!NUMERIC) {
-    // count set bits, clearing as we go (only level-0 words flagged in level 1 are visited)
-    long long cnt = 0;
-    for (int64_t w1 = tid; w1 < words1; w1 += THREADS) {
-      unsigned int m1 = bm1[w1];
-      if (!m1) continue;
-      bm1[w1] = 0;
-      while (m1) {
-        const int b = __ffs(m1) - 1;
-        m1 &= m1 - 1;
-        const int64_t w0 = w1 * 32 + b;
-        cnt += __popc(bm0[w0]);
-        bm0[w0] = 0;
-      }
-    }
-    double tot = block_sum<THREADS>((double)cnt, red);
-    if (tid == 0) c_ptr[row] = (long long)(tot + 0.5);
-  } else {
-    // ordered emission: walk level-1 words in chunks of THREADS, block-scan the popcounts
-    if (tid == 0) s_base = c_ptr[row];
-    __syncthreads();
-    for (int64_t c0 = 0; c0 < words1; c0 += THREADS) {
-      const int64_t w1 = c0 + tid;
-      unsigned int m1 = (w1 < words1) ? bm1[w1] : 0u;
-      int mine = 0;
-      {
-        unsigned int t1 = m1;
-        while (t1) { const int b = __ffs(t1) - 1; t1 &= t1 - 1; mine += __popc(bm0[w1 * 32 + b]); }
-      }
-      // block exclusive scan of `mine`
-      int inc = mine;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
-      if (lane == 31) s_scan[wid] = inc;
-      __syncthreads();
-      int woff = 0, total = 0;
-      for (int w = 0; w < NWARPS; w++) { if (w < wid) woff += s_scan[w]; total += s_scan[w]; }
-      long long pos = s_base + woff + inc - mine;
-      if (m1) {
-        bm1[w1] = 0;
-        while (m1) {
-          const int b = __ffs(m1) - 1;
-          m1 &= m1 - 1;
-          const int64_t w0 = w1 * 32 + b;
-          unsigned int m0 = bm0[w0];
-          bm0[w0] = 0;
-          while (m0) {
-            const int bb = __ffs(m0) - 1;
-            m0 &= m0 - 1;
-            const int64_t j = w0 * 32 + bb;
-            c_idx[pos] = (int32_t)j;
-            c_val[pos] = acc[j];
-            acc[j] = (V)0;
-            pos++;
-          }
-        }
-      }
-      __syncthreads();
-      if (tid == 0) s_base += total;
-      __syncthreads();
-    }
-  }
-}
-
 // ---- host orchestration -----------------------------------------------------------------------------------------
 static int run_scan(long long* data, int64_t n, long long* block_sums, cudaStream_t st) {
   const int64_t nblocks = (n + SCAN_BLOCK - 1) / SCAN_BLOCK;
@@ -841,29 +702,6 @@ static int run_classes(int sm_count, const unsigned long long counts[8], const C
         L.bitmap_slot_bytes, L.bitmap_words0, L.bitmap_words1, (V*)dense, n);
     B2S_LAUNCH_CHECK();
   }
-  if (counts[6]) {
-    // hub rows: a few at a time, every one expanded by G CTAs (the slots are clean again: the class-5 kernel above
-    // leaves its bitmaps / accumulators zeroed, and stream order separates the two)
-    int64_t slots = L.nslots < 8 ? L.nslots : 8;
-    if (NUMERIC && dense_slots < slots) slots = dense_slots;
-    if ((int64_t)counts[6] < slots) slots = (int64_t)counts[6];
-    if (slots < 1) { set_error("dense accumulator workspace too small"); return B2S_ENOMEM; }
-    const int64_t cta_budget = (int64_t)sm_count * 8;        // 256-thread CTAs resident at once
-    for (int64_t rb = 0; rb < (int64_t)counts[6]; rb += slots) {
-      const int64_t nthis = ((int64_t)counts[6] - rb) < slots ? ((int64_t)counts[6] - rb) : slots;
-      int64_t G = cta_budget / nthis;
-      if (G < 1) G = 1;
-      if (G > 512) G = 512;
-      spgemm_dense_acc_kernel<V, P, 256, NUMERIC><<<(unsigned)(nthis * G), 256, 0, st>>>(
-          (int64_t)counts[6], rb, (int)G, perm + offs.off[6], ap, a_idx, av, bp, b_idx, bv, bitmaps, L.bitmap_slot_bytes,
-          L.bitmap_words0, (V*)dense, n);
-      B2S_LAUNCH_CHECK();
-      spgemm_dense_emit_kernel<V, 256, NUMERIC><<<(unsigned)nthis, 256, 0, st>>>(
-          (int64_t)counts[6], rb, perm + offs.off[6], c_ptr, c_idx, cv, bitmaps, L.bitmap_slot_bytes, L.bitmap_words0,
-          L.bitmap_words1, (V*)dense, n);
-      B2S_LAUNCH_CHECK();
-    }
-  }
   return B2S_OK;
 }
 
@@ -942,7 +780,7 @@ int b2s_spgemm_csr_symbolic(int pt, int64_t m, int64_t k, int64_t n, const void*
   unsigned long long flops = 0;
   ClsOffsets offs;
   if (int rc = run_binning<false>(m, ub, hdr, perm, true, counts, &flops, &offs, st)) return rc;
-  if (counts[5] || counts[6]) B2S_CUDA(cudaMemsetAsync(bitmaps, 0, (size_t)(L.bitmap_slot_bytes * L.nslots), st));
+  if (counts[5]) B2S_CUDA(cudaMemsetAsync(bitmaps, 0, (size_t)(L.bitmap_slot_bytes * L.nslots), st));
   int rc;
   long long* cp = (long long*)c_indptr;
   if (pt == B2S_I32) rc = run_classes<float, int32_t, false>(pr.sm_count, counts, offs, perm, a_indptr, a_indices, nullptr, b_indptr, b_indices, nullptr, cp, nullptr, nullptr, bitmaps, L, nullptr, 0, n, st);
@@ -958,7 +796,7 @@ int b2s_spgemm_csr_symbolic(int pt, int64_t m, int64_t k, int64_t n, const void*
   B2S_CUDA(cudaStreamSynchronize(st));
   info_host[0] = nnz;
   info_host[1] = (int64_t)flops;
-  info_host[2] = (int64_t)(counts2[5] + counts2[6]);
+  info_host[2] = (int64_t)counts2[5];
   return B2S_OK;
 }
 
@@ -983,7 +821,7 @@ int b2s_spgemm_csr_numeric(int vt, int pt, int64_t m, int64_t k, int64_t n, cons
   ClsOffsets offs;
   if (int rc = run_binning<true>(m, (const long long*)c_indptr, hdr, perm, false, counts, nullptr, &offs, st)) return rc;
   int64_t dense_slots = 0;
-  if (counts[5] || counts[6]) {
+  if (counts[5]) {
     const int64_t per = n * (vt == B2S_F32 ? 4 : 8);
     dense_slots = per > 0 ? dense_ws_bytes / per : 0;
     B2S_CHECK_ARG(dense_ws != nullptr && dense_slots >= 1, "numeric pass needs a dense accumulator workspace of >= %lld bytes", (long long)per);
