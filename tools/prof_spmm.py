@@ -15,7 +15,7 @@ A = gallery.banded(n, 11, dtype=np.float64)
 for k in ks:
     X = torch.rand((n, k), dtype=torch.float64, device="cuda")
     Y = torch.empty((n, k), dtype=torch.float64, device="cuda")
-    for kern in (1, 2, 3):
+    for kern in (1, 2, 3, 4):
         _lib.lib.b2s_spmm_set_kernel(kern)
         _ops.spmm(A._indptr, A._indices, A._data, X, Y, A.shape)
         torch.cuda.synchronize()
