@@ -18,6 +18,7 @@ static inline int resolve_cfg(int vt, bool scattered, bool likely_short) {
   if (forced >= 0) return forced;
   if (scattered && likely_short) return vt == B2S_F32 ? kScatterShortCfgF32 : kScatterShortCfgF64;
   if (scattered) return vt == B2S_F32 ? kScatterCfgF32 : kScatterCfgF64;
+  if (likely_short && vt == B2S_F64) return kShortCfgF64;
   return vt == B2S_F32 ? kDefaultCfgF32 : kDefaultCfgF64;
 }
 
@@ -187,9 +188,10 @@ int64_t b2s_spmv_plan_tiles(int vt, int64_t nrows, int64_t nnz) {
   // upper bound over the configurations plan_create may pick (it decides after sampling the matrix)
   int64_t m = 0;
   const int forced = g_cfg.load();
-  const int cands[5] = {forced >= 0 ? forced : (vt == B2S_F32 ? kDefaultCfgF32 : kDefaultCfgF64),
+  const int cands[6] = {forced >= 0 ? forced : (vt == B2S_F32 ? kDefaultCfgF32 : kDefaultCfgF64),
                         vt == B2S_F32 ? kScatterCfgF32 : kScatterCfgF64, vt == B2S_F32 ? kDefaultCfgF32 : kDefaultCfgF64,
-                        kScatterCfgF32, vt == B2S_F32 ? kScatterShortCfgF32 : kScatterShortCfgF64};
+                        kScatterCfgF32, vt == B2S_F32 ? kScatterShortCfgF32 : kScatterShortCfgF64,
+                        vt == B2S_F32 ? kDefaultCfgF32 : kShortCfgF64};
   for (int c : cands) { const int64_t t = tiles_for(c, vt, nrows, nnz); m = t > m ? t : m; }
   return m;
 }

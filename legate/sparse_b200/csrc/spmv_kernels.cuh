@@ -888,7 +888,7 @@ static int dispatch_cfg(int cfg, const SpmvArgs& a) {
 #define B2S_CFG_CASE(ID, K, A, B, C, D, XL)                               \
   case ID:                                                               \
     if constexpr (ID == kDefaultCfgF64 || ID == kDefaultCfgF32 || ID == kScatterCfgF64 || ID == kScatterCfgF32 || \
-                  ID == kScatterShortCfgF32 || ID == kScatterShortCfgF64 ||                                        \
+                  ID == kScatterShortCfgF32 || ID == kScatterShortCfgF64 || ID == kShortCfgF64 ||                  \
                   (sizeof(I) == 4 && sizeof(P) == 4))                                             \
       return launch_cfg<V, I, P, K, A, B, C, D, XL, DOT>(a);              \
     else                                                                 \
