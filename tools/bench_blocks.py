@@ -43,10 +43,12 @@ def blocks_of(A, P):
 
 
 def main():
-    Ps = [int(a) for a in sys.argv[1:]] or [2, 4, 8]
-    n = 10_000_000
+    weak = "--weak" in sys.argv          # 10M rows per shard, 10M*P columns (weak scaling) instead of 10M/P rows x 10M
+    one = "--one-block" in sys.argv      # profile mode: only block 1, default plan, 3 launches (target of ncu)
+    Ps = [int(a) for a in sys.argv[1:] if not a.startswith("--")] or [2, 4, 8]
     for P in Ps:
-        rows = n // P
+        n = 10_000_000 * (P if weak else 1)
+        rows = 10_000_000 if weak else n // P
         A = gallery.random_fixed(rows, n, 32, np.float32, seed=1234)
         x = torch.rand(n, dtype=torch.float32, device="cuda")
         y = torch.zeros(rows, dtype=torch.float32, device="cuda")
@@ -54,7 +56,15 @@ def main():
         t_unsplit = time_fn(lambda: _ops.spmv(A.indptr, A.indices, A.data, x, y, A.shape, plan=plan))
         print(f"P={P} shard {rows} rows: unsplit {plan.kernel_name}: {t_unsplit:8.1f} us", flush=True)
         blocks = blocks_of(A, P)
-        for cfg in (-1, 5, 8, 3, 0):
+        if one:
+            B = blocks[1]
+            pl = B._get_plan(tma_only=True)
+            for _ in range(3):
+                _ops.spmv_add(B.indptr, B.indices, B.data, x, y, B.shape, pl)
+            torch.cuda.synchronize()
+            print("profiled", pl.kernel_name, B.nnz, flush=True)
+            return
+        for cfg in ((-1, 8) if weak else (-1, 5, 8, 3, 0)):
             _lib.check(_lib.lib.b2s_spmv_set_config(cfg, 0))
             for flavor in (None, 0, 1, 2):
                 tot, names = 0.0, set()
