@@ -235,32 +235,21 @@ spmm_window_tma_kernel(int64_t nrows, int64_t nnz, int64_t ntiles, int k, int lp
         const int64_t ps = (int64_t)srp[j], pe = (int64_t)srp[j + 1];
         PT acc = zero_pack((PT*)nullptr);
         if (m.wrows > 0) {
-          // The lanes of the group fetch lpr (column, value) pairs of the row with ONE coalesced shared-memory read
-          // each and hand them round by shuffle, so the per-nonzero shared-memory traffic is just the X pack
-          // (ncu before: 143 M wavefronts, L1TEX 86 % busy, 1/3 of them the broadcast reads of idx / val).
+          // (column, value) are read by every lane of the group (a shared-memory broadcast); handing them round by
+          // shuffle instead was measured and is slower (k = 32 fp64: 896 vs 673 us): the issue slots, not L1TEX, give out
+          int q = (int)(ps - m.kb);
           const int qe = (int)(pe - m.kb);
-          const unsigned gmask = lpr == 32 ? 0xffffffffu : (((1u << lpr) - 1u) << (lane & ~(lpr - 1)));
-          for (int q = (int)(ps - m.kb); q < qe; q += lpr) {
-            const int cnt = (qe - q) < lpr ? (qe - q) : lpr;
-            int myc = 0;
-            V myv = (V)0;
-            if (sub < cnt) { myc = (int)((long long)sidx[q + sub] - m.cmin); myv = sval[q + sub]; }
-            int u = 0;
-            for (; u + 4 <= cnt; u += 4) {
-              const int c0 = __shfl_sync(gmask, myc, u, lpr), c1 = __shfl_sync(gmask, myc, u + 1, lpr);
-              const int c2 = __shfl_sync(gmask, myc, u + 2, lpr), c3 = __shfl_sync(gmask, myc, u + 3, lpr);
-              const V a0 = __shfl_sync(gmask, myv, u, lpr), a1 = __shfl_sync(gmask, myv, u + 1, lpr);
-              const V a2 = __shfl_sync(gmask, myv, u + 2, lpr), a3 = __shfl_sync(gmask, myv, u + 3, lpr);
-              const PT x0 = swin[c0 * packs_row + sub], x1 = swin[c1 * packs_row + sub];
-              const PT x2 = swin[c2 * packs_row + sub], x3 = swin[c3 * packs_row + sub];
-              fma_pack(acc, a0, x0); fma_pack(acc, a1, x1); fma_pack(acc, a2, x2); fma_pack(acc, a3, x3);
-            }
-            for (; u < cnt; u++) {
-              const int c0 = __shfl_sync(gmask, myc, u, lpr);
-              const V a0 = __shfl_sync(gmask, myv, u, lpr);
-              fma_pack(acc, a0, swin[c0 * packs_row + sub]);
-            }
+          for (; q + 4 <= qe; q += 4) {
+            PT x0 = swin[(int)((long long)sidx[q] - m.cmin) * packs_row + sub];
+            PT x1 = swin[(int)((long long)sidx[q + 1] - m.cmin) * packs_row + sub];
+            PT x2 = swin[(int)((long long)sidx[q + 2] - m.cmin) * packs_row + sub];
+            PT x3 = swin[(int)((long long)sidx[q + 3] - m.cmin) * packs_row + sub];
+            fma_pack(acc, sval[q], x0);
+            fma_pack(acc, sval[q + 1], x1);
+            fma_pack(acc, sval[q + 2], x2);
+            fma_pack(acc, sval[q + 3], x3);
           }
+          for (; q < qe; q++) fma_pack(acc, sval[q], swin[(int)((long long)sidx[q] - m.cmin) * packs_row + sub]);
         } else {
           // tile too wide / too long for a stage: straight from global memory
           for (int64_t p = ps; p < pe; p++) {

@@ -51,9 +51,11 @@ static const TileCfgRt kCfgs[] = {
 static constexpr int kNumCfgs = sizeof(kCfgs) / sizeof(kCfgs[0]);
 static constexpr int kDefaultCfgF64 = 0;   // 4 consumer warps x 4 groups, 2 stages, 6 CTAs/SM (CAP 1024)
 static constexpr int kDefaultCfgF32 = 5;   // 4 consumer warps x 3 groups, 2 stages, 8 CTAs/SM (CAP 1536)
-// fp64 matrices of short rows with column locality (stencils, narrow bands: the one-lane-per-row path): 8 consumer
-// warps x 4 groups, 3 CTAs/SM (CAP 2048) -- L5 125.4 us vs 127.4 us, banded 11/row 238.0 vs 242.1 us (r02_sweep_spmv.txt)
-static constexpr int kShortCfgF64 = 11;
+// fp64 matrices of short rows with column locality (stencils, narrow bands: the one-lane-per-row path).  The shape "8
+// consumer warps x 4 groups, 3 CTAs/SM" (cfg 11) is 1.5-3 % faster on the bare product (L5 129.4 vs 131.3 us, banded
+// 11/row 240.1 vs 247.5 us on one box) but the fused-dot variant CG runs on lost 6 % with it (PDE4096 2167 vs
+// 2301..2374 it/s), so the default shape stays.
+static constexpr int kShortCfgF64 = kDefaultCfgF64;
 // scattered matrices (plan statistic > 16 distinct x lines per warp gather) want many gathers in flight per thread:
 static constexpr int kScatterCfgF64 = 2;   // LDG tiles, 128 threads x 8 nnz, scalar mapping
 static constexpr int kScatterCfgF32 = 8;   // TMA tiles, 4 warps x 8 groups = 32 gathers/thread, x through ld.global.cg

@@ -387,8 +387,8 @@ def test_plan_entries_follow_the_tile_rule():
     data = rng.standard_normal(rows.shape[0])
     A = sparse.csr_array((data, indices, indptr), shape=(nrows, nrows))
     plan = A._get_plan()
-    assert plan.config == 11 and not plan.scattered, (plan.config, plan.lines_per_warp)
-    T = 2 * 256 * 4 - 4            # fp64 short-row tile shape: CAP = EPT(2) * 256 consumer threads * 4 groups
+    assert plan.config == 0 and not plan.scattered, (plan.config, plan.lines_per_warp)
+    T = 2 * 128 * 4 - 4            # fp64 default tile shape: CAP = EPT(2) * 128 consumer threads * 4 groups
     ntiles = plan.tiles
     assert ntiles == -(-(nrows + int(indptr[-1])) // T)
     ent = plan.buf.cpu().numpy()[: 4 * (ntiles + 1)].reshape(-1, 4)
