@@ -239,15 +239,33 @@ spmm_window_tma_kernel(int64_t nrows, int64_t nnz, int64_t ntiles, int k, int lp
           // shuffle instead was measured and is slower (k = 32 fp64: 896 vs 673 us): the issue slots, not L1TEX, give out
           int q = (int)(ps - m.kb);
           const int qe = (int)(pe - m.kb);
+          // head: up to the next 4-aligned slot, so that the main loop reads four (column, value) pairs with 16-byte
+          // broadcast loads (one shared-memory wavefront for 4 columns instead of four)
+          for (; q < qe && (q & 3) != 0; q++) fma_pack(acc, sval[q], swin[(int)((long long)sidx[q] - m.cmin) * packs_row + sub]);
           for (; q + 4 <= qe; q += 4) {
-            PT x0 = swin[(int)((long long)sidx[q] - m.cmin) * packs_row + sub];
-            PT x1 = swin[(int)((long long)sidx[q + 1] - m.cmin) * packs_row + sub];
-            PT x2 = swin[(int)((long long)sidx[q + 2] - m.cmin) * packs_row + sub];
-            PT x3 = swin[(int)((long long)sidx[q + 3] - m.cmin) * packs_row + sub];
-            fma_pack(acc, sval[q], x0);
-            fma_pack(acc, sval[q + 1], x1);
-            fma_pack(acc, sval[q + 2], x2);
-            fma_pack(acc, sval[q + 3], x3);
+            long long c0, c1, c2, c3;
+            if constexpr (sizeof(I) == 4) {
+              const int4 c4 = *reinterpret_cast<const int4*>(sidx + q);
+              c0 = c4.x; c1 = c4.y; c2 = c4.z; c3 = c4.w;
+            } else {
+              c0 = (long long)sidx[q]; c1 = (long long)sidx[q + 1]; c2 = (long long)sidx[q + 2]; c3 = (long long)sidx[q + 3];
+            }
+            V a0, a1, a2, a3;
+            if constexpr (sizeof(V) == 4) {
+              const float4 a4 = *reinterpret_cast<const float4*>(sval + q);
+              a0 = a4.x; a1 = a4.y; a2 = a4.z; a3 = a4.w;
+            } else {
+              const double2 a01 = *reinterpret_cast<const double2*>(sval + q), a23 = *reinterpret_cast<const double2*>(sval + q + 2);
+              a0 = a01.x; a1 = a01.y; a2 = a23.x; a3 = a23.y;
+            }
+            const PT x0 = swin[(int)(c0 - m.cmin) * packs_row + sub];
+            const PT x1 = swin[(int)(c1 - m.cmin) * packs_row + sub];
+            const PT x2 = swin[(int)(c2 - m.cmin) * packs_row + sub];
+            const PT x3 = swin[(int)(c3 - m.cmin) * packs_row + sub];
+            fma_pack(acc, a0, x0);
+            fma_pack(acc, a1, x1);
+            fma_pack(acc, a2, x2);
+            fma_pack(acc, a3, x3);
           }
           for (; q < qe; q++) fma_pack(acc, sval[q], swin[(int)((long long)sidx[q] - m.cmin) * packs_row + sub]);
         } else {

@@ -244,6 +244,22 @@ def _worker(rank, world, port, case, q):
             assert C.nnz_offset == ref.indptr[lo] and C.global_nnz == ref.nnz
             G = bd.gather_matrix(C).to_scipy_sparse_csr()
             assert (G != ref).nnz == 0
+            # nnz-balanced row cuts of A (uneven shards): C keeps A's row plan (it used to fall back to equal tiles)
+            skew = SA.tolil()
+            skew[:20, :] = 1.0                       # heavy leading rows -> very uneven balanced cuts
+            SK = skew.tocsr()
+            Ab = bd.dist_csr_array.from_global(SK, balanced=True)
+            assert not Ab.row_plan.uniform
+            Cb = bd.spgemm(Ab, B)
+            assert Cb.row_plan.bounds == Ab.row_plan.bounds
+            refb = (SK @ SB).tocsr()
+            refb.sort_indices()
+            lob, hib = Cb.row_plan.rows(rank)
+            locb = Cb.local.to_scipy_sparse_csr()
+            assert locb.shape[0] == hib - lob
+            assert np.array_equal(locb.indptr, refb.indptr[lob : hib + 1] - refb.indptr[lob])
+            assert np.array_equal(locb.indices, refb.indices[refb.indptr[lob] : refb.indptr[hib]])
+            assert Cb.nnz_offset == refb.indptr[lob] and Cb.global_nnz == refb.nnz
             out["ok"] = True
         elif case == "cg":
             from oracle import oracle as orc
