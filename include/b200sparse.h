@@ -313,6 +313,9 @@ int         b2s_allreduce_scalars(void* comm, void* scalars_dev, int count, void
  * rate the memory system sustains for the access pattern of a uniformly random CSR SpMV (BASELINE config 4).  Timed
  * by bench.py beside the R32 product; not used by any product path. */
 int         b2s_probe_gather(int vt, int64_t ncols, int64_t ngathers, const void* x_dev, void* out_dev, void* stream);
+/* cudaLimitMaxL2FetchGranularity of the current device (bytes L2 fetches from HBM per miss: 32 / 64 / 128; a driver
+ * hint).  set_bytes = 0 reads it back only.  Relevant for scattered reads of vectors larger than L2. */
+int         b2s_device_l2_fetch_granularity(int set_bytes, int64_t* current);
 
 #ifdef __cplusplus
 }

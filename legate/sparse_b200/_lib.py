@@ -81,6 +81,7 @@ SIGNATURES = {
     "b2s_allgather_x": (c_i32, [c_i32, c_i32, c_vp, c_i64, c_vp, c_vp]),
     "b2s_allreduce_scalars": (c_i32, [c_vp, c_vp, c_i32, c_vp]),
     "b2s_probe_gather": (c_i32, [c_i32, c_i64, c_i64, c_vp, c_vp, c_vp]),
+    "b2s_device_l2_fetch_granularity": (c_i32, [c_i32, ctypes.POINTER(c_i64)]),
     # tuning hooks (not in the public header)
     "b2s_spmv_set_config": (c_i32, [c_i32, c_i32]),
     "b2s_spmv_get_config": (c_i32, []),

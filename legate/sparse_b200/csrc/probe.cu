@@ -47,3 +47,15 @@ extern "C" int b2s_probe_gather(int vt, int64_t ncols, int64_t ngathers, const v
   B2S_LAUNCH_CHECK();
   return B2S_OK;
 }
+
+// cudaLimitMaxL2FetchGranularity of the current device: the size (32 / 64 / 128 bytes) L2 fetches from HBM on a miss.
+// A hint to the driver; matters only for scattered reads of a vector larger than L2 (weak-scaled R32: x = 320 MB), where
+// 128-byte fills move 4x the sectors the product consumes.  set_bytes = 0 only reads the limit back.
+extern "C" int b2s_device_l2_fetch_granularity(int set_bytes, int64_t* current) {
+  B2S_CHECK_ARG(set_bytes == 0 || set_bytes == 32 || set_bytes == 64 || set_bytes == 128, "granularity must be 0/32/64/128");
+  if (set_bytes) B2S_CUDA(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)set_bytes));
+  size_t v = 0;
+  B2S_CUDA(cudaDeviceGetLimit(&v, cudaLimitMaxL2FetchGranularity));
+  if (current) *current = (int64_t)v;
+  return B2S_OK;
+}

@@ -129,8 +129,11 @@ struct Layout {
   static constexpr int TOTAL = BAR_OFF + 2 * STAGES * 8;
 };
 
-// k*sizeof(V) <= 512 bytes (one 16-byte pack per lane, lpr = k / N lanes per row, a power of two <= 32)
-template <typename V, typename I, typename P>
+// NP 16-byte packs per lane, lpr = k / (N * NP) lanes per row (a power of two <= 32).  NP > 1 puts more rows of A on a
+// warp: the (column, value) broadcast reads and the address arithmetic of a step are shared by 32 / lpr rows, so both the
+// instruction count and the shared-memory wavefronts per nonzero drop (k = 32 fp64: 3.5 -> 2.5 instructions, 3 -> 2.5
+// wavefronts per nonzero with NP = 2)
+template <typename V, typename I, typename P, int NP>
 __global__ void __launch_bounds__(THREADS, 2)
 spmm_window_tma_kernel(int64_t nrows, int64_t nnz, int64_t ntiles, int k, int lpr_shift, const P* __restrict__ indptr,
                        const I* __restrict__ indices, const V* __restrict__ vals, const V* __restrict__ X, int64_t ldx,
@@ -230,52 +233,52 @@ spmm_window_tma_kernel(int64_t nrows, int64_t nnz, int64_t ntiles, int k, int lp
       const V* sval = reinterpret_cast<const V*>(st + LY::IDX_B);
       const P* srp = reinterpret_cast<const P*>(st + LY::IDX_B + LY::VAL_B) + (m.r0 & 3);
       const PT* swin = reinterpret_cast<const PT*>(st + LY::IDX_B + LY::VAL_B + LY::RP_B);
-      const int packs_row = k / N;              // == lpr
+      const int packs_row = k / N;              // == lpr * NP
       for (int j = grp; j < m.nr; j += ngrp) {
         const int64_t ps = (int64_t)srp[j], pe = (int64_t)srp[j + 1];
-        PT acc = zero_pack((PT*)nullptr);
+        PT acc[NP];
+#pragma unroll
+        for (int u = 0; u < NP; u++) acc[u] = zero_pack((PT*)nullptr);
         if (m.wrows > 0) {
           // (column, value) are read by every lane of the group (a shared-memory broadcast); handing them round by
-          // shuffle instead was measured and is slower (k = 32 fp64: 896 vs 673 us): the issue slots, not L1TEX, give out
+          // shuffle instead was measured and is slower (k = 32 fp64: 896 vs 673 us): the issue slots, not L1TEX, give out.
+          // 16-byte broadcast loads of four pairs behind an alignment head loop: 821 us (rows of 11 are mostly head/tail)
           int q = (int)(ps - m.kb);
           const int qe = (int)(pe - m.kb);
-          // head: up to the next 4-aligned slot, so that the main loop reads four (column, value) pairs with 16-byte
-          // broadcast loads (one shared-memory wavefront for 4 columns instead of four)
-          for (; q < qe && (q & 3) != 0; q++) fma_pack(acc, sval[q], swin[(int)((long long)sidx[q] - m.cmin) * packs_row + sub]);
-          for (; q + 4 <= qe; q += 4) {
-            long long c0, c1, c2, c3;
-            if constexpr (sizeof(I) == 4) {
-              const int4 c4 = *reinterpret_cast<const int4*>(sidx + q);
-              c0 = c4.x; c1 = c4.y; c2 = c4.z; c3 = c4.w;
-            } else {
-              c0 = (long long)sidx[q]; c1 = (long long)sidx[q + 1]; c2 = (long long)sidx[q + 2]; c3 = (long long)sidx[q + 3];
+          constexpr int UN = NP >= 4 ? 2 : 4;    // nonzeros in flight per group: UN * NP 16-byte loads
+          for (; q + UN <= qe; q += UN) {
+            PT x[UN][NP];
+#pragma unroll
+            for (int e = 0; e < UN; e++) {
+              const PT* xr = swin + (int)((long long)sidx[q + e] - m.cmin) * packs_row + sub;
+#pragma unroll
+              for (int u = 0; u < NP; u++) x[e][u] = xr[u * lpr];
             }
-            V a0, a1, a2, a3;
-            if constexpr (sizeof(V) == 4) {
-              const float4 a4 = *reinterpret_cast<const float4*>(sval + q);
-              a0 = a4.x; a1 = a4.y; a2 = a4.z; a3 = a4.w;
-            } else {
-              const double2 a01 = *reinterpret_cast<const double2*>(sval + q), a23 = *reinterpret_cast<const double2*>(sval + q + 2);
-              a0 = a01.x; a1 = a01.y; a2 = a23.x; a3 = a23.y;
+#pragma unroll
+            for (int e = 0; e < UN; e++) {
+              const V a = sval[q + e];
+#pragma unroll
+              for (int u = 0; u < NP; u++) fma_pack(acc[u], a, x[e][u]);
             }
-            const PT x0 = swin[(int)(c0 - m.cmin) * packs_row + sub];
-            const PT x1 = swin[(int)(c1 - m.cmin) * packs_row + sub];
-            const PT x2 = swin[(int)(c2 - m.cmin) * packs_row + sub];
-            const PT x3 = swin[(int)(c3 - m.cmin) * packs_row + sub];
-            fma_pack(acc, a0, x0);
-            fma_pack(acc, a1, x1);
-            fma_pack(acc, a2, x2);
-            fma_pack(acc, a3, x3);
           }
-          for (; q < qe; q++) fma_pack(acc, sval[q], swin[(int)((long long)sidx[q] - m.cmin) * packs_row + sub]);
+          for (; q < qe; q++) {
+            const PT* xr = swin + (int)((long long)sidx[q] - m.cmin) * packs_row + sub;
+            const V a = sval[q];
+#pragma unroll
+            for (int u = 0; u < NP; u++) fma_pack(acc[u], a, xr[u * lpr]);
+          }
         } else {
           // tile too wide / too long for a stage: straight from global memory
           for (int64_t p = ps; p < pe; p++) {
-            const PT xv = __ldg(reinterpret_cast<const PT*>(X + (int64_t)indices[p] * ldx) + sub);
-            fma_pack(acc, vals[p], xv);
+            const PT* xr = reinterpret_cast<const PT*>(X + (int64_t)indices[p] * ldx) + sub;
+            const V a = vals[p];
+#pragma unroll
+            for (int u = 0; u < NP; u++) fma_pack(acc[u], a, __ldg(xr + u * lpr));
           }
         }
-        reinterpret_cast<PT*>(Y + (int64_t)(m.r0 + j) * ldy)[sub] = acc;
+        PT* yr = reinterpret_cast<PT*>(Y + (int64_t)(m.r0 + j) * ldy) + sub;
+#pragma unroll
+        for (int u = 0; u < NP; u++) yr[u * lpr] = acc[u];
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[s]);
@@ -294,11 +297,20 @@ int spmm_window_try(int64_t nrows, int64_t nnz, int64_t k, const void* indptr, c
   *used = 0;
   constexpr int N = Pk<V>::N;
   if (nrows <= 0 || nnz <= 0 || k <= 0) return B2S_OK;
-  // eligibility: one 16-byte pack per lane, a power-of-two number of lanes per row, contiguous 16-byte aligned rows
+  // eligibility: 16-byte packs, a power-of-two number of them per row, contiguous 16-byte aligned rows
   if (k % N != 0) return B2S_OK;
-  const int64_t lpr = k / N;
-  if (lpr > 32 || (lpr & (lpr - 1)) != 0) return B2S_OK;
-  if (!force && lpr < 8) return B2S_OK;   // X rows under 128 bytes: the gather kernels are as fast (k = 8: 330 vs 343 us)
+  const int64_t packs = k / N;
+  if (packs > 128 || (packs & (packs - 1)) != 0) return B2S_OK;
+  if (!force && packs < 8) return B2S_OK;   // X rows under 128 bytes: the gather kernels are as fast (k = 8: 330 vs 343 us)
+  // packs per lane: as many as keep 8 lanes on a row (quarter-warp 16-byte accesses stay conflict-free), at most 4
+  int np = 1;
+  while (np < 4 && packs / (np * 2) >= 8) np *= 2;
+  if (const char* e = getenv("B2S_SPMM_NP")) {
+    const int v = atoi(e);
+    if ((v == 1 || v == 2 || v == 4) && packs % v == 0) np = v;
+  }
+  const int64_t lpr = packs / np;
+  if (lpr > 32) return B2S_OK;
   if (ldx != k || (ldy % N) != 0 || !aligned16(X) || !aligned16(Y) || !aligned16(indices) || !aligned16(vals) || !aligned16(indptr))
     return B2S_OK;
   int shift = 0;
@@ -346,13 +358,20 @@ int spmm_window_try(int64_t nrows, int64_t nnz, int64_t k, const void* indptr, c
     }
   }
   using LY = Layout<V, I, P>;
-  auto kern = spmm_window_tma_kernel<V, I, P>;
-  struct TagSpmmW {};
-  if (int rc = ensure_dyn_smem<TagSpmmW>(kern, LY::TOTAL)) return rc;
   int64_t grid = (int64_t)pr.sm_count * 2;
   if (grid > ntiles) grid = ntiles;
-  kern<<<(unsigned)grid, THREADS, LY::TOTAL, st>>>(nrows, nnz, ntiles, (int)k, shift, (const P*)indptr, (const I*)indices,
-                                                   (const V*)vals, (const V*)X, ldx, (V*)Y, ldy, plan);
+  auto launch = [&](auto kern, auto tag) -> int {
+    if (int rc = ensure_dyn_smem<decltype(tag)>(kern, LY::TOTAL)) return rc;
+    kern<<<(unsigned)grid, THREADS, LY::TOTAL, st>>>(nrows, nnz, ntiles, (int)k, shift, (const P*)indptr, (const I*)indices,
+                                                     (const V*)vals, (const V*)X, ldx, (V*)Y, ldy, plan);
+    return B2S_OK;
+  };
+  struct TagW1 {}; struct TagW2 {}; struct TagW4 {};
+  int lrc;
+  if (np == 4) lrc = launch(spmm_window_tma_kernel<V, I, P, 4>, TagW4{});
+  else if (np == 2) lrc = launch(spmm_window_tma_kernel<V, I, P, 2>, TagW2{});
+  else lrc = launch(spmm_window_tma_kernel<V, I, P, 1>, TagW1{});
+  if (lrc) { cudaFreeAsync(plan, st); return lrc; }
   B2S_LAUNCH_CHECK();
   B2S_CUDA(cudaFreeAsync(plan, st));
   *used = 1;

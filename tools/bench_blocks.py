@@ -42,7 +42,39 @@ def blocks_of(A, P):
     return out
 
 
+def l2_gran(set_bytes=0):
+    import ctypes
+    cur = ctypes.c_int64(0)
+    _lib.check(_lib.lib.b2s_device_l2_fetch_granularity(set_bytes, ctypes.byref(cur)))
+    return cur.value
+
+
+def gran_sweep(P):
+    """--l2gran: the weak-scaled shard (x = 40 MB * P) unsplit and in column blocks under each L2 fetch granularity."""
+    n = 10_000_000 * P
+    rows = 10_000_000
+    A = gallery.random_fixed(rows, n, 32, np.float32, seed=1234)
+    x = torch.rand(n, dtype=torch.float32, device="cuda")
+    y = torch.zeros(rows, dtype=torch.float32, device="cuda")
+    plan = A._get_plan()
+    blocks = blocks_of(A, P)
+    plans = [B._get_plan(tma_only=True) for B in blocks]
+    print(f"l2 fetch granularity at start: {l2_gran()} bytes", flush=True)
+    for g in (128, 64, 32, 128):
+        got = l2_gran(g)
+        t_un = time_fn(lambda: _ops.spmv(A.indptr, A.indices, A.data, x, y, A.shape, plan=plan), reps=10)
+        tot = 0.0
+        for B, pl in zip(blocks, plans):
+            tot += time_fn(lambda: _ops.spmv_add(B.indptr, B.indices, B.data, x, y, B.shape, pl), reps=10)
+        print(f"P={P} weak, l2 fetch granularity set {g} -> {got}: unsplit {t_un:8.1f} us ({plan.kernel_name}), "
+              f"{P} blocks {tot:8.1f} us ({plans[0].kernel_name})", flush=True)
+
+
 def main():
+    if "--l2gran" in sys.argv:
+        for P in [int(a) for a in sys.argv[1:] if not a.startswith("--")] or [8]:
+            gran_sweep(P)
+        return
     weak = "--weak" in sys.argv          # 10M rows per shard, 10M*P columns (weak scaling) instead of 10M/P rows x 10M
     one = "--one-block" in sys.argv      # profile mode: only block 1, default plan, 3 launches (target of ncu)
     Ps = [int(a) for a in sys.argv[1:] if not a.startswith("--")] or [2, 4, 8]
@@ -53,7 +85,7 @@ def main():
         x = torch.rand(n, dtype=torch.float32, device="cuda")
         y = torch.zeros(rows, dtype=torch.float32, device="cuda")
         plan = A._get_plan()
-        t_unsplit = time_fn(lambda: _ops.spmv(A.indptr, A.indices, A.data, x, y, A.shape, plan=plan))
+        t_unsplit = 0.0 if one else time_fn(lambda: _ops.spmv(A.indptr, A.indices, A.data, x, y, A.shape, plan=plan))
         print(f"P={P} shard {rows} rows: unsplit {plan.kernel_name}: {t_unsplit:8.1f} us", flush=True)
         blocks = blocks_of(A, P)
         if one:
