@@ -572,21 +572,27 @@ spmv_tma_kernel(TileOrder order, int64_t nrows, int64_t nnz, const P* __restrict
       const int shortlen = m.pad < 0 ? -m.pad : (m.pad <= kShortRowMax ? m.pad : 0);
       if (FLAVOR == 2 && shortlen > 0) {
         const int maxlen = shortlen;
-        for (int j = ctid; j < nr; j += CT) {
-          const int sidx = (int)((int64_t)srp[j] - kb), eidx = (int)((int64_t)srp[j + 1] - kb);
+        for (int j0 = ctid - lane; j0 < nr; j0 += CT) {      // warp-uniform trip count (the round count below is per warp)
+          const int j = j0 + lane;
+          const bool live = j < nr;
+          const int sidx = live ? (int)((int64_t)srp[j] - kb) : 0, eidx = live ? (int)((int64_t)srp[j + 1] - kb) : 0;
           const int row = r0 + j;
           // y += A x: fetch the old y BEFORE the gathers so the two global round trips overlap
-          const V yold = acc_y ? __ldcg(y + row) : (V)0;
+          const V yold = (acc_y && live) ? __ldcg(y + row) : (V)0;
+          // rounds of 8 gathers: as many as the longest row of THIS warp needs, not of the tile (ragged rows: the tile's
+          // longest row is an outlier; every round is one more dependent trip to L2)
+          const int wlen = maxlen > 8 ? (int)__reduce_max_sync(0xffffffffu, (unsigned)(eidx - sidx)) : maxlen;
           V sum;
           if (remote_tile) {   // columns other GPUs push: L2-coherent gathers (tile-uniform branch)
             if (maxlen <= 5) sum = short_row_sum<5, 2>(scols, svals, x, sidx, eidx, 5);
-            else             sum = short_row_sum<8, 2>(scols, svals, x, sidx, eidx, maxlen);
+            else             sum = short_row_sum<8, 2>(scols, svals, x, sidx, eidx, wlen);
           }
           else if (maxlen <= 4) sum = short_row_sum<4, XL>(scols, svals, x, sidx, eidx, 4);
           else if (maxlen <= 5) sum = short_row_sum<5, XL>(scols, svals, x, sidx, eidx, 5);
           else if (maxlen <= 6) sum = short_row_sum<6, XL>(scols, svals, x, sidx, eidx, 6);
           else if (maxlen <= 7) sum = short_row_sum<7, XL>(scols, svals, x, sidx, eidx, 7);
-          else                  sum = short_row_sum<8, XL>(scols, svals, x, sidx, eidx, maxlen);
+          else                  sum = short_row_sum<8, XL>(scols, svals, x, sidx, eidx, wlen);
+          if (!live) continue;
           sum += yold;
           y[row] = sum;
           if (DOT) dot_acc += (double)sum * (double)w[row];

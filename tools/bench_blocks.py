@@ -78,6 +78,9 @@ def main():
     weak = "--weak" in sys.argv          # 10M rows per shard, 10M*P columns (weak scaling) instead of 10M/P rows x 10M
     one = "--one-block" in sys.argv      # profile mode: only block 1, default plan, 3 launches (target of ncu)
     Ps = [int(a) for a in sys.argv[1:] if not a.startswith("--")] or [2, 4, 8]
+    nblk = [int(a.split("=")[1]) for a in sys.argv[1:] if a.startswith("--nblocks=")]   # column blocks != ranks
+    cfgs = [int(c) for a in sys.argv[1:] if a.startswith("--cfgs=") for c in a.split("=")[1].split(",")]
+    flavors = [None, 0, 1, 2] if "--all-flavors" in sys.argv or not weak else [None]
     for P in Ps:
         n = 10_000_000 * (P if weak else 1)
         rows = 10_000_000 if weak else n // P
@@ -87,7 +90,8 @@ def main():
         plan = A._get_plan()
         t_unsplit = 0.0 if one else time_fn(lambda: _ops.spmv(A.indptr, A.indices, A.data, x, y, A.shape, plan=plan))
         print(f"P={P} shard {rows} rows: unsplit {plan.kernel_name}: {t_unsplit:8.1f} us", flush=True)
-        blocks = blocks_of(A, P)
+        Q = nblk[0] if nblk else P
+        blocks = blocks_of(A, Q)
         if one:
             B = blocks[1]
             pl = B._get_plan(tma_only=True)
@@ -96,9 +100,9 @@ def main():
             torch.cuda.synchronize()
             print("profiled", pl.kernel_name, B.nnz, flush=True)
             return
-        for cfg in ((-1, 8) if weak else (-1, 5, 8, 3, 0)):
+        for cfg in (cfgs or ((-1, 8) if weak else (-1, 5, 8, 3, 0))):
             _lib.check(_lib.lib.b2s_spmv_set_config(cfg, 0))
-            for flavor in (None, 0, 1, 2):
+            for flavor in flavors:
                 tot, names = 0.0, set()
                 for B in blocks:
                     B._plan = None
@@ -107,7 +111,7 @@ def main():
                         pl.set_flavor(flavor)
                     names.add(pl.kernel_name)
                     tot += time_fn(lambda: _ops.spmv_add(B.indptr, B.indices, B.data, x, y, B.shape, pl), reps=10)
-                print(f"   cfg {cfg:2d} flavor {str(flavor):4s}: sum over {P} blocks {tot:8.1f} us   ({sorted(names)[0]})", flush=True)
+                print(f"   cfg {cfg:2d} flavor {str(flavor):4s}: sum over {Q} blocks {tot:8.1f} us   ({sorted(names)[0]})", flush=True)
         _lib.check(_lib.lib.b2s_spmv_set_config(-1, 0))
         del A, blocks, x, y
         torch.cuda.empty_cache()
