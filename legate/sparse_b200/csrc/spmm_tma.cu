@@ -10,12 +10,11 @@
 // 16-byte stores.  L2->SM traffic for X drops from nnz*k*sv to (distinct columns per tile)*k*sv, and the copy of tile
 // t+1 overlaps the products of tile t.
 //
-// The producer WARP finds [cmin, cmax] of the next tile itself (32 lanes scan the tile's column indices, which the bulk
-// copy issued a moment later then finds in L2) while the consumers are busy with the current one, so the library stays
-// stateless without a pass over `indices` per call.  Tiles whose window or nonzeros do not fit a stage (wide column
-// spans, very long rows) are multiplied by the consumers straight from global memory, so the kernel is correct for
-// every matrix; the launcher only selects it when most tiles fit (one counting pre-pass per matrix STRUCTURE, its
-// verdict remembered), else the gather kernels of spmm.cu run.
+// A small pre-kernel computes [cmin, cmax] per tile on every call (one pass over `indices`; the library stays
+// stateless).  Letting the producer warp find the window of the next tile itself was tried and is slower (k = 32 fp64:
+// 795 vs 567 us -- the scan's two dependent trips to memory per tile sit on the producer's critical path).  Tiles whose window or nonzeros do not fit a stage (wide column spans, very long rows) are multiplied by
+// the consumers straight from global memory, so the kernel is correct for every matrix; the launcher only selects it
+// when most tiles fit (`win_ok` fraction), else the gather kernels of spmm.cu run.
 // Replaces SpMMCSR::gpu_variant (reference src/sparse/array/csr/spmm.cu:25-110) on that class of matrices.
 #include "common.cuh"
 #include <limits.h>
@@ -32,10 +31,10 @@ constexpr int R = 64;                 // rows of A per tile
 constexpr int NCAP = 1024;            // nonzeros staged per tile (+4 alignment slack)
 constexpr int WIN_BYTES = 40 * 1024;  // X window per stage
 
-struct TileInfo {
-  long long k0, k1;                   // nonzero range of the tile
+struct __align__(16) TilePlan {
   long long cmin;                     // first column of the window
   int wrows;                          // rows of X in the window; 0 = tile does not fit (direct path)
+  int pad;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -69,22 +68,27 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                : "memory");
 }
 
-// warp-collective: nonzero range and column window of tile t (R rows); wrows = 0 when the tile cannot be staged
+// [cmin, cmax] of every tile of R rows; wrows = 0 when the tile cannot be staged
 template <typename I, typename P>
-__device__ __forceinline__ TileInfo tile_window(int64_t t, int64_t nrows, const P* __restrict__ indptr,
-                                                const I* __restrict__ indices, int win_rows_cap, int lane) {
+__global__ void __launch_bounds__(256)
+tile_window_kernel(int64_t nrows, int64_t ntiles, const P* __restrict__ indptr, const I* __restrict__ indices,
+                   int win_rows_cap, TilePlan* __restrict__ plan, unsigned long long* __restrict__ fit_count) {
+  const int lane = threadIdx.x & 31;
+  const int64_t t = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;   // one warp per tile
+  if (t >= ntiles) return;
   const int64_t r0 = t * R, r1 = (r0 + R < nrows) ? r0 + R : nrows;
-  TileInfo ti;
-  ti.k0 = (long long)indptr[r0];
-  ti.k1 = (long long)indptr[r1];
-  ti.cmin = 0;
-  ti.wrows = 0;
-  if (ti.k1 - ti.k0 > NCAP || ti.k1 <= ti.k0) return ti;   // uniform over the warp
+  const int64_t lo = (int64_t)indptr[r0], hi = (int64_t)indptr[r1];
   long long mn = LLONG_MAX, mx = -1;
-  for (long long q = ti.k0 + lane; q < ti.k1; q += 32) {
-    const long long c = (long long)indices[q];
-    mn = c < mn ? c : mn;
-    mx = c > mx ? c : mx;
+  // 8 independent loads per lane and round (a tile is ~R * nnz/row indices: two or three rounds, not twenty dependent ones)
+  for (int64_t q = lo + lane; q < hi; q += 32 * 8) {
+    I c[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) c[u] = (q + 32 * u < hi) ? indices[q + 32 * u] : (I)-1;
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      const long long v = (long long)c[u];
+      if (v >= 0) { mn = v < mn ? v : mn; mx = v > mx ? v : mx; }
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -92,21 +96,16 @@ __device__ __forceinline__ TileInfo tile_window(int64_t t, int64_t nrows, const 
     mn = a < mn ? a : mn;
     mx = b > mx ? b : mx;
   }
-  const long long w = mx - mn + 1;
-  if (w <= (long long)win_rows_cap) { ti.cmin = mn; ti.wrows = (int)w; }
-  return ti;
-}
-
-// how many tiles fit a stage (or are empty): the launcher's verdict for a matrix structure
-template <typename I, typename P>
-__global__ void __launch_bounds__(256)
-tile_fit_kernel(int64_t nrows, int64_t ntiles, const P* __restrict__ indptr, const I* __restrict__ indices,
-                int win_rows_cap, unsigned long long* __restrict__ fit_count) {
-  const int lane = threadIdx.x & 31;
-  const int64_t t = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;   // one warp per tile
-  if (t >= ntiles) return;
-  const TileInfo ti = tile_window<I, P>(t, nrows, indptr, indices, win_rows_cap, lane);
-  if (lane == 0 && (ti.wrows > 0 || ti.k1 == ti.k0)) atomicAdd(fit_count, 1ull);
+  if (lane == 0) {
+    TilePlan e;
+    e.cmin = mx >= 0 ? mn : 0;
+    const long long w = mx >= 0 ? mx - mn + 1 : 0;
+    const bool fits = (hi - lo) <= NCAP && w <= (long long)win_rows_cap;
+    e.wrows = fits ? (int)w : 0;
+    e.pad = 0;
+    plan[t] = e;
+    if (fits || hi == lo) atomicAdd(fit_count, 1ull);
+  }
 }
 
 template <typename V> struct Pk;      // 16-byte pack of the value type
@@ -145,7 +144,7 @@ template <typename V, typename I, typename P, int NP>
 __global__ void __launch_bounds__(THREADS, 2)
 spmm_window_tma_kernel(int64_t nrows, int64_t nnz, int64_t ntiles, int k, int lpr_shift, const P* __restrict__ indptr,
                        const I* __restrict__ indices, const V* __restrict__ vals, const V* __restrict__ X, int64_t ldx,
-                       V* __restrict__ Y, int64_t ldy, int win_rows_cap) {
+                       V* __restrict__ Y, int64_t ldy, const TilePlan* __restrict__ plan) {
   using LY = Layout<V, I, P>;
   using PT = typename Pk<V>::T;
   constexpr int N = Pk<V>::N;
@@ -161,17 +160,12 @@ spmm_window_tma_kernel(int64_t nrows, int64_t nnz, int64_t ntiles, int k, int lp
   __syncthreads();
 
   if (warp == 0) {
-    // ===== producer warp: lane 0 issues the copies of tile t, all lanes look up the window of the tile after it =====
-    const int64_t nnz4 = nnz & ~(int64_t)3;
-    const int64_t rp4 = (nrows + 1) & ~(int64_t)3;
-    int it = 0;
-    int64_t t = blockIdx.x;
-    TileInfo cur;
-    if (t < ntiles) cur = tile_window<I, P>(t, nrows, indptr, indices, win_rows_cap, lane);
-    for (; t < ntiles; t += gridDim.x) {
-      TileInfo nxt = cur;
-      if (t + gridDim.x < ntiles) nxt = tile_window<I, P>(t + gridDim.x, nrows, indptr, indices, win_rows_cap, lane);
-      if (lane == 0) {
+    // ===== producer =====
+    if (lane == 0) {
+      const int64_t nnz4 = nnz & ~(int64_t)3;
+      const int64_t rp4 = (nrows + 1) & ~(int64_t)3;
+      int it = 0;
+      for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
         const int s = it % STAGES;
         const uint32_t par = (uint32_t)((it / STAGES) & 1);
         mbar_wait(&empty[s], par ^ 1u);
@@ -181,9 +175,10 @@ spmm_window_tma_kernel(int64_t nrows, int64_t nnz, int64_t ntiles, int k, int lp
         P* srp = reinterpret_cast<P*>(st + LY::IDX_B + LY::VAL_B);
         V* swin = reinterpret_cast<V*>(st + LY::IDX_B + LY::VAL_B + LY::RP_B);
         const int64_t r0 = t * R, r1 = (r0 + R < nrows) ? r0 + R : nrows;
-        const int64_t k0 = cur.k0, k1 = cur.k1;
+        const TilePlan tp = plan[t];
+        const int64_t k0 = (int64_t)indptr[r0], k1 = (int64_t)indptr[r1];
         StageMeta m;
-        m.k0 = k0; m.kb = k0 & ~(int64_t)3; m.cmin = cur.cmin; m.r0 = (int)r0; m.nr = (int)(r1 - r0); m.wrows = cur.wrows;
+        m.k0 = k0; m.kb = k0 & ~(int64_t)3; m.cmin = tp.cmin; m.r0 = (int)r0; m.nr = (int)(r1 - r0); m.wrows = tp.wrows;
         m.last = 0;
         uint32_t bytes = 0;
         // row pointers [rb, rend) (16-byte groups inside the array; the few trailing ones by plain loads)
@@ -195,13 +190,13 @@ spmm_window_tma_kernel(int64_t nrows, int64_t nnz, int64_t ntiles, int k, int lp
         const uint32_t nrp = (uint32_t)(rend - rb);
         bytes += nrp * (uint32_t)sizeof(P);
         uint32_t nb = 0;
-        if (cur.wrows > 0 && k1 > k0) {
+        if (tp.wrows > 0 && k1 > k0) {
           int64_t kend = (k1 + 3) & ~(int64_t)3;
           if (kend > nnz4) kend = nnz4;
           if (kend < m.kb) kend = m.kb;
           for (int64_t q = kend; q < k1; q++) { sidx[q - m.kb] = indices[q]; sval[q - m.kb] = vals[q]; }
           nb = (uint32_t)(kend - m.kb);
-          bytes += nb * (uint32_t)(sizeof(I) + sizeof(V)) + (uint32_t)cur.wrows * (uint32_t)k * (uint32_t)sizeof(V);
+          bytes += nb * (uint32_t)(sizeof(I) + sizeof(V)) + (uint32_t)tp.wrows * (uint32_t)k * (uint32_t)sizeof(V);
         }
         metas[s] = m;
         if (bytes) {
@@ -211,17 +206,13 @@ spmm_window_tma_kernel(int64_t nrows, int64_t nnz, int64_t ntiles, int k, int lp
             bulk_g2s(sidx, indices + m.kb, nb * (uint32_t)sizeof(I), &full[s]);
             bulk_g2s(sval, vals + m.kb, nb * (uint32_t)sizeof(V), &full[s]);
           }
-          if (cur.wrows > 0 && k1 > k0)
-            bulk_g2s(swin, X + cur.cmin * ldx, (uint32_t)cur.wrows * (uint32_t)k * (uint32_t)sizeof(V), &full[s]);
+          if (tp.wrows > 0 && k1 > k0)
+            bulk_g2s(swin, X + tp.cmin * ldx, (uint32_t)tp.wrows * (uint32_t)k * (uint32_t)sizeof(V), &full[s]);
         } else {
           mbar_arrive(&full[s]);
         }
+        it++;
       }
-      __syncwarp();
-      cur = nxt;
-      it++;
-    }
-    if (lane == 0) {
       // sentinel
       const int s = it % STAGES;
       const uint32_t par = (uint32_t)((it / STAGES) & 1);
@@ -336,10 +327,19 @@ int spmm_window_try(int64_t nrows, int64_t nnz, int64_t k, const void* indptr, c
   const int64_t ntiles = (nrows + R - 1) / R;
   DeviceProps pr;
   if (int rc = get_props(&pr)) return rc;
+  TilePlan* plan = nullptr;
+  B2S_CUDA(cudaMallocAsync((void**)&plan, sizeof(TilePlan) * (size_t)ntiles + 16, st));
+  unsigned long long* fit = reinterpret_cast<unsigned long long*>(plan + ntiles);
+  B2S_CUDA(cudaMemsetAsync(fit, 0, 8, st));
+  {
+    const int64_t nthreads = ntiles * 32;
+    tile_window_kernel<I, P><<<(unsigned)((nthreads + 255) / 256), 256, 0, st>>>(nrows, ntiles, (const P*)indptr,
+                                                                                (const I*)indices, win_rows_cap, plan, fit);
+    B2S_LAUNCH_CHECK();
+  }
   if (!force) {
-    // The window kernel pays only when most tiles fit a stage.  The verdict for a structure (one counting pass over
-    // `indices` and one 8-byte read-back, the only synchronisation) is remembered per (arrays, shape), so repeated
-    // products with one matrix launch the product kernel alone and stay asynchronous.
+    // The window kernel pays only when most tiles fit a stage.  The verdict for a structure (one 8-byte read-back, the
+    // only synchronisation) is remembered per (arrays, shape), so repeated products with one matrix stay asynchronous.
     struct Verdict { const void *ip, *ix; int64_t nrows, nnz, k; int sv, ok; };
     static Verdict cache[32];
     static int next = 0;
@@ -351,23 +351,18 @@ int spmm_window_try(int64_t nrows, int64_t nnz, int64_t k, const void* indptr, c
         if (e.ip == indptr && e.ix == indices && e.nrows == nrows && e.nnz == nnz && e.k == k && e.sv == (int)sizeof(V)) verdict = e.ok;
     }
     if (verdict < 0) {
-      unsigned long long* fit = nullptr;
-      B2S_CUDA(cudaMallocAsync((void**)&fit, 8, st));
-      B2S_CUDA(cudaMemsetAsync(fit, 0, 8, st));
-      const int64_t nthreads = ntiles * 32;
-      tile_fit_kernel<I, P><<<(unsigned)((nthreads + 255) / 256), 256, 0, st>>>(nrows, ntiles, (const P*)indptr,
-                                                                               (const I*)indices, win_rows_cap, fit);
-      B2S_LAUNCH_CHECK();
       unsigned long long nfit = 0;
       B2S_CUDA(cudaMemcpyAsync(&nfit, fit, 8, cudaMemcpyDeviceToHost, st));
       B2S_CUDA(cudaStreamSynchronize(st));
-      B2S_CUDA(cudaFreeAsync(fit, st));
       verdict = nfit * 10 >= (unsigned long long)ntiles * 9 ? 1 : 0;
       std::lock_guard<std::mutex> g(mu);
       cache[next] = Verdict{indptr, indices, nrows, nnz, k, (int)sizeof(V), verdict};
       next = (next + 1) % 32;
     }
-    if (!verdict) return B2S_OK;
+    if (!verdict) {
+      B2S_CUDA(cudaFreeAsync(plan, st));
+      return B2S_OK;
+    }
   }
   using LY = Layout<V, I, P>;
   int64_t grid = (int64_t)pr.sm_count * 2;
@@ -375,7 +370,7 @@ int spmm_window_try(int64_t nrows, int64_t nnz, int64_t k, const void* indptr, c
   auto launch = [&](auto kern, auto tag) -> int {
     if (int rc = ensure_dyn_smem<decltype(tag)>(kern, LY::TOTAL)) return rc;
     kern<<<(unsigned)grid, THREADS, LY::TOTAL, st>>>(nrows, nnz, ntiles, (int)k, shift, (const P*)indptr, (const I*)indices,
-                                                     (const V*)vals, (const V*)X, ldx, (V*)Y, ldy, win_rows_cap);
+                                                     (const V*)vals, (const V*)X, ldx, (V*)Y, ldy, plan);
     return B2S_OK;
   };
   struct TagW1 {}; struct TagW2 {}; struct TagW4 {};
@@ -383,8 +378,9 @@ int spmm_window_try(int64_t nrows, int64_t nnz, int64_t k, const void* indptr, c
   if (np == 4) lrc = launch(spmm_window_tma_kernel<V, I, P, 4>, TagW4{});
   else if (np == 2) lrc = launch(spmm_window_tma_kernel<V, I, P, 2>, TagW2{});
   else lrc = launch(spmm_window_tma_kernel<V, I, P, 1>, TagW1{});
-  if (lrc) return lrc;
+  if (lrc) { cudaFreeAsync(plan, st); return lrc; }
   B2S_LAUNCH_CHECK();
+  B2S_CUDA(cudaFreeAsync(plan, st));
   *used = 1;
   return B2S_OK;
 }
