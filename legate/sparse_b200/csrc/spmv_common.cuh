@@ -43,7 +43,9 @@ struct __align__(16) PlanEntry {
   X(10, 1, 4, 2, 3, 8, 0)   \
   X(11, 1, 8, 4, 2, 3, 0)   \
   X(12, 1, 8, 4, 2, 3, 2)   \
-  X(13, 1, 8, 4, 2, 2, 2)
+  X(13, 1, 8, 4, 2, 2, 2)   \
+  X(14, 1, 8, 8, 2, 1, 2)   \
+  X(15, 1, 16, 4, 2, 1, 2)
 struct TileCfgRt { int kind, a, b, c, d, xl; };
 static const TileCfgRt kCfgs[] = {
 #define X(ID, K, A, B, C, D, XL) {K, A, B, C, D, XL},

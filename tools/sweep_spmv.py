@@ -117,5 +117,7 @@ if __name__ == "__main__":
         if "r4" in which:     # scattered AND short rows (what a column block of a weak-scaled R32 shard looks like)
             run("R4 fp32 random 10M x 40M", gallery.random_fixed(10_000_000, 40_000_000, 4, np.float32), cfgs, [0], out)
             run("R4 fp32 random 10M x 10M", gallery.random_fixed(10_000_000, 10_000_000, 4, np.float32), cfgs, [0], out)
+        if "r4f64" in which:
+            run("R4 fp64 random 10M x 5M", gallery.random_fixed(10_000_000, 5_000_000, 4, np.float64), cfgs, [0], out)
         if "r32f64" in which:
             run("R32 fp64 random 10M", gallery.random_fixed(10_000_000, 10_000_000, 32, np.float64), cfgs, [0], out)
