@@ -534,6 +534,20 @@ int b2s_spmv_csr_host(int vt, int it, int pt, int64_t nrows, int64_t ncols, int6
       P.ok = true;
     }
   }
+  // y straight into the caller's host buffer: when y_host is page-locked and mapped (cudaHostAlloc / cudaHostRegister;
+  // torch's pin_memory), the tiles of a stage store their rows over PCIe themselves (coalesced 128-byte posted writes)
+  // instead of a device buffer + a D2H copy per stage.  One dependency chain less per stage (copy -> tiles, done), and the
+  // upstream direction is driven by the SMs while the copy engine keeps the downstream one busy.  B2S_PIPE_DIRECT=0
+  // keeps the copy-engine path; pageable y_host falls back to it by itself.
+  void* y_map = nullptr;
+  {
+    const char* e = getenv("B2S_PIPE_DIRECT");
+    const bool want = !(e && e[0] == '0');
+    if (want && nrows > 0) {
+      if (cudaHostGetDevicePointer(&y_map, y_host, 0) != cudaSuccess) { y_map = nullptr; cudaGetLastError(); }
+    }
+  }
+  const bool direct = y_map != nullptr;
   // B2S_PIPE_TRACE=1: print when each chunk's H2D / tiles / D2H started and ended (debugging the overlap)
   const char* trace_env = getenv("B2S_PIPE_TRACE");
   const bool trace = trace_env != nullptr && trace_env[0] == '1';
@@ -558,6 +572,7 @@ int b2s_spmv_csr_host(int vt, int it, int pt, int64_t nrows, int64_t ncols, int6
   {
     int stages = 0;
     if (const char* e = getenv("B2S_PIPE_CHUNKS")) { const int v = atoi(e); if (v >= 1 && v <= kPlanChunks) stages = v; }
+    if (stages <= 0 && direct) stages = h->nchunks;   // no D2H chain to amortise: the finest stages fill fastest
     if (stages > 0 || h->nchunks != kPlanChunks) {
       if (stages <= 0) stages = h->nchunks;
       const int grp = (h->nchunks + stages - 1) / stages;
@@ -584,11 +599,11 @@ int b2s_spmv_csr_host(int vt, int it, int pt, int64_t nrows, int64_t ncols, int6
       B2S_CUDA(cudaStreamWaitEvent(st, P.ev_in[c], 0));
     }
     if (trace) B2S_CUDA(cudaEventRecord(tr[c][2], st));
-    if (int rc = b2s_spmv_csr_tiles(vt, it, pt, nrows, ncols, nnz, indptr, indices, vals, x_dev, y_dev, plan,
-                                    h->ctile[c], h->ctile[ce], stream)) return rc;
+    if (int rc = b2s_spmv_csr_tiles(vt, it, pt, nrows, ncols, nnz, indptr, indices, vals, x_dev, direct ? y_map : y_dev,
+                                    plan, h->ctile[c], h->ctile[ce], stream)) return rc;
     if (trace) B2S_CUDA(cudaEventRecord(tr[c][3], st));
     const int64_t r0 = h->crow[c], r1 = h->crow[ce];
-    if (r1 > r0) {
+    if (r1 > r0 && !direct) {
       B2S_CUDA(cudaEventRecord(P.ev_k[c], st));
       B2S_CUDA(cudaStreamWaitEvent(P.s_out, P.ev_k[c], 0));
       if (trace) B2S_CUDA(cudaEventRecord(tr[c][4], P.s_out));

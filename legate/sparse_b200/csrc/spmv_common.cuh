@@ -43,9 +43,7 @@ struct __align__(16) PlanEntry {
   X(10, 1, 4, 2, 3, 8, 0)   \
   X(11, 1, 8, 4, 2, 3, 0)   \
   X(12, 1, 8, 4, 2, 3, 2)   \
-  X(13, 1, 8, 4, 2, 2, 2)   \
-  X(14, 1, 8, 8, 2, 1, 2)   \
-  X(15, 1, 16, 4, 2, 1, 2)
+  X(13, 1, 8, 4, 2, 2, 2)
 struct TileCfgRt { int kind, a, b, c, d, xl; };
 static const TileCfgRt kCfgs[] = {
 #define X(ID, K, A, B, C, D, XL) {K, A, B, C, D, XL},
@@ -64,10 +62,14 @@ static constexpr int kShortCfgF64 = kDefaultCfgF64;
 static constexpr int kScatterCfgF64 = 2;   // LDG tiles, 128 threads x 8 nnz, scalar mapping
 static constexpr int kScatterCfgF32 = 8;   // TMA tiles, 4 warps x 8 groups = 32 gathers/thread, x through ld.global.cg
                                            // (R32 fp32 on B200: .cg 1265 us, .nc 1355 us, .nc.L1::no_allocate 2744 us)
-// scattered SHORT rows (one lane per row): the default tile shapes, but x through ld.global.cg -- the L1-allocating
-// path thrashes on random columns (column blocks of an R32 shard, 16 per row: 1194 us with .nc vs 706 us with .cg)
-static constexpr int kScatterShortCfgF32 = 7;
-static constexpr int kScatterShortCfgF64 = 9;
+// scattered SHORT rows (one lane per row): x through ld.global.cg -- the L1-allocating path thrashes on random columns
+// (column blocks of an R32 shard, 16 per row: 1194 us with .nc vs 706 us with .cg) -- and 8 consumer warps on tiles of
+// 4096 (fp32) / 2048 (fp64) entries, 2 CTAs/SM: a tile's rows spread over 256 lanes, i.e. fewer dependent gather rounds
+// per lane.  10M rows x 4 random entries (profiles/r02_sweep_r4.txt): fp32 172 us (cfg 13) vs 275 us (cfg 7: 4 warps x 3
+// groups) vs 224 us without a plan; fp64 187 us (cfg 13) vs 293 us (cfg 9) vs 234 us.  Tiles of 8192 entries (8 warps x 8
+// groups, 16 warps x 4 groups) were measured too: slower (181 / 183 us).
+static constexpr int kScatterShortCfgF32 = 13;
+static constexpr int kScatterShortCfgF64 = 13;
 
 static inline int cfg_cap(int c, int vt) {
   const TileCfgRt& k = kCfgs[c];

@@ -283,14 +283,14 @@ def test_plan_kernel_choice_by_column_locality():
     assert pl.short_rows and pb.short_rows and pl.tma
     assert gallery.banded(100000, 32, np.float32)._get_plan().uniform
     assert pr.scattered and pr.lines_per_warp > 28 and pr.config == 8   # deep-MLP tile shape for scattered fp32, x via ld.global.cg
-    # scattered SHORT rows (a column block of a random shard): default tile shape, one lane per row, x via ld.global.cg
+    # scattered SHORT rows (a column block of a random shard): 8-warp tile shape, one lane per row, x via ld.global.cg
     rng = np.random.default_rng(9)
     ip, ix, dv = _random_csr(rng, 100000, 100000, rng.integers(1, 8, 100000), np.float32)
     R4 = sparse.csr_array((dv, ix, ip), shape=(100000, 100000))._get_plan()
-    assert R4.scattered and R4.short_rows and R4.tma and R4.config == 7
+    assert R4.scattered and R4.short_rows and R4.tma and R4.config == 13
     # ... and uniform short rows (exactly 4 per row = one 16-byte group per lane) take the register path
     U4 = gallery.random_fixed(100000, 100000, 4, np.float32)._get_plan()
-    assert U4.scattered and U4.uniform and U4.tma and U4.config == 7
+    assert U4.scattered and U4.uniform and U4.tma and U4.config == 13
     # both kernel families give the same answer on the same plan
     x = torch.rand(100000, dtype=torch.float32, device="cuda")
     y1 = R @ x
@@ -360,8 +360,19 @@ def test_host_vectors_pipelined_path(kind, pinned, monkeypatch):
     ref = (A @ xh.cuda()).cpu().numpy()
     got = A @ x_np
     assert isinstance(got, np.ndarray) and np.array_equal(got, ref)
-    r = A.dot(x_np, out=y_np)
+    r = A.dot(x_np, out=y_np)     # pinned out: the tiles store y straight into it; pageable: staged + copied back
     assert r is y_np and np.array_equal(y_np, ref)
+    monkeypatch.setenv("B2S_PIPE_DIRECT", "0")          # copy-engine D2H per stage
+    y_np[:] = 0
+    A.dot(x_np, out=y_np)
+    assert np.array_equal(y_np, ref)
+    monkeypatch.delenv("B2S_PIPE_DIRECT")
+    for stages in ("3", "16"):
+        monkeypatch.setenv("B2S_PIPE_CHUNKS", stages)
+        y_np[:] = 0
+        A.dot(x_np, out=y_np)
+        assert np.array_equal(y_np, ref)
+    monkeypatch.delenv("B2S_PIPE_CHUNKS")
     monkeypatch.setenv("B2S_PIPELINE", "0")
     assert np.array_equal(A @ x_np, ref)
     # (n, 1) host vectors
