@@ -534,15 +534,15 @@ int b2s_spmv_csr_host(int vt, int it, int pt, int64_t nrows, int64_t ncols, int6
       P.ok = true;
     }
   }
-  // y straight into the caller's host buffer: when y_host is page-locked and mapped (cudaHostAlloc / cudaHostRegister;
-  // torch's pin_memory), the tiles of a stage store their rows over PCIe themselves (coalesced 128-byte posted writes)
-  // instead of a device buffer + a D2H copy per stage.  One dependency chain less per stage (copy -> tiles, done), and the
-  // upstream direction is driven by the SMs while the copy engine keeps the downstream one busy.  B2S_PIPE_DIRECT=0
-  // keeps the copy-engine path; pageable y_host falls back to it by itself.
+  // B2S_PIPE_DIRECT=1: y straight into the caller's host buffer.  When y_host is page-locked and mapped (cudaHostAlloc /
+  // cudaHostRegister; torch's pin_memory) the tiles of a stage store their rows over PCIe themselves instead of a device
+  // buffer + a D2H copy per stage.  Measured (profiles/r02_e2e_direct.txt): NOT faster -- with the upstream direction busy
+  // either way, a 5 MB H2D copy takes 137 us (36 GB/s) instead of 99 us, and the stores of a stage take as long; 2.32..2.47
+  // ms per product vs 2.23 ms with copy-engine D2H.  Kept as an option (a box with a slower copy engine may differ).
   void* y_map = nullptr;
   {
     const char* e = getenv("B2S_PIPE_DIRECT");
-    const bool want = !(e && e[0] == '0');
+    const bool want = e && e[0] == '1';
     if (want && nrows > 0) {
       if (cudaHostGetDevicePointer(&y_map, y_host, 0) != cudaSuccess) { y_map = nullptr; cudaGetLastError(); }
     }
@@ -572,7 +572,7 @@ int b2s_spmv_csr_host(int vt, int it, int pt, int64_t nrows, int64_t ncols, int6
   {
     int stages = 0;
     if (const char* e = getenv("B2S_PIPE_CHUNKS")) { const int v = atoi(e); if (v >= 1 && v <= kPlanChunks) stages = v; }
-    if (stages <= 0 && direct) stages = h->nchunks;   // no D2H chain to amortise: the finest stages fill fastest
+    if (stages <= 0 && direct) stages = 6;          // measured best for the direct-store option
     if (stages > 0 || h->nchunks != kPlanChunks) {
       if (stages <= 0) stages = h->nchunks;
       const int grp = (h->nchunks + stages - 1) / stages;

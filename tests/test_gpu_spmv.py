@@ -203,7 +203,7 @@ def test_all_tile_configs(oracle, cfg, dtype):
     lens = np.where(np.arange(nrows) % 501 == 0, 9000, rng.integers(0, 12, nrows))
     indptr, indices, data = _random_csr(rng, nrows, ncols, lens, dtype)
     x = rng.standard_normal(ncols).astype(dtype)
-    assert _lib.lib.b2s_spmv_num_configs() == 12
+    assert _lib.lib.b2s_spmv_num_configs() == 14
     try:
         _lib.check(_lib.lib.b2s_spmv_set_config(cfg, cfg % 3))
         A = sparse.csr_array((data, indices, indptr), shape=(nrows, ncols))
@@ -360,9 +360,9 @@ def test_host_vectors_pipelined_path(kind, pinned, monkeypatch):
     ref = (A @ xh.cuda()).cpu().numpy()
     got = A @ x_np
     assert isinstance(got, np.ndarray) and np.array_equal(got, ref)
-    r = A.dot(x_np, out=y_np)     # pinned out: the tiles store y straight into it; pageable: staged + copied back
+    r = A.dot(x_np, out=y_np)
     assert r is y_np and np.array_equal(y_np, ref)
-    monkeypatch.setenv("B2S_PIPE_DIRECT", "0")          # copy-engine D2H per stage
+    monkeypatch.setenv("B2S_PIPE_DIRECT", "1")   # option: tiles store y straight into a pinned out (pageable: falls back)
     y_np[:] = 0
     A.dot(x_np, out=y_np)
     assert np.array_equal(y_np, ref)
