@@ -573,7 +573,22 @@ int b2s_spmv_csr_host(int vt, int it, int pt, int64_t nrows, int64_t ncols, int6
     int stages = 0;
     if (const char* e = getenv("B2S_PIPE_CHUNKS")) { const int v = atoi(e); if (v >= 1 && v <= kPlanChunks) stages = v; }
     if (stages <= 0 && direct) stages = 6;          // measured best for the direct-store option
-    if (stages > 0 || h->nchunks != kPlanChunks) {
+    int pattern[kPlanChunks], npat = 0, psum = 0;   // B2S_PIPE_PATTERN = "1,3,4,4,3,1": chunks per stage (sum 16)
+    if (const char* e = getenv("B2S_PIPE_PATTERN")) {
+      const char* q = e;
+      while (*q && npat < kPlanChunks) {
+        const int v = atoi(q);
+        if (v <= 0) { npat = 0; break; }
+        pattern[npat++] = v; psum += v;
+        while (*q && *q != ',') q++;
+        if (*q == ',') q++;
+      }
+      if (psum != h->nchunks) npat = 0;
+    }
+    if (npat > 0) {
+      int c = 0;
+      for (int i = 0; i < npat; i++) { c += pattern[i]; bounds[++nst] = c; }
+    } else if (stages > 0 || h->nchunks != kPlanChunks) {
       if (stages <= 0) stages = h->nchunks;
       const int grp = (h->nchunks + stages - 1) / stages;
       for (int c = grp; c < h->nchunks; c += grp) bounds[++nst] = c;
@@ -584,11 +599,16 @@ int b2s_spmv_csr_host(int vt, int it, int pt, int64_t nrows, int64_t ncols, int6
       for (int i = 0; i < 6; i++) { c += graded[i]; bounds[++nst] = c; }
     }
   }
-  int64_t copied = 0;
+  // B2S_PIPE_ALIGN = n: copy boundaries on multiples of n elements (x: rounded up, y: rounded down; the rows a stage
+  // finishes past its aligned end travel with the next stage)
+  int64_t align = 0;
+  if (const char* e = getenv("B2S_PIPE_ALIGN")) { align = atoll(e); if (align < 0) align = 0; }
+  int64_t copied = 0, y_done = 0;
   for (int sidx = 0; sidx < nst; sidx++) {
     const int c = bounds[sidx], ce = bounds[sidx + 1];            // chunks [c, ce)
     int64_t need = 0;
     for (int q = c; q < ce; q++) need = h->ccol_hi[q] > need ? h->ccol_hi[q] : need;
+    if (align > 1) { need = (need + align - 1) / align * align; if (need > ncols) need = ncols; }
     if (need > copied) {
       if (trace) B2S_CUDA(cudaEventRecord(tr[c][0], P.s_in));
       B2S_CUDA(cudaMemcpyAsync((char*)x_dev + sv * copied, (const char*)x_host + sv * copied, sv * (size_t)(need - copied),
@@ -602,8 +622,10 @@ int b2s_spmv_csr_host(int vt, int it, int pt, int64_t nrows, int64_t ncols, int6
     if (int rc = b2s_spmv_csr_tiles(vt, it, pt, nrows, ncols, nnz, indptr, indices, vals, x_dev, direct ? y_map : y_dev,
                                     plan, h->ctile[c], h->ctile[ce], stream)) return rc;
     if (trace) B2S_CUDA(cudaEventRecord(tr[c][3], st));
-    const int64_t r0 = h->crow[c], r1 = h->crow[ce];
+    int64_t r0 = y_done, r1 = h->crow[ce];
+    if (align > 1 && sidx + 1 < nst) r1 = r1 / align * align;
     if (r1 > r0 && !direct) {
+      y_done = r1;
       B2S_CUDA(cudaEventRecord(P.ev_k[c], st));
       B2S_CUDA(cudaStreamWaitEvent(P.s_out, P.ev_k[c], 0));
       if (trace) B2S_CUDA(cudaEventRecord(tr[c][4], P.s_out));
