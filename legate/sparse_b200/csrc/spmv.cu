@@ -564,8 +564,10 @@ int b2s_spmv_csr_host(int vt, int it, int pt, int64_t nrows, int64_t ncols, int6
   B2S_CUDA(cudaStreamWaitEvent(P.s_out, P.ev0, 0));
   // pipeline schedule over the plan's 16 chunks.  Small copies run well below the duplex PCIe rate (5 MB stages: ~75
   // GB/s aggregate, 256 MB copies: 99 GB/s) but long first / last stages leave one direction idle while the pipeline
-  // fills and drains, so the default is GRADED: 1, 3, 4, 4, 3, 1 chunks per stage.  B2S_PIPE_CHUNKS = n (1..16) asks
-  // for n equal stages instead.
+  // fills and drains, so the default is GRADED: 1, 2, 2, 2, 2, 2, 2, 2, 1 chunks per stage (short first and last stages:
+  // the pipeline fills and drains in 1/16 of the vector; 10 MB ones in between).  Copies alone, staged the same way,
+  // need 1.86 ms on the bench box (tools/pcie_duplex_chunks.py), this pipeline 2.02 ms.  B2S_PIPE_CHUNKS = n (1..16)
+  // asks for n equal stages instead, B2S_PIPE_PATTERN = "a,b,..." (sum 16) for any other grading.
   int bounds[kPlanChunks + 2];
   int nst = 0;
   bounds[0] = 0;
@@ -594,14 +596,16 @@ int b2s_spmv_csr_host(int vt, int it, int pt, int64_t nrows, int64_t ncols, int6
       for (int c = grp; c < h->nchunks; c += grp) bounds[++nst] = c;
       bounds[++nst] = h->nchunks;
     } else {
-      static const int graded[6] = {1, 3, 4, 4, 3, 1};
+      static const int graded[9] = {1, 2, 2, 2, 2, 2, 2, 2, 1};
       int c = 0;
-      for (int i = 0; i < 6; i++) { c += graded[i]; bounds[++nst] = c; }
+      for (int i = 0; i < 9; i++) { c += graded[i]; bounds[++nst] = c; }
     }
   }
-  // B2S_PIPE_ALIGN = n: copy boundaries on multiples of n elements (x: rounded up, y: rounded down; the rows a stage
-  // finishes past its aligned end travel with the next stage)
-  int64_t align = 0;
+  // Copy boundaries sit on multiples of 4 KB (x: rounded up, y: rounded down; the rows a stage finishes past its aligned
+  // end travel with the next stage): D2H copies that start inside a page run at ~40 GB/s next to a busy H2D direction,
+  // page-aligned ones at ~47 (L5 product 2.20 -> 2.03 ms, profiles/r02_e2e_patterns.txt).  B2S_PIPE_ALIGN = n elements
+  // overrides (0 = exact chunk boundaries).
+  int64_t align = (int64_t)(4096 / sv);
   if (const char* e = getenv("B2S_PIPE_ALIGN")) { align = atoll(e); if (align < 0) align = 0; }
   int64_t copied = 0, y_done = 0;
   for (int sidx = 0; sidx < nst; sidx++) {

@@ -373,6 +373,14 @@ def test_host_vectors_pipelined_path(kind, pinned, monkeypatch):
         A.dot(x_np, out=y_np)
         assert np.array_equal(y_np, ref)
     monkeypatch.delenv("B2S_PIPE_CHUNKS")
+    for pat, align in (("1,3,4,4,3,1", "0"), ("4,4,4,4", "100"), ("16", "512")):
+        monkeypatch.setenv("B2S_PIPE_PATTERN", pat)
+        monkeypatch.setenv("B2S_PIPE_ALIGN", align)
+        y_np[:] = 0
+        A.dot(x_np, out=y_np)
+        assert np.array_equal(y_np, ref)
+    monkeypatch.delenv("B2S_PIPE_PATTERN")
+    monkeypatch.delenv("B2S_PIPE_ALIGN")
     monkeypatch.setenv("B2S_PIPELINE", "0")
     assert np.array_equal(A @ x_np, ref)
     # (n, 1) host vectors
