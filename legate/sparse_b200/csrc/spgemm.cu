@@ -51,7 +51,7 @@ static ScratchLayout scratch_layout(int64_t m, int64_t n, int sm_count) {
   L.bitmap_words0 = (n + 31) / 32;
   L.bitmap_words1 = (L.bitmap_words0 + 31) / 32;
   L.bitmap_slot_bytes = align_up(4 * (L.bitmap_words0 + L.bitmap_words1), 256);
-  L.nslots = 2 * sm_count;
+  L.nslots = 4 * sm_count;   // dense-row CTAs resident at once (28 registers: the accumulators are the limit, not the SM)
   L.off_bitmaps = o;   o += L.bitmap_slot_bytes * L.nslots;
   L.total = o;
   return L;
@@ -446,17 +446,36 @@ spgemm_cta_kernel(int64_t count, const int32_t* __restrict__ perm, const P* __re
         if (NUMERIC) s_av[tid] = a_val[ka];
       }
       const int total = block_exclusive_scan<THREADS>(len, s_excl, s_wsum);
-      for (int p = tid; p < total; p += THREADS) {
-        int lo = 0, hi = THREADS - 1;  // largest t with s_excl[t] <= p
+      // U consecutive products per thread and round: one owner search, the U column (and value) loads in flight
+      // together, then the U table insertions
+      constexpr int U = 4;
+      for (int p0 = tid * U; p0 < total; p0 += THREADS * U) {
+        int lo = 0, hi = THREADS - 1;  // largest t with s_excl[t] <= p0
         while (lo < hi) {
           const int mid = (lo + hi + 1) >> 1;
-          if (s_excl[mid] <= p) lo = mid; else hi = mid - 1;
+          if (s_excl[mid] <= p0) lo = mid; else hi = mid - 1;
         }
-        const long long jb = s_blo[lo] + (p - s_excl[lo]);
-        bool fresh;
-        const int slot = hash_insert<TBL, BITS>(keys, b_idx[jb], &fresh);
-        fresh_cnt += fresh ? 1 : 0;
-        if (NUMERIC) atomicAdd(&vals[slot], s_av[lo] * b_val[jb]);
+        int32_t j[U];
+        V pv[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+          const int p = p0 + u;
+          j[u] = -1;
+          if (p < total) {
+            while (lo + 1 < THREADS && s_excl[lo + 1] <= p) lo++;
+            const long long jb = s_blo[lo] + (p - s_excl[lo]);
+            j[u] = b_idx[jb];
+            if (NUMERIC) pv[u] = s_av[lo] * b_val[jb];
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+          if (j[u] < 0) continue;
+          bool fresh;
+          const int slot = hash_insert<TBL, BITS>(keys, j[u], &fresh);
+          fresh_cnt += fresh ? 1 : 0;
+          if (NUMERIC) atomicAdd(&vals[slot], pv[u]);
+        }
       }
       __syncthreads();
     }
@@ -537,18 +556,39 @@ spgemm_dense_kernel(int64_t count, const int32_t* __restrict__ perm, const P* __
         if (NUMERIC) s_av[tid] = a_val[ka];
       }
       const int total = block_exclusive_scan<THREADS>(len, s_excl, s_wsum);
-      for (int p = tid; p < total; p += THREADS) {
-        int lo = 0, hi = THREADS - 1;
+      // U consecutive products per thread and round: one owner search, then a short walk; the U column loads are all
+      // issued before the first atomic, and no atomic returns a value (RED.OR / RED.ADD: nothing waits for L2).  ncu
+      // of the one-product-per-iteration version with returning atomics (R-MAT 18, profiles/r02_spgemm_dense_*):
+      // issue slots 12 %, 22 cycles of long-scoreboard stall per instruction, 0.13 eligible warps per cycle.
+      constexpr int U = 4;
+      for (int p0 = tid * U; p0 < total; p0 += THREADS * U) {
+        int lo = 0, hi = THREADS - 1;   // largest t with s_excl[t] <= p0
         while (lo < hi) {
           const int mid = (lo + hi + 1) >> 1;
-          if (s_excl[mid] <= p) lo = mid; else hi = mid - 1;
+          if (s_excl[mid] <= p0) lo = mid; else hi = mid - 1;
         }
-        const long long jb = s_blo[lo] + (p - s_excl[lo]);
-        const int32_t j = b_idx[jb];
-        const unsigned int bit = 1u << (j & 31);
-        const unsigned int old = atomicOr(&bm0[j >> 5], bit);
-        if (old == 0) atomicOr(&bm1[j >> 10], 1u << ((j >> 5) & 31));
-        if (NUMERIC) atomicAdd(&acc[j], s_av[lo] * b_val[jb]);
+        int32_t j[U];
+        V pv[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+          const int p = p0 + u;
+          j[u] = -1;
+          if (p < total) {
+            while (lo + 1 < THREADS && s_excl[lo + 1] <= p) lo++;
+            const long long jb = s_blo[lo] + (p - s_excl[lo]);
+            j[u] = b_idx[jb];
+            if (NUMERIC) pv[u] = s_av[lo] * b_val[jb];
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+          if (j[u] < 0) continue;
+          atomicOr(&bm0[j[u] >> 5], 1u << (j[u] & 31));
+          // level 1: test first (an L2 read; a stale answer only repeats the OR), so the steady state adds no atomic
+          const unsigned int bit1 = 1u << ((j[u] >> 5) & 31);
+          if ((__ldcg(&bm1[j[u] >> 10]) & bit1) == 0) atomicOr(&bm1[j[u] >> 10], bit1);
+          if (NUMERIC) atomicAdd(&acc[j[u]], pv[u]);
+        }
       }
       __syncthreads();
     }
@@ -723,9 +763,9 @@ int64_t b2s_spgemm_dense_bytes(int vt, int64_t n, int64_t dense_rows) {
   DeviceProps pr;
   if (get_props(&pr)) return 0;
   const int64_t per = n * (vt == B2S_F32 ? 4 : 8);
-  int64_t slots = 2 * pr.sm_count;
+  int64_t slots = 4 * pr.sm_count;
   if (dense_rows < slots) slots = dense_rows;
-  const int64_t budget = 8LL << 30;  // at most 8 GiB of accumulators
+  const int64_t budget = 24LL << 30;  // at most 24 GiB of accumulators
   if (slots * per > budget) slots = budget / per;
   if (slots < 1) slots = 1;
   return slots * per;
