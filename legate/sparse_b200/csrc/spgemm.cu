@@ -21,18 +21,24 @@ namespace b2s {
 
 // row bins: 0 empty | 1: <=32 (warp, 64-slot table) | 2: <=128 (warp, 256) | 3: <=1024 (CTA, 2048) |
 //           4: <=8192 (CTA, 16384) | 5: larger (global bitmap + dense accumulator)
-constexpr int NCLS = 6;
+// classes 0..4 by size (empty / warp 32 / warp 128 / CTA 1024 / CTA 8192); the dense class is split into DSUB sub-classes
+// ordered HEAVIEST FIRST (class 5: > 2^23 ... class 10: <= 2^15), so that the permutation hands the dense kernel its rows
+// in roughly descending work and the CTAs, which fetch rows from a ticket counter, finish together (R-MAT: the heaviest
+// row of a chunk is 1-2.5 % of the chunk; started last it is a tail of its own)
+constexpr int DSUB = 6;
+constexpr int NCLS = 5 + DSUB;
 constexpr int64_t CLS0_MAX = 32, CLS1_MAX = 128, CLS2_MAX = 1024, CLS3_MAX = 8192;
 constexpr int TBL0 = 64, TBL1 = 256, TBL2 = 2048, TBL3 = 16384;
 constexpr int SCAN_BLOCK = 1024;        // elements per scan block (256 threads x 4)
 
-struct Header {                          // first 256 bytes of scratch (device)
-  unsigned long long counts[8];          // class histogram
-  unsigned long long cursors[8];         // class fill cursors
+struct Header {                          // first 512 bytes of scratch (device)
+  unsigned long long counts[16];         // class histogram
+  unsigned long long cursors[16];        // class fill cursors
   unsigned long long flops;              // number of A*B products
-  unsigned long long pad[15];
+  unsigned long long ticket;             // row ticket of the dense kernel (zeroed before each launch)
+  unsigned long long pad[30];
 };
-static_assert(sizeof(Header) == 256, "header layout");
+static_assert(sizeof(Header) == 512, "header layout");
 
 struct ScratchLayout {
   int64_t off_ub, off_perm, off_blocksums, off_bitmaps, total;
@@ -42,9 +48,15 @@ struct ScratchLayout {
 
 static inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
 
+static inline unsigned long long dense_total(const unsigned long long counts[16]) {
+  unsigned long long t = 0;
+  for (int c = 5; c < NCLS; c++) t += counts[c];
+  return t;
+}
+
 static ScratchLayout scratch_layout(int64_t m, int64_t n, int sm_count) {
   ScratchLayout L;
-  int64_t o = 256;
+  int64_t o = 512;
   L.off_ub = o;        o = align_up(o + 8 * (m > 0 ? m : 1), 256);
   L.off_perm = o;      o = align_up(o + 4 * (m > 0 ? m : 1), 256);
   L.off_blocksums = o; o = align_up(o + 8 * ((m + 1 + SCAN_BLOCK - 1) / SCAN_BLOCK + 1), 256);
@@ -58,7 +70,10 @@ static ScratchLayout scratch_layout(int64_t m, int64_t n, int sm_count) {
 }
 
 __host__ __device__ __forceinline__ int classify(long long v) {
-  return v == 0 ? 0 : (v <= CLS0_MAX ? 1 : (v <= CLS1_MAX ? 2 : (v <= CLS2_MAX ? 3 : (v <= CLS3_MAX ? 4 : 5))));
+  if (v <= CLS3_MAX) return v == 0 ? 0 : (v <= CLS0_MAX ? 1 : (v <= CLS1_MAX ? 2 : (v <= CLS2_MAX ? 3 : 4)));
+  int sub = DSUB - 1;                    // dense: 5 = heaviest ... 5 + DSUB - 1 = lightest
+  for (long long t = 1LL << 15; sub > 0 && v > t; t <<= 2) sub--;
+  return 5 + sub;
 }
 
 __device__ __forceinline__ unsigned hash_col(int32_t c, int bits) {
@@ -528,8 +543,10 @@ spgemm_dense_kernel(int64_t count, const int32_t* __restrict__ perm, const P* __
                     const int32_t* __restrict__ a_idx, const V* __restrict__ a_val, const P* __restrict__ b_ptr,
                     const int32_t* __restrict__ b_idx, const V* __restrict__ b_val, long long* __restrict__ c_ptr,
                     int32_t* __restrict__ c_idx, V* __restrict__ c_val, unsigned char* __restrict__ bitmaps,
-                    int64_t slot_bytes, int64_t words0, int64_t words1, V* __restrict__ dense, int64_t n) {
+                    int64_t slot_bytes, int64_t words0, int64_t words1, V* __restrict__ dense, int64_t n,
+                    unsigned long long* __restrict__ ticket) {
   __shared__ double red[32];
+  __shared__ long long s_it;
   __shared__ int s_scan[THREADS / 32];
   __shared__ long long s_base;
   __shared__ int s_excl[THREADS];
@@ -541,7 +558,13 @@ spgemm_dense_kernel(int64_t count, const int32_t* __restrict__ perm, const P* __
   unsigned int* bm0 = reinterpret_cast<unsigned int*>(bitmaps + slot_bytes * blockIdx.x);
   unsigned int* bm1 = bm0 + words0;
   V* acc = NUMERIC ? dense + n * (int64_t)blockIdx.x : nullptr;
-  for (int64_t it = blockIdx.x; it < count; it += gridDim.x) {
+  while (true) {
+    // rows are handed out in permutation order (heaviest sub-class first) from a ticket counter
+    __syncthreads();
+    if (tid == 0) s_it = (long long)atomicAdd(ticket, 1ull);
+    __syncthreads();
+    const int64_t it = s_it;
+    if (it >= count) break;
     const int32_t row = perm[it];
     const int64_t alo = (int64_t)a_ptr[row], ahi = (int64_t)a_ptr[row + 1];
     // flattened expansion, THREADS A-entries per round (see spgemm_warp_kernel)
@@ -674,7 +697,7 @@ static int run_scan(long long* data, int64_t n, long long* block_sums, cudaStrea
 
 template <bool FROM_INDPTR>
 static int run_binning(int64_t m, const long long* src, Header* hdr, int32_t* perm, bool add_flops,
-                       unsigned long long counts_host[8], unsigned long long* flops_host, ClsOffsets* offs,
+                       unsigned long long counts_host[16], unsigned long long* flops_host, ClsOffsets* offs,
                        cudaStream_t st) {
   B2S_CUDA(cudaMemsetAsync(hdr, 0, sizeof(Header), st));
   const unsigned grid = (unsigned)((m + 255) / 256);
@@ -693,11 +716,11 @@ static int run_binning(int64_t m, const long long* src, Header* hdr, int32_t* pe
 }
 
 template <typename V, typename P, bool NUMERIC>
-static int run_classes(int sm_count, const unsigned long long counts[8], const ClsOffsets& offs, const int32_t* perm,
+static int run_classes(int sm_count, const unsigned long long counts[16], const ClsOffsets& offs, const int32_t* perm,
                        const void* a_ptr, const int32_t* a_idx, const void* a_val, const void* b_ptr,
                        const int32_t* b_idx, const void* b_val, long long* c_ptr, int32_t* c_idx, void* c_val,
                        unsigned char* bitmaps, const ScratchLayout& L, void* dense, int64_t dense_slots, int64_t n,
-                       cudaStream_t st) {
+                       Header* hdr, cudaStream_t st) {
   const P* ap = (const P*)a_ptr; const P* bp = (const P*)b_ptr;
   const V* av = (const V*)a_val; const V* bv = (const V*)b_val; V* cv = (V*)c_val;
   if (counts[1]) {
@@ -732,14 +755,15 @@ static int run_classes(int sm_count, const unsigned long long counts[8], const C
     kern<<<grid, 256, smem, st>>>((int64_t)counts[4], perm + offs.off[4], ap, a_idx, av, bp, b_idx, bv, c_ptr, c_idx, cv);
     B2S_LAUNCH_CHECK();
   }
-  if (counts[5]) {
+  if (const int64_t ndense = (int64_t)dense_total(counts)) {
     int64_t slots = L.nslots;
     if (NUMERIC && dense_slots < slots) slots = dense_slots;
-    if ((int64_t)counts[5] < slots) slots = (int64_t)counts[5];
+    if (ndense < slots) slots = ndense;
     if (slots < 1) { set_error("dense accumulator workspace too small"); return B2S_ENOMEM; }
+    B2S_CUDA(cudaMemsetAsync(&hdr->ticket, 0, sizeof(unsigned long long), st));
     spgemm_dense_kernel<V, P, 256, NUMERIC><<<(unsigned)slots, 256, 0, st>>>(
-        (int64_t)counts[5], perm + offs.off[5], ap, a_idx, av, bp, b_idx, bv, c_ptr, c_idx, cv, bitmaps,
-        L.bitmap_slot_bytes, L.bitmap_words0, L.bitmap_words1, (V*)dense, n);
+        ndense, perm + offs.off[5], ap, a_idx, av, bp, b_idx, bv, c_ptr, c_idx, cv, bitmaps,
+        L.bitmap_slot_bytes, L.bitmap_words0, L.bitmap_words1, (V*)dense, n, &hdr->ticket);
     B2S_LAUNCH_CHECK();
   }
   return B2S_OK;
@@ -816,27 +840,27 @@ int b2s_spgemm_csr_symbolic(int pt, int64_t m, int64_t k, int64_t n, const void*
     else               spgemm_ub_kernel<int64_t><<<grid, 256, 0, st>>>(m, (const int64_t*)a_indptr, a_indices, (const int64_t*)b_indptr, ub);
     B2S_LAUNCH_CHECK();
   }
-  unsigned long long counts[8] = {0};
+  unsigned long long counts[16] = {0};
   unsigned long long flops = 0;
   ClsOffsets offs;
   if (int rc = run_binning<false>(m, ub, hdr, perm, true, counts, &flops, &offs, st)) return rc;
-  if (counts[5]) B2S_CUDA(cudaMemsetAsync(bitmaps, 0, (size_t)(L.bitmap_slot_bytes * L.nslots), st));
+  if (dense_total(counts)) B2S_CUDA(cudaMemsetAsync(bitmaps, 0, (size_t)(L.bitmap_slot_bytes * L.nslots), st));
   int rc;
   long long* cp = (long long*)c_indptr;
-  if (pt == B2S_I32) rc = run_classes<float, int32_t, false>(pr.sm_count, counts, offs, perm, a_indptr, a_indices, nullptr, b_indptr, b_indices, nullptr, cp, nullptr, nullptr, bitmaps, L, nullptr, 0, n, st);
-  else               rc = run_classes<float, int64_t, false>(pr.sm_count, counts, offs, perm, a_indptr, a_indices, nullptr, b_indptr, b_indices, nullptr, cp, nullptr, nullptr, bitmaps, L, nullptr, 0, n, st);
+  if (pt == B2S_I32) rc = run_classes<float, int32_t, false>(pr.sm_count, counts, offs, perm, a_indptr, a_indices, nullptr, b_indptr, b_indices, nullptr, cp, nullptr, nullptr, bitmaps, L, nullptr, 0, n, hdr, st);
+  else               rc = run_classes<float, int64_t, false>(pr.sm_count, counts, offs, perm, a_indptr, a_indices, nullptr, b_indptr, b_indices, nullptr, cp, nullptr, nullptr, bitmaps, L, nullptr, 0, n, hdr, st);
   if (rc) return rc;
   if (int rc2 = run_scan(cp, m + 1, bsums, st)) return rc2;
   long long nnz = 0;
   B2S_CUDA(cudaMemcpyAsync(&nnz, cp + m, sizeof(long long), cudaMemcpyDeviceToHost, st));
   // rows whose exact nnz exceeds the largest shared-memory table need the dense accumulator in pass 2
-  unsigned long long counts2[8] = {0};
+  unsigned long long counts2[16] = {0};
   ClsOffsets offs2;
   if (int rc3 = run_binning<true>(m, cp, hdr, perm, false, counts2, nullptr, &offs2, st)) return rc3;
   B2S_CUDA(cudaStreamSynchronize(st));
   info_host[0] = nnz;
   info_host[1] = (int64_t)flops;
-  info_host[2] = (int64_t)counts2[5];
+  info_host[2] = (int64_t)dense_total(counts2);
   return B2S_OK;
 }
 
@@ -857,11 +881,11 @@ int b2s_spgemm_csr_numeric(int vt, int pt, int64_t m, int64_t k, int64_t n, cons
   Header* hdr = (Header*)sc;
   int32_t* perm = (int32_t*)(sc + L.off_perm);
   unsigned char* bitmaps = sc + L.off_bitmaps;
-  unsigned long long counts[8] = {0};
+  unsigned long long counts[16] = {0};
   ClsOffsets offs;
   if (int rc = run_binning<true>(m, (const long long*)c_indptr, hdr, perm, false, counts, nullptr, &offs, st)) return rc;
   int64_t dense_slots = 0;
-  if (counts[5]) {
+  if (dense_total(counts)) {
     const int64_t per = n * (vt == B2S_F32 ? 4 : 8);
     dense_slots = per > 0 ? dense_ws_bytes / per : 0;
     B2S_CHECK_ARG(dense_ws != nullptr && dense_slots >= 1, "numeric pass needs a dense accumulator workspace of >= %lld bytes", (long long)per);
@@ -870,11 +894,11 @@ int b2s_spgemm_csr_numeric(int vt, int pt, int64_t m, int64_t k, int64_t n, cons
   }
   long long* cp = (long long*)const_cast<int64_t*>(c_indptr);
   if (vt == B2S_F32) {
-    if (pt == B2S_I32) return run_classes<float, int32_t, true>(pr.sm_count, counts, offs, perm, a_indptr, a_indices, a_vals, b_indptr, b_indices, b_vals, cp, c_indices, c_vals, bitmaps, L, dense_ws, dense_slots, n, st);
-    return run_classes<float, int64_t, true>(pr.sm_count, counts, offs, perm, a_indptr, a_indices, a_vals, b_indptr, b_indices, b_vals, cp, c_indices, c_vals, bitmaps, L, dense_ws, dense_slots, n, st);
+    if (pt == B2S_I32) return run_classes<float, int32_t, true>(pr.sm_count, counts, offs, perm, a_indptr, a_indices, a_vals, b_indptr, b_indices, b_vals, cp, c_indices, c_vals, bitmaps, L, dense_ws, dense_slots, n, hdr, st);
+    return run_classes<float, int64_t, true>(pr.sm_count, counts, offs, perm, a_indptr, a_indices, a_vals, b_indptr, b_indices, b_vals, cp, c_indices, c_vals, bitmaps, L, dense_ws, dense_slots, n, hdr, st);
   }
-  if (pt == B2S_I32) return run_classes<double, int32_t, true>(pr.sm_count, counts, offs, perm, a_indptr, a_indices, a_vals, b_indptr, b_indices, b_vals, cp, c_indices, c_vals, bitmaps, L, dense_ws, dense_slots, n, st);
-  return run_classes<double, int64_t, true>(pr.sm_count, counts, offs, perm, a_indptr, a_indices, a_vals, b_indptr, b_indices, b_vals, cp, c_indices, c_vals, bitmaps, L, dense_ws, dense_slots, n, st);
+  if (pt == B2S_I32) return run_classes<double, int32_t, true>(pr.sm_count, counts, offs, perm, a_indptr, a_indices, a_vals, b_indptr, b_indices, b_vals, cp, c_indices, c_vals, bitmaps, L, dense_ws, dense_slots, n, hdr, st);
+  return run_classes<double, int64_t, true>(pr.sm_count, counts, offs, perm, a_indptr, a_indices, a_vals, b_indptr, b_indices, b_vals, cp, c_indices, c_vals, bitmaps, L, dense_ws, dense_slots, n, hdr, st);
 }
 
 }  // extern "C"
