@@ -538,13 +538,13 @@ spgemm_cta_kernel(int64_t count, const int32_t* __restrict__ perm, const P* __re
 // profiles/README.md) and lost: rounds of rows with G CTAs per row (79 s vs 44 s: a round lasts as long as its
 // heaviest row / G while the other slots idle) and a separate many-CTA class for hub rows only (103 s).
 template <typename V, typename P, int THREADS, bool NUMERIC>
-__global__ void __launch_bounds__(THREADS)
+__global__ void __launch_bounds__(THREADS, 4)
 spgemm_dense_kernel(int64_t count, const int32_t* __restrict__ perm, const P* __restrict__ a_ptr,
                     const int32_t* __restrict__ a_idx, const V* __restrict__ a_val, const P* __restrict__ b_ptr,
                     const int32_t* __restrict__ b_idx, const V* __restrict__ b_val, long long* __restrict__ c_ptr,
                     int32_t* __restrict__ c_idx, V* __restrict__ c_val, unsigned char* __restrict__ bitmaps,
                     int64_t slot_bytes, int64_t words0, int64_t words1, V* __restrict__ dense, int64_t n,
-                    unsigned long long* __restrict__ ticket) {
+                    unsigned long long* __restrict__ ticket, int l1_shared) {
   __shared__ double red[32];
   __shared__ long long s_it;
   __shared__ int s_scan[THREADS / 32];
@@ -556,7 +556,13 @@ spgemm_dense_kernel(int64_t count, const int32_t* __restrict__ perm, const P* __
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   constexpr int NWARPS = THREADS / 32;
   unsigned int* bm0 = reinterpret_cast<unsigned int*>(bitmaps + slot_bytes * blockIdx.x);
-  unsigned int* bm1 = bm0 + words0;
+  // level 1 (one bit per level-0 word) lives in shared memory when it fits (n <= 8 M columns): the expansion then
+  // touches global memory only with loads of B and non-returning atomics
+  extern __shared__ unsigned int s_l1[];
+  unsigned int* bm1 = l1_shared ? s_l1 : bm0 + words0;
+  if (l1_shared) {
+    for (int64_t i = tid; i < words1; i += THREADS) s_l1[i] = 0;
+  }
   V* acc = NUMERIC ? dense + n * (int64_t)blockIdx.x : nullptr;
   while (true) {
     // rows are handed out in permutation order (heaviest sub-class first) from a ticket counter
@@ -567,23 +573,36 @@ spgemm_dense_kernel(int64_t count, const int32_t* __restrict__ perm, const P* __
     if (it >= count) break;
     const int32_t row = perm[it];
     const int64_t alo = (int64_t)a_ptr[row], ahi = (int64_t)a_ptr[row + 1];
-    // flattened expansion, THREADS A-entries per round (see spgemm_warp_kernel)
+    // flattened expansion, THREADS A-entries per round (see spgemm_warp_kernel).  The (B row start, length, A value) of
+    // the NEXT round's entry are fetched before the products of this round, so that chain of three dependent loads
+    // (a_idx -> b_ptr) overlaps them.
+    long long n_blo = 0;
+    int n_len = 0;
+    V n_av = (V)0;
+    if (alo + tid < ahi) {
+      const int32_t kk = a_idx[alo + tid];
+      n_blo = (long long)b_ptr[kk];
+      n_len = (int)((long long)b_ptr[kk + 1] - n_blo);
+      if (NUMERIC) n_av = a_val[alo + tid];
+    }
     for (int64_t base = alo; base < ahi; base += THREADS) {
-      const int64_t ka = base + tid;
-      int len = 0;
-      if (ka < ahi) {
-        const int32_t kk = a_idx[ka];
-        const long long blo = (long long)b_ptr[kk];
-        len = (int)((long long)b_ptr[kk + 1] - blo);
-        s_blo[tid] = blo;
-        if (NUMERIC) s_av[tid] = a_val[ka];
-      }
+      const int len = n_len;
+      s_blo[tid] = n_blo;
+      if (NUMERIC) s_av[tid] = n_av;
       const int total = block_exclusive_scan<THREADS>(len, s_excl, s_wsum);
-      // U consecutive products per thread and round: one owner search, then a short walk; the U column loads are all
-      // issued before the first atomic, and no atomic returns a value (RED.OR / RED.ADD: nothing waits for L2).  ncu
-      // of the one-product-per-iteration version with returning atomics (R-MAT 18, profiles/r02_spgemm_dense_*):
-      // issue slots 12 %, 22 cycles of long-scoreboard stall per instruction, 0.13 eligible warps per cycle.
-      constexpr int U = 4;
+      n_len = 0;
+      if (base + THREADS + tid < ahi) {
+        const int32_t kk = a_idx[base + THREADS + tid];
+        n_blo = (long long)b_ptr[kk];
+        n_len = (int)((long long)b_ptr[kk + 1] - n_blo);
+        if (NUMERIC) n_av = a_val[base + THREADS + tid];
+      }
+      // U consecutive products per thread and round: one owner search, then a short walk; the U column (and value) loads
+      // are all issued before anything else touches memory, and no atomic returns a value (RED.OR / RED.ADD: nothing
+      // waits for L2).  ncu of the first version -- one product per iteration, atomics with return values, level 1 in
+      // global memory (R-MAT 18, profiles/r02_spgemm_dense_*): issue slots 12 %, 22..85 cycles of long-scoreboard stall
+      // per instruction, 0.07..0.13 eligible warps per cycle: pure latency.
+      constexpr int U = 8;
       for (int p0 = tid * U; p0 < total; p0 += THREADS * U) {
         int lo = 0, hi = THREADS - 1;   // largest t with s_excl[t] <= p0
         while (lo < hi) {
@@ -603,13 +622,25 @@ spgemm_dense_kernel(int64_t count, const int32_t* __restrict__ perm, const P* __
             if (NUMERIC) pv[u] = s_av[lo] * b_val[jb];
           }
         }
+        if (!l1_shared) {
+          // level 1 in global memory: test first (L2 reads, all issued together; a stale answer only repeats the OR)
+          unsigned int cur[U];
+#pragma unroll
+          for (int u = 0; u < U; u++) cur[u] = j[u] >= 0 ? __ldcg(&bm1[j[u] >> 10]) : 0xffffffffu;
+#pragma unroll
+          for (int u = 0; u < U; u++) {
+            const unsigned int bit1 = 1u << ((j[u] >> 5) & 31);
+            if (j[u] >= 0 && (cur[u] & bit1) == 0) atomicOr(&bm1[j[u] >> 10], bit1);
+          }
+        }
 #pragma unroll
         for (int u = 0; u < U; u++) {
           if (j[u] < 0) continue;
           atomicOr(&bm0[j[u] >> 5], 1u << (j[u] & 31));
-          // level 1: test first (an L2 read; a stale answer only repeats the OR), so the steady state adds no atomic
-          const unsigned int bit1 = 1u << ((j[u] >> 5) & 31);
-          if ((__ldcg(&bm1[j[u] >> 10]) & bit1) == 0) atomicOr(&bm1[j[u] >> 10], bit1);
+          if (l1_shared) {
+            const unsigned int bit1 = 1u << ((j[u] >> 5) & 31);
+            if ((s_l1[j[u] >> 10] & bit1) == 0) atomicOr(&s_l1[j[u] >> 10], bit1);
+          }
           if (NUMERIC) atomicAdd(&acc[j[u]], pv[u]);
         }
       }
@@ -761,9 +792,11 @@ static int run_classes(int sm_count, const unsigned long long counts[16], const 
     if (ndense < slots) slots = ndense;
     if (slots < 1) { set_error("dense accumulator workspace too small"); return B2S_ENOMEM; }
     B2S_CUDA(cudaMemsetAsync(&hdr->ticket, 0, sizeof(unsigned long long), st));
-    spgemm_dense_kernel<V, P, 256, NUMERIC><<<(unsigned)slots, 256, 0, st>>>(
+    const int l1_shared = L.bitmap_words1 <= 8192 ? 1 : 0;      // 32 KB of shared memory: n <= 8 M columns
+    const size_t l1_bytes = l1_shared ? sizeof(unsigned int) * (size_t)L.bitmap_words1 : 0;
+    spgemm_dense_kernel<V, P, 256, NUMERIC><<<(unsigned)slots, 256, l1_bytes, st>>>(
         ndense, perm + offs.off[5], ap, a_idx, av, bp, b_idx, bv, c_ptr, c_idx, cv, bitmaps,
-        L.bitmap_slot_bytes, L.bitmap_words0, L.bitmap_words1, (V*)dense, n, &hdr->ticket);
+        L.bitmap_slot_bytes, L.bitmap_words0, L.bitmap_words1, (V*)dense, n, &hdr->ticket, l1_shared);
     B2S_LAUNCH_CHECK();
   }
   return B2S_OK;
