@@ -648,37 +648,25 @@ spgemm_dense_kernel(int64_t count, const int32_t* __restrict__ perm, const P* __
     }
     __threadfence_block();
     __syncthreads();
-    if (!NUMERIC) {
-      // count set bits, clearing as we go (only level-0 words flagged in level 1 are visited)
-      long long cnt = 0;
-      for (int64_t w1 = tid; w1 < words1; w1 += THREADS) {
-        unsigned int m1 = bm1[w1];
-        if (!m1) continue;
-        bm1[w1] = 0;
-        while (m1) {
-          const int b = __ffs(m1) - 1;
-          m1 &= m1 - 1;
-          const int64_t w0 = w1 * 32 + b;
-          cnt += __popc(bm0[w0]);
-          bm0[w0] = 0;
-        }
-      }
-      double tot = block_sum<THREADS>((double)cnt, red);
-      if (tid == 0) c_ptr[row] = (long long)(tot + 0.5);
-      __syncthreads();
-    } else {
-      // ordered emission: walk level-1 words in chunks of THREADS, block-scan the popcounts
-      if (tid == 0) s_base = c_ptr[row];
-      __syncthreads();
-      for (int64_t c0 = 0; c0 < words1; c0 += THREADS) {
-        const int64_t w1 = c0 + tid;
-        unsigned int m1 = (w1 < words1) ? bm1[w1] : 0u;
-        int mine = 0;
-        {
-          unsigned int t1 = m1;
-          while (t1) { const int b = __ffs(t1) - 1; t1 &= t1 - 1; mine += __popc(bm0[w1 * 32 + b]); }
-        }
-        // block exclusive scan of `mine`
+    // Emission / counting: one thread per LEVEL-0 word (32 columns), THREADS / 32 level-1 words per step; steps whose
+    // level-1 words are all empty cost one barrier.  (One thread per level-1 word = 1024 columns, as it was first
+    // written, left a thread with up to 1024 dependent trips to the accumulator while its 255 neighbours idled: R-MAT
+    // columns are as skewed as the rows.)
+    long long cnt = 0;
+    if (NUMERIC && tid == 0) s_base = c_ptr[row];
+    for (int64_t g = 0; g < words1; g += NWARPS) {
+      const int64_t w1 = g + wid;
+      const unsigned int m1 = (w1 < words1) ? bm1[w1] : 0u;           // the lanes of a warp read one level-1 word
+      if (!__syncthreads_or(m1 != 0)) continue;                       // block-uniform
+      const int64_t w0 = w1 * 32 + lane;
+      unsigned int m0 = ((m1 >> lane) & 1u) ? bm0[w0] : 0u;
+      if (m0) bm0[w0] = 0;
+      __syncwarp();
+      if (lane == 0 && m1) bm1[w1] = 0;
+      if (!NUMERIC) {
+        cnt += __popc(m0);
+      } else {
+        const int mine = __popc(m0);
         int inc = mine;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
@@ -687,29 +675,31 @@ spgemm_dense_kernel(int64_t count, const int32_t* __restrict__ perm, const P* __
         int woff = 0, total = 0;
         for (int w = 0; w < NWARPS; w++) { if (w < wid) woff += s_scan[w]; total += s_scan[w]; }
         long long pos = s_base + woff + inc - mine;
-        if (m1) {
-          bm1[w1] = 0;
-          while (m1) {
-            const int b = __ffs(m1) - 1;
-            m1 &= m1 - 1;
-            const int64_t w0 = w1 * 32 + b;
-            unsigned int m0 = bm0[w0];
-            bm0[w0] = 0;
-            while (m0) {
-              const int bb = __ffs(m0) - 1;
-              m0 &= m0 - 1;
-              const int64_t j = w0 * 32 + bb;
-              c_idx[pos] = (int32_t)j;
-              c_val[pos] = acc[j];
-              acc[j] = (V)0;
-              pos++;
-            }
+        // up to 32 entries per thread, four accumulator loads in flight at a time
+        while (m0) {
+          int jj[4];
+          V vv[4];
+          int k = 0;
+#pragma unroll
+          for (int q = 0; q < 4; q++) {
+            jj[q] = -1;
+            if (m0) { const int bb = __ffs(m0) - 1; m0 &= m0 - 1; jj[q] = (int)(w0 * 32 + bb); k++; }
           }
+#pragma unroll
+          for (int q = 0; q < 4; q++) vv[q] = jj[q] >= 0 ? acc[jj[q]] : (V)0;
+#pragma unroll
+          for (int q = 0; q < 4; q++) {
+            if (jj[q] >= 0) { c_idx[pos + q] = (int32_t)jj[q]; c_val[pos + q] = vv[q]; acc[jj[q]] = (V)0; }
+          }
+          pos += k;
         }
         __syncthreads();
         if (tid == 0) s_base += total;
-        __syncthreads();
       }
+    }
+    if (!NUMERIC) {
+      double tot = block_sum<THREADS>((double)cnt, red);
+      if (tid == 0) c_ptr[row] = (long long)(tot + 0.5);
     }
   }
 }
