@@ -69,8 +69,10 @@ static ScratchLayout scratch_layout(int64_t m, int64_t n, int sm_count) {
   return L;
 }
 
-__host__ __device__ __forceinline__ int classify(long long v) {
-  if (v <= CLS3_MAX) return v == 0 ? 0 : (v <= CLS0_MAX ? 1 : (v <= CLS1_MAX ? 2 : (v <= CLS2_MAX ? 3 : 4)));
+// cls3: largest row that still takes the 16384-entry shared-memory table (class 4); longer rows are dense.  The symbolic
+// pass classifies by the product count (table = candidate set), the numeric pass by the exact nnz, with its own limit.
+__host__ __device__ __forceinline__ int classify(long long v, long long cls3) {
+  if (v <= cls3 || v <= CLS2_MAX) return v == 0 ? 0 : (v <= CLS0_MAX ? 1 : (v <= CLS1_MAX ? 2 : (v <= CLS2_MAX ? 3 : 4)));
   int sub = DSUB - 1;                    // dense: 5 = heaviest ... 5 + DSUB - 1 = lightest
   for (long long t = 1LL << 15; sub > 0 && v > t; t <<= 2) sub--;
   return 5 + sub;
@@ -117,7 +119,7 @@ spgemm_ub_kernel(int64_t m, const P* __restrict__ a_ptr, const int32_t* __restri
 // `size_of(i)` is ub[i] (symbolic) or c_indptr[i+1]-c_indptr[i] (numeric).
 template <bool FROM_INDPTR>
 __global__ void __launch_bounds__(256)
-bin_count_kernel(int64_t m, const long long* __restrict__ src, Header* hdr, int add_flops) {
+bin_count_kernel(int64_t m, const long long* __restrict__ src, Header* hdr, int add_flops, long long cls3) {
   __shared__ unsigned long long s_cnt[NCLS];
   __shared__ unsigned long long s_flops;
   if (threadIdx.x < NCLS) s_cnt[threadIdx.x] = 0;
@@ -129,7 +131,7 @@ bin_count_kernel(int64_t m, const long long* __restrict__ src, Header* hdr, int 
   int c = -1;
   if (i < m) {
     v = FROM_INDPTR ? (src[i + 1] - src[i]) : src[i];
-    c = classify(v);
+    c = classify(v, cls3);
   }
   // warp-aggregated: one shared-memory atomic per (warp, class) instead of one per row
 #pragma unroll
@@ -153,7 +155,7 @@ struct ClsOffsets { long long off[NCLS + 1]; };
 template <bool FROM_INDPTR>
 __global__ void __launch_bounds__(256)
 bin_scatter_kernel(int64_t m, const long long* __restrict__ src, Header* hdr, ClsOffsets offs,
-                   int32_t* __restrict__ perm) {
+                   int32_t* __restrict__ perm, long long cls3) {
   __shared__ unsigned int s_cnt[NCLS];
   __shared__ unsigned long long s_base[NCLS];
   if (threadIdx.x < NCLS) s_cnt[threadIdx.x] = 0;
@@ -163,7 +165,7 @@ bin_scatter_kernel(int64_t m, const long long* __restrict__ src, Header* hdr, Cl
   unsigned int local = 0;
   if (i < m) {
     const long long v = FROM_INDPTR ? (src[i + 1] - src[i]) : src[i];
-    c = classify(v);
+    c = classify(v, cls3);
     local = atomicAdd(&s_cnt[c], 1u);
   }
   __syncthreads();
@@ -716,13 +718,26 @@ static int run_scan(long long* data, int64_t n, long long* block_sums, cudaStrea
   return B2S_OK;
 }
 
+// Numeric pass: rows with more than this many entries go to the dense kernel rather than the 16384-entry table kernel
+// (one CTA per SM, compaction + bitonic sort of the row).  B2S_SPGEMM_DENSE_MIN overrides (1024 .. 8192).
+static long long numeric_cls3() {
+  static long long v = -1;
+  if (v < 0) {
+    long long t = CLS3_MAX;
+    if (const char* e = getenv("B2S_SPGEMM_DENSE_MIN")) { const long long q = atoll(e); if (q >= CLS2_MAX && q <= CLS3_MAX) t = q; }
+    v = t;
+  }
+  return v;
+}
+
 template <bool FROM_INDPTR>
 static int run_binning(int64_t m, const long long* src, Header* hdr, int32_t* perm, bool add_flops,
                        unsigned long long counts_host[16], unsigned long long* flops_host, ClsOffsets* offs,
                        cudaStream_t st) {
   B2S_CUDA(cudaMemsetAsync(hdr, 0, sizeof(Header), st));
   const unsigned grid = (unsigned)((m + 255) / 256);
-  bin_count_kernel<FROM_INDPTR><<<grid, 256, 0, st>>>(m, src, hdr, add_flops ? 1 : 0);
+  const long long cls3 = FROM_INDPTR ? numeric_cls3() : CLS3_MAX;
+  bin_count_kernel<FROM_INDPTR><<<grid, 256, 0, st>>>(m, src, hdr, add_flops ? 1 : 0, cls3);
   B2S_LAUNCH_CHECK();
   Header h;
   B2S_CUDA(cudaMemcpyAsync(&h, hdr, sizeof(Header), cudaMemcpyDeviceToHost, st));
@@ -731,7 +746,7 @@ static int run_binning(int64_t m, const long long* src, Header* hdr, int32_t* pe
   for (int c = 0; c < NCLS; c++) { offs->off[c] = o; o += (long long)h.counts[c]; counts_host[c] = h.counts[c]; }
   offs->off[NCLS] = o;
   if (flops_host) *flops_host = h.flops;
-  bin_scatter_kernel<FROM_INDPTR><<<grid, 256, 0, st>>>(m, src, hdr, *offs, perm);
+  bin_scatter_kernel<FROM_INDPTR><<<grid, 256, 0, st>>>(m, src, hdr, *offs, perm, cls3);
   B2S_LAUNCH_CHECK();
   return B2S_OK;
 }
