@@ -719,11 +719,14 @@ static int run_scan(long long* data, int64_t n, long long* block_sums, cudaStrea
 }
 
 // Numeric pass: rows with more than this many entries go to the dense kernel rather than the 16384-entry table kernel
-// (one CTA per SM, compaction + bitonic sort of the row).  B2S_SPGEMM_DENSE_MIN overrides (1024 .. 8192).
+// (192 KB of shared memory = one CTA per SM, then compaction + bitonic sort of the row: ncu on R-MAT 18 showed it taking
+// as long as the dense kernel for a fraction of the products).  Limit 8192 / 4096 / 2048 / 1024: R-MAT 16 41.5 / 24.0 /
+// 16.3 / 13.1 ms, R-MAT 18 206 / 156 / 134 / 129 ms, R-MAT 20 1390 / 1234 / 1190 / 1180 ms -- so every row beyond the
+// 2048-entry table is dense.  B2S_SPGEMM_DENSE_MIN overrides (1024 .. 8192).
 static long long numeric_cls3() {
   static long long v = -1;
   if (v < 0) {
-    long long t = CLS3_MAX;
+    long long t = CLS2_MAX;
     if (const char* e = getenv("B2S_SPGEMM_DENSE_MIN")) { const long long q = atoll(e); if (q >= CLS2_MAX && q <= CLS3_MAX) t = q; }
     v = t;
   }

@@ -140,7 +140,7 @@ def test_rmat_all_bins(oracle, scale, ef):
     lens = np.diff(S.indptr)
     info = C.spgemm_info
     assert info["nnz"] == S.nnz
-    assert info["dense_rows"] == int((lens > 8192).sum())
+    assert info["dense_rows"] == int((lens > 1024).sum())   # numeric pass: beyond the 2048-entry table -> dense kernel
     op, oi, ov = oracle.spgemm((A.indptr, A.indices, A.data), (A.indptr, A.indices, A.data), A.shape, A.shape,
                                sort_rows=True)
     cp, ci, cv = _triple(C)
