@@ -478,6 +478,17 @@ def _r32_case(torch, gallery, _ops, peak, dtype, reps=20):
            "frac_of_gather_ceiling": g_med / med, "matrix_stream_ms_at_hbm_peak": stream_ms,
            "lines_per_warp": plan.lines_per_warp, "kernel": plan.kernel_name,
            "limiter": "L1TEX tag stage: one distinct 128-byte line per cycle per SM (see profiles/ and DESIGN.md 3.2)"}
+    # the public call (csr_array.dot) column-splits by itself when x exceeds L2 and the columns are scattered (fp64: x =
+    # 80 MB -> two column blocks, each gathering from a 40 MB slice); `ms` above stays the unsplit kernel
+    if A._wants_col_split(plan):
+        A.dot(x, out=y)
+        y_ref = torch.empty_like(y)
+        _ops.spmv(A.indptr, A.indices, A.data, x, y_ref, A.shape, plan=plan)
+        err = float((y - y_ref).abs().max() / y_ref.abs().max())
+        cs_med, cs_min = _time_launches(torch, lambda: A.dot(x, out=y), reps)
+        out["col_split"] = {"blocks": len(A._col_split()), "ms": cs_med, "min_ms": cs_min,
+                            "gflops": 2.0 * A.nnz / (cs_med * 1e-3) / 1e9, "frac_of_gather_ceiling": g_med / cs_med,
+                            "max_rel_diff_vs_unsplit": err, "kernel": A._col_split()[0][1].kernel_name}
     del A, x, y
     torch.cuda.empty_cache()
     return out

@@ -282,6 +282,69 @@ class csr_array:
             self._plan_key = key
         return self._plan
 
+    # -- column-split SpMV (reference csr.py:869-927 / spmv.cu:125-153: x partitioned, y reduced) -------------------
+    _COL_BLOCK_BYTES = 40 << 20      # one block's slice of x: what stays L2-resident next to the matrix stream
+
+    def _col_split(self, nblocks=None):
+        """[(column block, plan)]: block q holds the entries whose column lies in [q*T, (q+1)*T), global column ids
+        kept, so `y = sum_q A_q x` with every block gathering from ONE slice of x.  Built once per structure / values
+        and cached.  The reference's column-split SpMV partitions x the same way and reduces the partial y with ADD."""
+        n = self.shape[1]
+        if nblocks is None:
+            nblocks = max(2, min(16, -(-n * self.dtype.itemsize // self._COL_BLOCK_BYTES)))
+        nblocks = max(1, min(int(nblocks), max(n, 1)))
+        key = (self._indptr.data_ptr(), self._indices.data_ptr(), self._data.data_ptr(), self._data._version, self.nnz,
+               nblocks)
+        hit = self.__dict__.get("_colsplit")
+        if hit is not None and hit[0] == key:
+            return hit[1]
+        T = -(-n // nblocks)
+        idx = self._indices
+        nrows = self.shape[0]
+        counts = (self._indptr[1:] - self._indptr[:-1]).to(torch.int64)
+        rows = torch.repeat_interleave(torch.arange(nrows, device=idx.device, dtype=torch.int64), counts)
+        blocks = []
+        for q in range(nblocks):
+            mask = (idx >= q * T) & (idx < min((q + 1) * T, n))
+            nnz_q = int(mask.sum())
+            if nnz_q == 0:
+                continue
+            cnt = torch.bincount(rows[mask], minlength=nrows)
+            ip = torch.zeros(nrows + 1, dtype=torch.int64, device=idx.device)
+            torch.cumsum(cnt, 0, out=ip[1:])
+            B = csr_array._from_parts(ip.to(self._indptr.dtype), idx[mask].contiguous(), self._data[mask].contiguous(),
+                                      self.shape)
+            blocks.append((B, B._get_plan(tma_only=True)))
+        self.__dict__["_colsplit"] = (key, blocks)
+        return blocks
+
+    def _dot_col_split(self, xd, y, nblocks=None):
+        """y = A @ xd as a sum over column blocks: the first block writes y, the others accumulate (b2s_spmv_csr_add)."""
+        blocks = self._col_split(nblocks)
+        if not blocks:
+            y.zero_()
+            return y
+        first = True
+        for B, pl in blocks:
+            if first:
+                _ops.spmv(B._indptr, B._indices, B._data, xd, y, B.shape, plan=pl)
+                first = False
+            else:
+                _ops.spmv_add(B._indptr, B._indices, B._data, xd, y, B.shape, pl)
+        return y
+
+    def _wants_col_split(self, plan) -> bool:
+        """Scattered columns and an x larger than L2 can hold next to the matrix stream: gathers from one slice of x at a
+        time hit L2, the unsplit product misses it (R32 fp64, x = 80 MB: 1.98 ms unsplit; weak-scaled fp32 shard, x =
+        320 MB: 5.5 ms unsplit vs 1.65 ms in 8 blocks).  Only when the blocks keep a few entries per row."""
+        if os.environ.get("B2S_COL_SPLIT", "auto") == "0":
+            return False
+        xbytes = self.shape[1] * self.dtype.itemsize
+        if not getattr(plan, "scattered", False) or xbytes <= (48 << 20):
+            return False
+        nblocks = -(-xbytes // self._COL_BLOCK_BYTES)
+        return self.nnz >= 4 * nblocks * max(self.shape[0], 1)
+
     def _promoted(self, common):
         """A cast to the resolved dtype of (A, x) -- reference cast_to_common_type, csr.py:493 -- cached
         so a mixed-dtype SpMV does not re-cast the matrix on every call."""
@@ -402,8 +465,9 @@ class csr_array:
         * x 1-D or (n,1), numpy or torch CUDA tensor -> SpMV; result has x's array kind.
         * other dense 2-D (n,k) -> SpMM, dense (m,k) result of the same array kind.
         * other a csr_array -> SpGEMM (CSR x CSR -> CSR).
-        `spmv_domain_part` (column-split SpMV, csr.py:869-927) is accepted for signature
-        compatibility; a single GPU has no column split and the row-split kernel is used.
+        `spmv_domain_part=True` (column-split SpMV, csr.py:869-927, spmv.cu:125-153): x is partitioned into column
+        blocks, every block's partial product is reduced into y by the accumulating kernel (`_dot_col_split`); the
+        same path is taken by itself when the columns are scattered and x exceeds L2 (`_wants_col_split`).
         """
         from .module import is_sparse_matrix
 
@@ -455,7 +519,7 @@ class csr_array:
             plan = A._get_plan()
             if (not on_device and isinstance(x, np.ndarray) and xdt == common and x.flags.c_contiguous
                     and (out is None or (isinstance(out, np.ndarray) and out.flags.c_contiguous))
-                    and plan.chunks and os.environ.get("B2S_PIPELINE", "1") != "0"):
+                    and plan.chunks and not spmv_domain_part and os.environ.get("B2S_PIPELINE", "1") != "0"):
                 # host vectors: stream x in / y out chunk by chunk, overlapping both PCIe directions with the kernel
                 res = A._dot_host_pipelined(x, None if out is None else out.reshape(-1), plan)
                 result = out if out is not None else (res.reshape(-1, 1) if other_originally_2d else res)
@@ -465,7 +529,10 @@ class csr_array:
             xd = to_device(x, dtype=common)
             direct = isinstance(out, torch.Tensor) and out.is_cuda and out.is_contiguous()
             y = out.reshape(-1) if direct else torch.empty(self.shape[0], dtype=torch_dtype(common), device=A.device)
-            _ops.spmv(A._indptr, A._indices, A._data, xd, y, A.shape, plan=plan)
+            if spmv_domain_part or A._wants_col_split(plan):
+                A._dot_col_split(xd, y)      # x partitioned by columns, partial products reduced into y
+            else:
+                _ops.spmv(A._indptr, A._indices, A._data, xd, y, A.shape, plan=plan)
             if out is None:
                 result = y if on_device else to_host(y)
                 if other_originally_2d:

@@ -56,6 +56,10 @@ def install():
         y[:] = torch.from_numpy(orc.spmv(indptr.numpy(), indices.numpy(), data.numpy(), x.numpy()))
         return y
 
+    def spmv_add(indptr, indices, data, x, y, shape, plan):
+        y += torch.from_numpy(orc.spmv(indptr.numpy(), indices.numpy(), data.numpy(), x.numpy()))
+        return y
+
     def spmm(indptr, indices, data, X, Y, shape):
         Y[:] = torch.from_numpy(orc.spmm(indptr.numpy(), indices.numpy(), data.numpy(), X.contiguous().numpy()))
         return Y
@@ -122,6 +126,7 @@ def install():
 
     _ops.coo_to_csr, _ops.csr_transpose = coo_to_csr, csr_transpose
     _ops.spmv_plan, _ops.spmv, _ops.spmm, _ops.dot, _ops.nrm2 = spmv_plan, spmv, spmm, dot, nrm2
+    _ops.spmv_add = spmv_add
     _ops.axpby, _ops.spmv_dot, _ops.cg_update_xr, _ops.csr_diagonal, _ops.spgemm = (axpby, spmv_dot, cg_update_xr,
                                                                                       csr_diagonal, spgemm)
     runtime.require_cuda = lambda what: None

@@ -55,6 +55,46 @@ def test_csr_dot(filename, mat_type, vec_type, col_split):
     assert (arr @ vec).shape == (arr.shape[0], 1)
 
 
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_column_split_product(oracle, dt):
+    """`spmv_domain_part=True` (reference csr.py:869-927, spmv.cu:125-153): x is partitioned into column blocks and the
+    partial products are reduced into y.  Same result as the row-split kernel (up to the order of the partial sums)
+    and as the oracle, for every block count, with empty blocks, empty rows, and after an in-place edit of .data."""
+    rng = np.random.default_rng(31)
+    nrows, ncols = 4001, 9000
+    lens = rng.integers(0, 40, nrows)
+    lens[100:200] = 0
+    ip, ix, dv = _random_csr(rng, nrows, ncols, lens, dt)
+    ix = np.where(np.arange(len(ix)) % 7 == 0, ix % 1000, ix)          # crowd some entries into the first block
+    order = np.lexsort((ix, np.repeat(np.arange(nrows), lens)))          # keep rows sorted by column
+    ix, dv = ix[order], dv[order]
+    A = sparse.csr_array((dv, ix, ip), shape=(nrows, ncols))
+    x = rng.random(ncols).astype(dt)
+    ref = oracle.spmv(ip, ix, dv, x)
+    absx = oracle.spmv(ip, ix, np.abs(dv), np.abs(x))
+    xd = torch.from_numpy(x).cuda()
+    y_row = (A @ xd).cpu().numpy()
+    y_col = A.dot(xd, spmv_domain_part=True).cpu().numpy()
+    assert _close_rowscaled(y_col, ref, absx, dt) and _close_rowscaled(y_col, y_row, absx, dt)
+    assert np.array_equal(A.dot(x, spmv_domain_part=True), y_col)        # host vectors take the same path
+    for nb in (1, 3, 9, 16):
+        y = torch.full((nrows,), 7.0, dtype=xd.dtype, device="cuda")
+        A._dot_col_split(xd, y, nblocks=nb)
+        assert _close_rowscaled(y.cpu().numpy(), ref, absx, dt)
+        assert len(A._col_split(nb)) <= nb
+    # all columns in the first of 4 blocks: three blocks are empty and skipped
+    B = sparse.csr_array((dv, ix % 2000, ip), shape=(nrows, ncols))
+    assert len(B._col_split(4)) == 1
+    yb = torch.empty(nrows, dtype=xd.dtype, device="cuda")
+    B._dot_col_split(xd, yb, nblocks=4)
+    assert _close_rowscaled(yb.cpu().numpy(), oracle.spmv(ip, ix % 2000, dv, x), absx, dt)
+    # in-place edit of the values: the cached blocks are rebuilt
+    A.data[:] = A.data * 2
+    assert _close_rowscaled(A.dot(xd, spmv_domain_part=True).cpu().numpy(), 2 * ref, 2 * absx, dt)
+    # the automatic choice: only scattered matrices whose x exceeds L2
+    assert not A._wants_col_split(A._get_plan())
+
+
 @pytest.mark.parametrize("key", [n.split(".")[0] for n in MTX_FILES])
 def test_golden_vectors(golden, oracle, key):
     A = sparse.csr_array((golden[f"{key}_data"], golden[f"{key}_indices"], golden[f"{key}_indptr"]),
