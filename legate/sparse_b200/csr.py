@@ -291,7 +291,11 @@ class csr_array:
         and cached.  The reference's column-split SpMV partitions x the same way and reduces the partial y with ADD."""
         n = self.shape[1]
         if nblocks is None:
-            nblocks = max(2, min(16, -(-n * self.dtype.itemsize // self._COL_BLOCK_BYTES)))
+            # scattered columns: one block per 40 MB of x (each block's slice stays in L2); otherwise the split is only
+            # the partitioning the caller asked for -- two blocks (GMG's restriction: 514 it/s unsplit, 490 with five
+            # blocks of a one-entry-per-row operator)
+            scattered = bool(getattr(self._get_plan(), "scattered", False))
+            nblocks = max(2, min(16, -(-n * self.dtype.itemsize // self._COL_BLOCK_BYTES))) if scattered else 2
         nblocks = max(1, min(int(nblocks), max(n, 1)))
         key = (self._indptr.data_ptr(), self._indices.data_ptr(), self._data.data_ptr(), self._data._version, self.nnz,
                nblocks)
