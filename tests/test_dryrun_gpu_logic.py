@@ -9,7 +9,7 @@ import pytest
 
 from conftest import ROOT
 
-FILES = ["test_gpu_zspmm.py", "test_gpu_zy_krylov.py", "test_gpu_zzassembly.py", "test_gpu_cg.py"]
+FILES = ["test_gpu_zspmm.py", "test_gpu_zy_krylov.py", "test_gpu_zzassembly.py", "test_gpu_cg.py", "test_gpu_spmv.py"]
 
 
 @pytest.mark.parametrize("name", FILES)
@@ -17,6 +17,8 @@ def test_gpu_test_file_passes_the_cpu_dry_run(name):
     extra = []
     if name == "test_gpu_zzassembly.py":
         extra = ["-k", "not spectral_norm"]        # that one launches the real example in a subprocess
+    if name == "test_gpu_spmv.py":
+        extra = ["-k", "column_split"]             # host logic of the column-split product (blocks, caches, empty blocks)
     if name == "test_gpu_cg.py":
         extra = ["-k", "not full_size"]            # BASELINE-size problems are for the GPU box (minutes of scipy here)
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "dryrun_cpu.py"), os.path.join(ROOT, "tests", name), *extra],
