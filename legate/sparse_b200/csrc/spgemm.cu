@@ -800,7 +800,8 @@ static int run_classes(int sm_count, const unsigned long long counts[16], const 
     if (ndense < slots) slots = ndense;
     if (slots < 1) { set_error("dense accumulator workspace too small"); return B2S_ENOMEM; }
     B2S_CUDA(cudaMemsetAsync(&hdr->ticket, 0, sizeof(unsigned long long), st));
-    const int l1_shared = L.bitmap_words1 <= 8192 ? 1 : 0;      // 32 KB of shared memory: n <= 8 M columns
+    int l1_shared = L.bitmap_words1 <= 8192 ? 1 : 0;            // 32 KB of shared memory: n <= 8 M columns
+    if (const char* e = getenv("B2S_SPGEMM_L1_GLOBAL")) { if (e[0] == '1') l1_shared = 0; }   // tests: the wide-matrix path
     const size_t l1_bytes = l1_shared ? sizeof(unsigned int) * (size_t)L.bitmap_words1 : 0;
     spgemm_dense_kernel<V, P, 256, NUMERIC><<<(unsigned)slots, 256, l1_bytes, st>>>(
         ndense, perm + offs.off[5], ap, a_idx, av, bp, b_idx, bv, c_ptr, c_idx, cv, bitmaps,

@@ -6,6 +6,7 @@ import numpy as np
 import pytest
 import scipy.io as sio
 import scipy.sparse as sp
+import torch
 
 from conftest import MTX_FILES, mtx_path
 
@@ -126,6 +127,22 @@ def _rmat(scale, ef, seed):
     A.sum_duplicates()
     A.sort_indices()
     return A
+
+
+def test_dense_rows_with_the_level1_bitmap_in_global_memory(monkeypatch):
+    """Matrices wider than 8 M columns keep the dense kernel's level-1 bitmap in global memory instead of shared
+    memory; B2S_SPGEMM_L1_GLOBAL=1 forces that path on a small power-law matrix.  Same structure and values as scipy."""
+    A = _rmat(13, 16, 7)
+    S = A @ A
+    G = sparse.csr_array(A)
+    monkeypatch.setenv("B2S_SPGEMM_L1_GLOBAL", "1")
+    C = G @ G
+    monkeypatch.delenv("B2S_SPGEMM_L1_GLOBAL")
+    _check_vs_scipy(C, S, 1e-12)
+    assert C.spgemm_info["dense_rows"] > 0
+    C2 = G @ G                                      # and the shared-memory variant gives the identical matrix
+    assert torch.equal(C.indptr, C2.indptr) and torch.equal(C.indices, C2.indices)
+    assert torch.allclose(C.data, C2.data, rtol=1e-12, atol=1e-12)   # atomics: the order of the partial sums is free
 
 
 @pytest.mark.parametrize("scale,ef", [(10, 8), (13, 16)])
