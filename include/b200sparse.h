@@ -147,14 +147,19 @@ int         b2s_spmv_csr_fused(int vt, int it, int pt, int64_t nrows, int64_t nc
                                const void* indptr, const void* indices, const void* vals,
                                const void* x, void* y, const void* w, void* dot_out, const void* plan,
                                void* ws, const b2s_fuse_desc* desc_host, void* stream);
-/* y += A x (needs a TMA tile plan): one column block of a column-blocked shard at a time */
+/* y += A x (needs a TMA tile plan): one column block at a time -- the reduction step of the column-split SpMV (reference
+ * sparse/csr.py:869-927, spmv_col_split_kernel src/sparse/array/csr/spmv.cu:125-153: x partitioned by columns, partial
+ * products summed into y) and of the column-blocked shards of the multi-GPU all-gather exchange */
 int         b2s_spmv_csr_add(int vt, int it, int pt, int64_t nrows, int64_t ncols, int64_t nnz,
                              const void* indptr, const void* indices, const void* vals,
                              const void* x, void* y, const void* plan, void* stream);
 
 /* y_host = A x_host for HOST vectors (the matrix stays resident): pipelined H2D / tiles / D2H over the plan's
- * chunks on internal copy streams; x_dev / y_dev are caller-owned device scratch (ncols / nrows elements).
- * Pinned host memory gives true overlap.  syncs: y_host is complete on return. */
+ * chunks on internal copy streams (9 stages of 1-2-..-2-1 sixteenths, copy boundaries on 4 KB multiples);
+ * x_dev / y_dev are caller-owned device scratch (ncols / nrows elements).  Pinned host memory gives true overlap.
+ * Environment (read per call): B2S_PIPE_CHUNKS=n equal stages, B2S_PIPE_PATTERN="a,b,.." chunks per stage (sum 16),
+ * B2S_PIPE_ALIGN=elements, B2S_PIPE_DIRECT=1 (tiles store y straight into mapped pinned memory), B2S_PIPE_TRACE=1.
+ * syncs: y_host is complete on return. */
 int         b2s_spmv_csr_host(int vt, int it, int pt, int64_t nrows, int64_t ncols, int64_t nnz,
                               const void* indptr, const void* indices, const void* vals,
                               const void* x_host, void* y_host, void* x_dev, void* y_dev,
@@ -209,8 +214,8 @@ int         b2s_csr_diagonal(int vt, int it, int pt, int64_t nrows, const void* 
  *      spgemm_csr_csr_csr.cc:26-154).  C[m,n] = A[m,k] * B[k,n].  int32 column indices.
  * Pass 1 (symbolic): c_indptr[m+1] (int64) = exclusive scan of per-row structural nnz.
  *   info_host[0] = nnz(C), info_host[1] = number of A*B products ("flops/2"),
- *   info_host[2] = rows whose nnz exceeds the largest shared-memory table (they need the
- *   dense accumulator in pass 2; size it with b2s_spgemm_dense_bytes).  syncs the stream
+ *   info_host[2] = rows with more than 1024 entries, i.e. beyond the 2048-entry shared-memory table (they take
+ *   the dense accumulator in pass 2; size it with b2s_spgemm_dense_bytes).  syncs the stream
  *   (the reference also blocks here: sparse/csr.py:1442 `int(nnz)`).
  * Pass 2 (numeric): fills c_indices (int32) / c_vals; rows come out SORTED by column
  *   (canonical form; reference/scipy rows are unsorted, compare after sort_indices()).
