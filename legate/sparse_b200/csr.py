@@ -347,7 +347,18 @@ class csr_array:
         if not getattr(plan, "scattered", False) or xbytes <= (48 << 20):
             return False
         nblocks = -(-xbytes // self._COL_BLOCK_BYTES)
-        return self.nnz >= 4 * nblocks * max(self.shape[0], 1)
+        if self.nnz < 4 * nblocks * max(self.shape[0], 1):
+            return False
+        if "_colsplit" in self.__dict__:
+            return True
+        # the blocks are a second copy of the matrix (+ one indptr per block, + transient masks while they are cut):
+        # only when that fits comfortably in what the device has free
+        need = self.nnz * (self.dtype.itemsize + 4 + 9) + nblocks * (self.shape[0] + 1) * 16
+        try:
+            free, _total = torch.cuda.mem_get_info(self.device)
+        except Exception:  # pragma: no cover - no usable device query: keep the unsplit product
+            return False
+        return need < 0.6 * free
 
     def _promoted(self, common):
         """A cast to the resolved dtype of (A, x) -- reference cast_to_common_type, csr.py:493 -- cached
