@@ -600,7 +600,7 @@ spgemm_dense_kernel(int64_t count, const int32_t* __restrict__ perm, const P* __
         if (NUMERIC) n_av = a_val[base + THREADS + tid];
       }
       // U consecutive products per thread and round: one owner search, then a short walk; the U column (and value) loads
-      // are all issued before anything else touches memory, and no atomic returns a value (RED.OR / RED.ADD: nothing
+      // are all issued before anything else touches memory, and no atomic returns a value (SASS: ATOMG.OR / ATOMG.ADD.F64 with destination RZ: nothing
       // waits for L2).  ncu of the first version -- one product per iteration, atomics with return values, level 1 in
       // global memory (R-MAT 18, profiles/r02_spgemm_dense_*): issue slots 12 %, 22..85 cycles of long-scoreboard stall
       // per instruction, 0.07..0.13 eligible warps per cycle: pure latency.
